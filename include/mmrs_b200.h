@@ -1,0 +1,221 @@
+/* ============================================================================
+ * mmrs_b200.h — C ABI of the B200-native Hausdorff rotation-sweep library
+ * (libmmrs_b200.so, built from multimoda-rs_b200/csrc/).
+ *
+ * This is the drop-in boundary for ONE path of yungselm/multimoda-rs v0.7.0:
+ * the brute-force / coarse-to-fine rotation sweep scored by symmetric 2-D
+ * Hausdorff distance. Every entry point cites the reference interface it
+ * replaces (paths relative to the reference checkout root). Plain pointers and
+ * sizes only; no C++ / torch types. All host arrays are caller-owned; the
+ * opaque context owns device workspaces. Functions return 0 on success and a
+ * non-zero status otherwise; mmrs_last_error() gives the message (the
+ * reference surfaces anyhow::Error chains as PyRuntimeError,
+ * src/intravascular/binding/functions.rs:228).
+ *
+ * There is NO CPU fallback: every compute entry point fails with
+ * MMRS_ERR_CUDA when no CUDA device / sm_100a image is available.
+ * ========================================================================== */
+#ifndef MMRS_B200_H
+#define MMRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMRS_OK 0
+#define MMRS_ERR_ARG 1    /* invalid argument                                  */
+#define MMRS_ERR_CUDA 2   /* CUDA runtime / no device / wrong architecture     */
+#define MMRS_ERR_INPUT 3  /* reference-style input error (anyhow! in the ref)  */
+#define MMRS_ERR_STATE 4  /* call order (e.g. run before upload)               */
+
+typedef struct mmrs_ctx mmrs_ctx;
+
+/* ---- context ------------------------------------------------------------- */
+/* `stream` is a cudaStream_t the library launches on (so the caller's CUDA
+ * events see the kernels); NULL = the library creates its own stream.        */
+int mmrs_ctx_create(int device, void* stream, mmrs_ctx** out);
+void mmrs_ctx_destroy(mmrs_ctx* ctx);
+/* Message of the last failing call on `ctx` (or of the last failing call that
+ * had no context when ctx == NULL). Never NULL.                               */
+const char* mmrs_last_error(const mmrs_ctx* ctx);
+const char* mmrs_version(void);
+
+/* ---- candidate grid ----------------------------------------------------------
+ * Replaces the grid construction inside `search_range`
+ * (src/intravascular/processing/process_utils.rs:43-67): start/stop clipped to
+ * +-limes, steps = max(ceil((stop-start)/step) as usize, 1), candidates
+ * start + i*step while <= stop, each wrapped to [-pi, pi).
+ * degenerate != 0  <=>  search_range returns `fallback` without evaluating.   */
+typedef struct mmrs_grid {
+    double start_rad;
+    double step_rad;
+    int64_t n_cand;
+    int32_t degenerate;
+    double fallback;
+} mmrs_grid;
+
+int mmrs_grid_from_reference_params(double step_deg, double range_deg, int has_center, double center_rad,
+                                    double limes_deg, mmrs_grid* out);
+/* Wrapped candidate angle i: ((start + i*step + pi).rem_euclid(2pi)) - pi.    */
+double mmrs_grid_angle(const mmrs_grid* g, int64_t i);
+
+/* The stage plan of the coarse-to-fine driver `find_best_rotation`
+ * (src/intravascular/processing/align_within.rs:208-246, identical copy in
+ * align_between.rs:219-257). Writes up to 4 (step_deg, half_window_deg) pairs;
+ * stage 0 is centred on 0 (None), stage k>0 on the result of stage k-1; every
+ * stage is clipped to +-range_deg. Returns the number of stages.              */
+int mmrs_stage_plan(double step_deg, double range_deg, double step_out[4], double window_out[4]);
+
+/* ---- batched sweep -------------------------------------------------------------
+ * One "unit" = one `search_range` call with the Hausdorff cost closure:
+ *   mode 0: intrapullback closure, align_within.rs:99-105 / :200-206
+ *           (ContourPoint::rotate about `centre`, identity iff angle == 0.0,
+ *            src/types/native/contour_point.rs:38-52)
+ *   mode 1: inter-pullback closure, align_between.rs:189-216 (no shortcut;
+ *           `centre` = the reference cloud's mean, align_between.rs:260-271)
+ * followed by `hausdorff_distance(reference, rotated)`
+ * (process_utils.rs:78-121) and the leftmost arg-min of process_utils.rs:69-74.
+ *
+ * Points are packed (x, y) doubles, units concatenated; unit u owns
+ * test_xy[2*test_off[u] .. 2*test_off[u+1]) and likewise for ref.
+ * `grid_of_unit` == NULL: every unit uses grids[0] (the brute-force case).    */
+typedef struct mmrs_sweep_batch {
+    int64_t n_units;
+    const double* test_xy;
+    const int64_t* test_off; /* [n_units + 1] */
+    const double* ref_xy;
+    const int64_t* ref_off;  /* [n_units + 1] */
+    const double* centre_xy; /* [n_units][2]  */
+    const mmrs_grid* grids;
+    int64_t n_grids;
+    const int32_t* grid_of_unit; /* [n_units] or NULL */
+    int32_t mode;
+} mmrs_sweep_batch;
+
+typedef struct mmrs_sweep_opts {
+    /* FP32 filter -> f64 exact recheck. A candidate is rechecked in the
+     * reference's f64 arithmetic when its FP32 distance is <=
+     * d32_min * (1 + shortlist_rel) + shortlist_abs * Rmax, Rmax being the
+     * unit's largest centred coordinate magnitude. <= 0 selects the defaults
+     * (2e-6 and 2e-6, twice the analysed FP32 error bound).    */
+    double shortlist_rel;
+    double shortlist_abs;
+    int32_t shortlist_cap; /* per unit; <= 0 selects 64. Overflow => the unit is
+                              rechecked over ALL its candidates in f64.        */
+    /* n_ties = number of rechecked candidates whose f64 distance is
+     * <= best + tie_margin * max(1, Rmax). 0 = exact ties only.               */
+    double tie_margin;
+    int32_t keep_dist32; /* != 0: keep the FP32 distance of every candidate for
+                            mmrs_sweep_get_dist32 (tests, diagnostics).        */
+} mmrs_sweep_opts;
+
+#define MMRS_FLAG_DEGENERATE 1 /* grid degenerate: best_angle = fallback, nothing evaluated */
+#define MMRS_FLAG_FULL_F64 2   /* shortlist overflowed: all candidates rechecked in f64     */
+#define MMRS_FLAG_EMPTY 4      /* empty point set: every candidate costs 0.0 (ref :86-88)   */
+
+typedef struct mmrs_unit_result {
+    int64_t best_idx;     /* leftmost arg-min in f64 (reference semantics); -1 if degenerate */
+    double best_angle;    /* wrapped angle of best_idx (what search_range returns)           */
+    double best_dist;     /* f64 Hausdorff distance at best_idx, reference arithmetic        */
+    float best_dist_f32;  /* FP32 sweep minimum (before the recheck)                         */
+    int32_t n_shortlist;  /* candidates rechecked in f64                                     */
+    int32_t n_ties;       /* rechecked candidates within tie_margin of best (>= 1)           */
+    int32_t flags;
+} mmrs_unit_result;
+
+/* Host buffers in, host results out: H2D, sweep, recheck, arg-min, D2H.      */
+int mmrs_sweep_batched(mmrs_ctx* ctx, const mmrs_sweep_batch* batch, const mmrs_sweep_opts* opts,
+                       mmrs_unit_result* out /* [n_units] */);
+
+/* The same in three steps, so a caller can keep inputs resident in HBM:
+ * upload (H2D + layout), run (all kernels; results stay on the device),
+ * download (D2H of the n_units results).                                     */
+int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* batch, const mmrs_sweep_opts* opts);
+int mmrs_sweep_run(mmrs_ctx* ctx);
+int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out);
+
+/* Diagnostics on the last run (valid until the next upload).                 */
+/* FP32 distance of every candidate of `unit` (needs opts.keep_dist32).       */
+int mmrs_sweep_get_dist32(mmrs_ctx* ctx, int64_t unit, float* out, int64_t cap);
+/* Rechecked candidates of `unit`: indices and their f64 distances.           */
+int mmrs_sweep_get_shortlist(mmrs_ctx* ctx, int64_t unit, int64_t* idx_out, double* dist_out, int32_t cap,
+                             int32_t* n_out);
+/* Device time of the last run in ms: [0] FP32 sweep kernel, [1] shortlist,
+ * [2] f64 recheck + select, [3] whole run. Kernel launches of the last run.   */
+int mmrs_last_timings(mmrs_ctx* ctx, float ms_out[4], int32_t* launches_out);
+
+/* Reference-arithmetic f64 cost of an explicit list of angles for one unit
+ * (the cost closure itself; used by the host to resolve tie sets on the
+ * sequential frame chain).                                                   */
+int mmrs_eval_exact(mmrs_ctx* ctx, const double* test_xy, int64_t n_test, const double* ref_xy, int64_t n_ref,
+                    double cx, double cy, int32_t mode, const double* angles, int64_t n_angles, double* dist_out);
+
+/* Pure-FFMA FP32 throughput probe (denominator check for the roofline): runs
+ * `iters` dependent FFMA chains on every SM, returns achieved TFLOP/s.        */
+int mmrs_fp32_probe(mmrs_ctx* ctx, int32_t iters, double* tflops_out);
+
+/* ---- geometry blob -------------------------------------------------------------
+ * Geometries cross the boundary as one f64 stream (u32 ids are exact in f64):
+ *   n_frames,
+ *   per frame : id, cx, cy, cz, has_ref, ref{frame_index, point_index, x, y, z, aortic}, n_contours,
+ *     per contour (lumen first, then extras by kind):
+ *       kind, id, original_frame, has_centroid, cx, cy, cz,
+ *       has_aortic_thickness, aortic_thickness, has_pulmonary_thickness, pulmonary_thickness, n_points,
+ *       per point: frame_index, point_index, x, y, z, aortic
+ * kind: 0 Lumen, 1 Eem, 2 Calcification, 3 Sidebranch, 4 Catheter, 5 Wall
+ * (src/types/native/contour.rs:8-16). Mirrors Geometry/Frame/Contour/
+ * ContourPoint of src/types/native/{geometry,frame,contour,contour_point}.rs.
+ * Blobs returned by the library are malloc'ed; release with mmrs_free.        */
+void mmrs_free(void* p);
+
+/* AlignLog rows (align_within.rs:14-22 as emitted by logs_to_tuples,
+ * binding/functions.rs:26-40): n x 7 doubles
+ * (contour_id, matched_to, rot_deg, tx, ty, centroid_x, centroid_y).          */
+
+/* Replaces `build_geometry_from_inputdata` (src/intravascular/io/build.rs:9-205)
+ * for a directory (io/input.rs:62-147) ...                                    */
+int mmrs_geometry_from_dir(mmrs_ctx* ctx, const char* path, const char* label, int diastole, double image_cx,
+                           double image_cy, double radius, uint32_t n_points, double** blob_out, int64_t* len_out);
+/* ... and for in-memory (N,4) [frame, x, y, z] arrays (PyInputData,
+ * src/types/binding/py_input_data.rs:103-172). records: (R,4)
+ * [frame, is_diastole, measurement_1, measurement_2], NaN = missing; any array
+ * pointer may be NULL except lumen and ref_point[4].                          */
+int mmrs_geometry_from_arrays(mmrs_ctx* ctx, const double* lumen, int64_t n_lumen, const double* eem, int64_t n_eem,
+                              const double* calc, int64_t n_calc, const double* side, int64_t n_side,
+                              const double* records, int64_t n_rec, const double* ref_point, int diastole,
+                              const char* label, double image_cx, double image_cy, double radius, uint32_t n_points,
+                              double** blob_out, int64_t* len_out);
+
+typedef struct mmrs_align_params {
+    double step_deg;      /* step_rotation_deg  */
+    double range_deg;     /* range_rotation_deg */
+    int64_t sample_size;
+    int32_t smooth;
+    int32_t bruteforce;
+} mmrs_align_params;
+
+/* Replaces the *_processing_rs orchestration of
+ * src/intravascular/binding/entry.rs for a batch of `n_cases` independent
+ * cases (patients): mode 4 = full_processing_rs (:71-361), 3 =
+ * double_pair_processing_rs (:363-570), 2 = pair_processing_rs (:572-689),
+ * 1 = single_processing_rs (:691-780); each with postprocessing = false and
+ * write_obj = false (both out of scope). Input: n_cases *
+ * n_in(mode) geometry blobs (n_in = 4,4,2,1). Output: n_cases * n_out(mode)
+ * blobs (8,4,2,1: pair ab = (a,b), cd, ac, bd) and n_cases * n_in log arrays.
+ * All intrapullback sweeps of all cases run as ONE batch per search stage, all
+ * inter-pullback sweeps of a dependency level likewise.                       */
+int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, const double* const* blobs,
+                       const int64_t* blob_lens, const mmrs_align_params* params, double** out_blobs,
+                       int64_t* out_lens, double** out_logs, int64_t* out_nlogs, int32_t* out_anomalous);
+
+/* Counters of the last mmrs_process_cases call: [0] units swept, [1] candidate
+ * evaluations (FP32), [2] f64 rechecks, [3] units resolved on the sequential
+ * chain (tie sets), [4] kernel launches.                                      */
+int mmrs_process_stats(mmrs_ctx* ctx, int64_t stats_out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMRS_B200_H */

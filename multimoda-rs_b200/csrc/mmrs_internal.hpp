@@ -1,0 +1,89 @@
+// mmrs_internal.hpp — private state behind the opaque mmrs_ctx of include/mmrs_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mmrs_b200.h"
+
+namespace mmrs {
+struct UnitDesc {
+    long long test_off, ref_off;  // point offsets into the f64 (x,y) arrays
+    int n, m;                     // test / reference point counts
+    double cx, cy;                // rotation centre
+    long long lay_off;            // float4 offset of this unit's staging block (A then B)
+    int n_chunks;                 // A is stored as n_chunks x (TA/2) x 32 float4
+    int m_pairs;                  // B is stored as 2*m_pairs float4 (bx,bx,by,by)
+    long long cand_off;           // offset of this unit's grid in the cos/sin tables
+    int n_cand;
+    int flags;
+    long long dist_off;           // offset of this unit's first candidate in dist32
+};
+
+struct WorkItem {
+    int unit;
+    int begin;  // first candidate
+    int count;  // candidates in this tile
+    int pad;
+};
+
+struct UnitResultDev {
+    long long best_idx;
+    double best_dist;
+    float best_d32;
+    int n_shortlist;
+    int n_ties;
+    int flags;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+int set_err(mmrs_ctx* ctx, int code, const std::string& msg);
+}  // namespace mmrs
+
+struct mmrs_ctx {
+    int device = 0;
+    int n_sm = 148;
+    int sm_clock_khz = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // batch state
+    bool ready = false, ran = false;
+    int64_t n_units = 0;
+    int mode = 0;
+    int TA = 2;
+    bool multi = false;
+    int max_pts = 1;
+    size_t smem_sweep = 0;
+    long long total_cands = 0;
+    double opt_rel = 2e-6, opt_abs = 2e-6, tie_margin = 0.0;
+    int cap = 64;
+    int launches = 0, upload_launches = 0;
+    long long eval_launches = 0;
+    std::vector<mmrs_grid> grids;
+    std::vector<int> grid_of_unit;
+    std::vector<mmrs::UnitDesc> h_units;
+    std::vector<mmrs::WorkItem> h_work;
+    std::vector<double> h_cs;
+    std::vector<unsigned char> h_zero;
+    std::vector<float> h_rmax;
+    std::map<int64_t, std::vector<double>> overflow_dist;
+    void* h_res = nullptr;  // pinned
+    size_t h_res_cap = 0;
+
+    mmrs::DevBuf d_test, d_ref, d_units, d_work, d_lay, d_cs64, d_cs32, d_zero, d_dist32, d_key, d_rmax, d_sl_idx,
+        d_sl_dist, d_sl_count, d_items, d_nitems, d_res, d_tmp;
+
+    // counters of the last mmrs_process_cases call
+    int64_t stats[5] = {0, 0, 0, 0, 0};
+
+    void free_all();
+};

@@ -1,0 +1,699 @@
+// =============================================================================
+// mmrs_sweep.cu — context, device workspaces and the sweep entry points of the
+// C ABI declared in include/mmrs_b200.h. No CPU fallback: every compute entry
+// point needs a CUDA device that can run the sm_100a image.
+// =============================================================================
+#include "mmrs_internal.hpp"
+#include "sweep_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mmrs;
+
+static thread_local std::string g_err_noctx = "";
+
+#define CUDA_TRY(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            return set_err(ctx, MMRS_ERR_CUDA,                                                    \
+                           std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                               std::to_string(__LINE__) + ")");                                   \
+        }                                                                                         \
+    } while (0)
+
+int mmrs::set_err(mmrs_ctx* ctx, int code, const std::string& msg) {
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_err_noctx = msg;
+    return code;
+}
+
+// ---- reference grid arithmetic (process_utils.rs:43-67) -------------------------
+static const double kPi = 3.14159265358979323846264338327950288;
+static inline double to_radians(double d) { return d * (kPi / 180.0); }
+static inline double rem_euclid(double a, double b) {
+    double r = std::fmod(a, b);
+    return (r < 0.0) ? r + std::fabs(b) : r;
+}
+static inline uint64_t f64_as_usize(double v) {
+    if (!(v == v) || v <= 0.0) return 0;
+    if (v >= 18446744073709551615.0) return ~0ull;
+    return (uint64_t)v;
+}
+
+extern "C" int mmrs_grid_from_reference_params(double step_deg, double range_deg, int has_center, double center_rad,
+                                               double limes_deg, mmrs_grid* out) {
+    if (!out) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_grid_from_reference_params: out is NULL");
+    mmrs_grid g{};
+    const double range_rad = to_radians(range_deg), step_rad = to_radians(step_deg);
+    const double center = has_center ? center_rad : 0.0;
+    g.step_rad = step_rad;
+    g.fallback = center;
+    if (step_rad <= 0.0) {
+        g.degenerate = 1;
+        *out = g;
+        return MMRS_OK;
+    }
+    const double limes = to_radians(limes_deg);
+    const double start = std::fmax(center - range_rad, -limes);
+    const double stop = std::fmin(center + range_rad, limes);
+    g.start_rad = start;
+    if (stop <= start) {
+        g.degenerate = 1;
+        *out = g;
+        return MMRS_OK;
+    }
+    uint64_t steps = std::max<uint64_t>(f64_as_usize(std::ceil((stop - start) / step_rad)), 1);
+    if (steps > (1ull << 31) - 2) return set_err(nullptr, MMRS_ERR_ARG, "grid has more than 2^31 candidates");
+    // take_while(a <= stop): candidates are increasing in i, so the count is the first failing i.
+    int64_t n = 0;
+    for (uint64_t i = 0; i <= steps; ++i) {
+        const double a = start + (double)i * step_rad;
+        if (!(a <= stop)) break;
+        ++n;
+    }
+    g.n_cand = n;
+    if (n == 0) g.degenerate = 1;  // .unwrap_or(center)
+    *out = g;
+    return MMRS_OK;
+}
+
+extern "C" double mmrs_grid_angle(const mmrs_grid* g, int64_t i) {
+    const double a = g->start_rad + (double)i * g->step_rad;
+    return rem_euclid(a + kPi, 2.0 * kPi) - kPi;
+}
+
+extern "C" int mmrs_stage_plan(double step_deg, double range_deg, double step_out[4], double window_out[4]) {
+    // align_within.rs:208-246 match arms: 1.0..=INF | 0.1..1.0 | 0.01..0.1 | _
+    const double r5 = (range_deg > 5.0) ? 5.0 : range_deg;
+    const double r10s = (range_deg > 10.0 * step_deg) ? 10.0 * step_deg : range_deg;
+    if (step_deg >= 1.0) {
+        step_out[0] = step_deg, window_out[0] = range_deg;
+        return 1;
+    }
+    step_out[0] = 1.0, window_out[0] = range_deg;
+    if (step_deg >= 0.1 && step_deg < 1.0) {
+        step_out[1] = step_deg, window_out[1] = r5;
+        return 2;
+    }
+    step_out[1] = 0.1, window_out[1] = r5;
+    if (step_deg >= 0.01 && step_deg < 0.1) {
+        step_out[2] = step_deg, window_out[2] = r10s;
+        return 3;
+    }
+    step_out[2] = 0.01, window_out[2] = (range_deg > 0.1) ? 0.1 : range_deg;
+    step_out[3] = step_deg, window_out[3] = r10s;
+    return 4;
+}
+
+// ---- context -----------------------------------------------------------------------
+extern "C" const char* mmrs_version(void) { return "mmrs_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char* mmrs_last_error(const mmrs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err_noctx.c_str(); }
+
+extern "C" int mmrs_ctx_create(int device, void* stream, mmrs_ctx** out) {
+    if (!out) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(nullptr, MMRS_ERR_CUDA,
+                       std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                           "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_ctx_create: bad device index");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return set_err(nullptr, MMRS_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return set_err(nullptr, MMRS_ERR_CUDA,
+                       "device compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor) +
+                           " cannot run the sm_100a image (B200 required); no fallback path exists");
+    mmrs_ctx* ctx = new mmrs_ctx();
+    ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->sm_clock_khz = prop.clockRate;
+    cudaSetDevice(device);
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->own_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return set_err(nullptr, MMRS_ERR_CUDA, cudaGetErrorString(e));
+        }
+        ctx->own_stream = true;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return MMRS_OK;
+}
+
+extern "C" void mmrs_ctx_destroy(mmrs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->free_all();
+    for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void mmrs_ctx::free_all() {
+    for (DevBuf* b : {&d_test, &d_ref, &d_units, &d_work, &d_lay, &d_cs64, &d_cs32, &d_zero, &d_dist32, &d_key,
+                      &d_rmax, &d_sl_idx, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp}) {
+        if (b->p) cudaFree(b->p);
+        b->p = nullptr;
+        b->cap = 0;
+    }
+    if (h_res) cudaFreeHost(h_res);
+    h_res = nullptr;
+    h_res_cap = 0;
+}
+
+static int ensure(mmrs_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return MMRS_OK;
+    if (b.p) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return MMRS_OK;
+}
+#define ENSURE(buf, bytes)                                 \
+    do {                                                   \
+        int _r = ensure(ctx, buf, (size_t)(bytes));        \
+        if (_r != MMRS_OK) return _r;                      \
+    } while (0)
+
+// ---- kernel dispatch over TA ----------------------------------------------------------
+template <int TA>
+static void launch_sweep_ta(bool multi, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
+                            const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
+                            unsigned long long* key) {
+    if (multi) {
+        cudaFuncSetAttribute(k_sweep<TA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_sweep<TA, true><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key);
+    } else {
+        cudaFuncSetAttribute(k_sweep<TA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_sweep<TA, false><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key);
+    }
+}
+static bool launch_sweep(int TA, bool multi, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
+                         const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
+                         unsigned long long* key) {
+    switch (TA) {
+#define CASE(T)                                                                     \
+    case T:                                                                         \
+        launch_sweep_ta<T>(multi, grid, smem, s, units, work, lay, cs32, dist32, key); \
+        return true;
+        CASE(2) CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(14) CASE(16) CASE(18)
+#undef CASE
+    }
+    return false;
+}
+
+// Choose the register tile: TA even in [2,18] minimising the padded work
+// sum_u ceil(n_u / (32 TA)) * 32 TA, ties -> larger TA (fewer chunks).
+static int choose_ta(const std::vector<int>& ns) {
+    int best_ta = 2;
+    double best_cost = 1e300;
+    for (int ta = 2; ta <= 18; ta += 2) {
+        double cost = 0;
+        for (int n : ns) {
+            if (n <= 0) continue;
+            const int per = 32 * ta;
+            const int chunks = (n + per - 1) / per;
+            // a chunk loop adds ~5% per extra chunk (column minima go through shared memory)
+            cost += (double)chunks * per * (chunks > 1 ? 1.05 : 1.0);
+        }
+        if (cost <= best_cost) {
+            best_cost = cost;
+            best_ta = ta;
+        }
+    }
+    return best_ta;
+}
+
+// ---- upload ----------------------------------------------------------------------------
+extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const mmrs_sweep_opts* o) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_sweep_upload: ctx is NULL");
+    if (!b || b->n_units < 0 || (b->n_units > 0 && (!b->test_off || !b->ref_off || !b->centre_xy || !b->grids)) ||
+        b->n_grids < 1 && b->n_units > 0)
+        return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: bad batch");
+    if (b->mode != 0 && b->mode != 1) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: mode must be 0 or 1");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->ready = false;
+    const int64_t U = b->n_units;
+    ctx->n_units = U;
+    ctx->mode = b->mode;
+    ctx->opt_rel = (o && o->shortlist_rel > 0) ? o->shortlist_rel : 2e-6;
+    ctx->opt_abs = (o && o->shortlist_abs > 0) ? o->shortlist_abs : 2e-6;
+    ctx->cap = (o && o->shortlist_cap > 0) ? o->shortlist_cap : 64;
+    ctx->tie_margin = (o && o->tie_margin > 0) ? o->tie_margin : 0.0;
+    ctx->grids.assign(b->grids, b->grids + (U > 0 ? b->n_grids : 0));
+    ctx->grid_of_unit.resize(U);
+    for (int64_t u = 0; u < U; ++u) {
+        int g = b->grid_of_unit ? b->grid_of_unit[u] : 0;
+        if (g < 0 || g >= b->n_grids) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: grid_of_unit out of range");
+        ctx->grid_of_unit[u] = g;
+    }
+    if (U == 0) {
+        ctx->ready = true;
+        ctx->total_cands = 0;
+        return MMRS_OK;
+    }
+    // cos/sin tables: HOST glibc (bit-identical to Rust's f64::sin/cos), one per grid.
+    std::vector<long long> grid_off(b->n_grids + 1, 0);
+    for (int64_t g = 0; g < b->n_grids; ++g) {
+        const mmrs_grid& gr = b->grids[g];
+        if (gr.n_cand < 0 || gr.n_cand > (1ll << 31) - 2) return set_err(ctx, MMRS_ERR_ARG, "grid: bad n_cand");
+        grid_off[g + 1] = grid_off[g] + (gr.degenerate ? 0 : gr.n_cand);
+    }
+    const long long n_cs = grid_off[b->n_grids];
+    ctx->h_cs.resize(2 * (size_t)n_cs);
+    ctx->h_zero.resize((size_t)n_cs);
+    for (int64_t g = 0; g < b->n_grids; ++g) {
+        const mmrs_grid& gr = b->grids[g];
+        if (gr.degenerate) continue;
+        for (int64_t i = 0; i < gr.n_cand; ++i) {
+            const double a = mmrs_grid_angle(&gr, i);
+            ctx->h_cs[2 * (grid_off[g] + i)] = std::cos(a);
+            ctx->h_cs[2 * (grid_off[g] + i) + 1] = std::sin(a);
+            ctx->h_zero[grid_off[g] + i] = (b->mode == 0 && a == 0.0) ? 1 : 0;
+        }
+    }
+    // unit descriptors
+    std::vector<int> ns(U);
+    int max_n = 1, max_m = 1;
+    for (int64_t u = 0; u < U; ++u) {
+        const int64_t n = b->test_off[u + 1] - b->test_off[u], m = b->ref_off[u + 1] - b->ref_off[u];
+        if (n < 0 || m < 0 || n > (1 << 24) || m > (1 << 24)) return set_err(ctx, MMRS_ERR_ARG, "bad point offsets");
+        ns[u] = (int)n;
+        max_n = std::max(max_n, (int)n);
+        max_m = std::max(max_m, (int)m);
+    }
+    const int TA = choose_ta(ns);
+    ctx->TA = TA;
+    ctx->max_pts = std::max(max_n, max_m);
+    std::vector<UnitDesc>& units = ctx->h_units;
+    units.assign(U, UnitDesc{});
+    long long lay_off = 0, dist_off = 0;
+    bool multi = false;
+    size_t smem_max = 0;
+    for (int64_t u = 0; u < U; ++u) {
+        UnitDesc& d = units[u];
+        d.test_off = b->test_off[u];
+        d.ref_off = b->ref_off[u];
+        d.n = ns[u];
+        d.m = (int)(b->ref_off[u + 1] - b->ref_off[u]);
+        d.cx = b->centre_xy[2 * u];
+        d.cy = b->centre_xy[2 * u + 1];
+        const mmrs_grid& gr = b->grids[ctx->grid_of_unit[u]];
+        d.cand_off = grid_off[ctx->grid_of_unit[u]];
+        d.n_cand = gr.degenerate ? 0 : (int)gr.n_cand;
+        d.flags = 0;
+        if (gr.degenerate) d.flags |= MMRS_FLAG_DEGENERATE;
+        if (d.n == 0 || d.m == 0) d.flags |= MMRS_FLAG_EMPTY;
+        d.dist_off = dist_off;
+        dist_off += d.n_cand;
+        d.lay_off = lay_off;
+        if (d.n > 0 && d.m > 0) {
+            d.n_chunks = (d.n + 32 * TA - 1) / (32 * TA);
+            d.m_pairs = (d.m + 1) / 2;
+            const long long a_elems = (long long)d.n_chunks * (TA / 2) * 32, b_elems = 2ll * d.m_pairs;
+            lay_off += a_elems + b_elems;
+            if (d.n_chunks > 1) multi = true;
+            smem_max = std::max(smem_max, (size_t)(a_elems + b_elems) * 16);
+        }
+    }
+    ctx->multi = multi;
+    size_t col_bytes = 0;
+    if (multi) {
+        int max_pairs = 0;
+        for (auto& d : units) max_pairs = std::max(max_pairs, d.m_pairs);
+        col_bytes = (size_t)kWarpsPerCta * 2 * max_pairs * 4;
+    }
+    ctx->smem_sweep = 16 + smem_max + col_bytes;
+    if (ctx->smem_sweep > 227 * 1024)
+        return set_err(ctx, MMRS_ERR_ARG,
+                       "unit too large for the shared-memory staging of the sweep kernel (" +
+                           std::to_string(ctx->smem_sweep) + " B > 227 KB)");
+    ctx->total_cands = dist_off;
+    // work list: one CTA = one unit x one tile of candidates (8 warps, one candidate per warp per pass)
+    {
+        long long live = 0;
+        for (auto& d : units)
+            if (!(d.flags & (MMRS_FLAG_EMPTY | MMRS_FLAG_DEGENERATE))) live += d.n_cand;
+        const long long slots = (long long)ctx->n_sm * 2 * 4;  // CTAs for ~4 waves at 2 CTAs/SM
+        long long per_warp = (live + slots * kWarpsPerCta - 1) / (slots * kWarpsPerCta);
+        per_warp = std::max<long long>(1, std::min<long long>(per_warp, 8));
+        const int tile = (int)per_warp * kWarpsPerCta;
+        ctx->h_work.clear();
+        for (int64_t u = 0; u < U; ++u) {
+            const UnitDesc& d = units[u];
+            if (d.flags & (MMRS_FLAG_EMPTY | MMRS_FLAG_DEGENERATE)) continue;
+            for (int c0 = 0; c0 < d.n_cand; c0 += tile)
+                ctx->h_work.push_back(WorkItem{(int)u, c0, std::min(tile, d.n_cand - c0), 0});
+        }
+    }
+    const size_t n_test = (size_t)b->test_off[U], n_ref = (size_t)b->ref_off[U];
+    if ((n_test && !b->test_xy) || (n_ref && !b->ref_xy)) return set_err(ctx, MMRS_ERR_ARG, "point arrays are NULL");
+    ENSURE(ctx->d_test, n_test * 16);
+    ENSURE(ctx->d_ref, n_ref * 16);
+    ENSURE(ctx->d_units, U * sizeof(UnitDesc));
+    ENSURE(ctx->d_work, ctx->h_work.size() * sizeof(WorkItem));
+    ENSURE(ctx->d_lay, (size_t)lay_off * 16);
+    ENSURE(ctx->d_cs64, (size_t)n_cs * 16);
+    ENSURE(ctx->d_cs32, (size_t)n_cs * 8);
+    ENSURE(ctx->d_zero, (size_t)n_cs);
+    ENSURE(ctx->d_dist32, (size_t)dist_off * 4);
+    ENSURE(ctx->d_key, U * 8);
+    ENSURE(ctx->d_rmax, U * 4);
+    ENSURE(ctx->d_sl_idx, (size_t)U * ctx->cap * 4);
+    ENSURE(ctx->d_sl_dist, (size_t)U * ctx->cap * 8);
+    ENSURE(ctx->d_sl_count, U * 4);
+    ENSURE(ctx->d_items, (size_t)U * ctx->cap * 8);
+    ENSURE(ctx->d_nitems, 16);
+    ENSURE(ctx->d_res, U * sizeof(UnitResultDev));
+    if ((size_t)U > ctx->h_res_cap) {
+        if (ctx->h_res) cudaFreeHost(ctx->h_res);
+        ctx->h_res = nullptr;
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->h_res, (size_t)U * sizeof(UnitResultDev)));
+        ctx->h_res_cap = (size_t)U;
+    }
+    cudaStream_t s = ctx->stream;
+    if (n_test) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_test.p, b->test_xy, n_test * 16, cudaMemcpyHostToDevice, s));
+    if (n_ref) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ref.p, b->ref_xy, n_ref * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), U * sizeof(UnitDesc), cudaMemcpyHostToDevice, s));
+    if (!ctx->h_work.empty())
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work.p, ctx->h_work.data(), ctx->h_work.size() * sizeof(WorkItem),
+                                      cudaMemcpyHostToDevice, s));
+    if (n_cs) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cs64.p, ctx->h_cs.data(), (size_t)n_cs * 16, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zero.p, ctx->h_zero.data(), (size_t)n_cs, cudaMemcpyHostToDevice, s));
+        k_cs32<<<(unsigned)((n_cs + 255) / 256), 256, 0, s>>>((const double2*)ctx->d_cs64.p, (float2*)ctx->d_cs32.p,
+                                                              n_cs);
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_rmax.p, 0, U * 4, s));
+    k_prep<<<(unsigned)U, 256, 0, s>>>((const UnitDesc*)ctx->d_units.p, (const double*)ctx->d_test.p,
+                                       (const double*)ctx->d_ref.p, (float4*)ctx->d_lay.p, (unsigned*)ctx->d_rmax.p,
+                                       TA);
+    CUDA_TRY(ctx, cudaGetLastError());
+    // The host arrays (and our own staging vectors) must outlive the async copies.
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    ctx->upload_launches = (n_cs ? 1 : 0) + 1;
+    ctx->ready = true;
+    ctx->ran = false;
+    return MMRS_OK;
+}
+
+// ---- run ------------------------------------------------------------------------------
+static int exact_smem(const mmrs_ctx* ctx) { return 64 + 2 * ctx->max_pts * 16; }
+
+// f64 recheck of every candidate of `unit` (shortlist overflow): leftmost arg-min on the host
+// over device-computed reference-arithmetic distances.
+static int full_f64_unit(mmrs_ctx* ctx, int64_t u, UnitResultDev& r) {
+    const UnitDesc& d = ctx->h_units[u];
+    ENSURE(ctx->d_tmp, (size_t)d.n_cand * 8);
+    const int smem = exact_smem(ctx);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_exact_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = std::min(d.n_cand, ctx->n_sm * 8);
+    k_exact_dense<<<grid, 256, smem, ctx->stream>>>((const UnitDesc*)ctx->d_units.p, (int)u,
+                                                    (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
+                                                    (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
+                                                    d.cand_off, d.n_cand, (double*)ctx->d_tmp.p, ctx->max_pts);
+    CUDA_TRY(ctx, cudaGetLastError());
+    std::vector<double> h(d.n_cand);
+    CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_tmp.p, (size_t)d.n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 1;
+    int best = 0;
+    for (int c = 1; c < d.n_cand; ++c)
+        if (h[c] < h[best]) best = c;
+    const double lim = h[best] + ctx->tie_margin * std::fmax(1.0, (double)ctx->h_rmax[u]);
+    int ties = 0;
+    for (int c = 0; c < d.n_cand; ++c) ties += (h[c] <= lim) ? 1 : 0;
+    r.best_idx = best;
+    r.best_dist = h[best];
+    r.n_shortlist = d.n_cand;
+    r.n_ties = ties;
+    r.flags |= MMRS_FLAG_FULL_F64;
+    ctx->overflow_dist[u] = std::move(h);
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_sweep_run: ctx is NULL");
+    if (!ctx->ready) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_run: no batch uploaded");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t U = ctx->n_units;
+    ctx->launches = 0;
+    ctx->ran = true;
+    ctx->overflow_dist.clear();
+    if (U == 0) return MMRS_OK;
+    cudaStream_t s = ctx->stream;
+    const UnitDesc* units = (const UnitDesc*)ctx->d_units.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_key.p, 0xff, U * 8, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_nitems.p, 0, 16, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    if (!ctx->h_work.empty()) {
+        if (!launch_sweep(ctx->TA, ctx->multi, (int)ctx->h_work.size(), ctx->smem_sweep, s, units,
+                          (const WorkItem*)ctx->d_work.p, (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p,
+                          (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p))
+            return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    k_shortlist<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p,
+                                            (const unsigned long long*)ctx->d_key.p, (const unsigned*)ctx->d_rmax.p,
+                                            (float)ctx->opt_rel, (float)ctx->opt_abs, ctx->cap, (int*)ctx->d_sl_idx.p,
+                                            (int*)ctx->d_sl_count.p, (int2*)ctx->d_items.p, (unsigned*)ctx->d_nitems.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    {
+        const int smem = exact_smem(ctx);
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const long long max_items = (long long)U * ctx->cap;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(max_items, (long long)ctx->n_sm * 8));
+        k_exact<<<grid, 256, smem, s>>>(units, (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
+                                        (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
+                                        (const int2*)ctx->d_items.p, (const unsigned*)ctx->d_nitems.p,
+                                        (const int*)ctx->d_sl_idx.p, (double*)ctx->d_sl_dist.p, ctx->cap, ctx->max_pts);
+        CUDA_TRY(ctx, cudaGetLastError());
+        k_select<<<(unsigned)((U + 7) / 8), 256, 0, s>>>(units, (int)U, (const int*)ctx->d_sl_idx.p,
+                                                         (const double*)ctx->d_sl_dist.p, (const int*)ctx->d_sl_count.p,
+                                                         (const unsigned long long*)ctx->d_key.p,
+                                                         (const unsigned*)ctx->d_rmax.p, ctx->cap, ctx->tie_margin,
+                                                         (UnitResultDev*)ctx->d_res.p);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
+    ctx->launches += 3;
+    return MMRS_OK;
+}
+
+// ---- download ------------------------------------------------------------------------
+extern "C" int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_sweep_download: ctx is NULL");
+    if (!ctx->ready || !ctx->ran) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_download: nothing has been run");
+    const int64_t U = ctx->n_units;
+    if (U == 0) return MMRS_OK;
+    if (!out) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_download: out is NULL");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res.p, U * sizeof(UnitResultDev), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const UnitResultDev* hr = (const UnitResultDev*)ctx->h_res;
+    bool need_rmax = false;
+    for (int64_t u = 0; u < U; ++u)
+        if (hr[u].n_shortlist < 0) need_rmax = true;
+    if (need_rmax) {
+        ctx->h_rmax.resize(U);
+        CUDA_TRY(ctx, cudaMemcpy(ctx->h_rmax.data(), ctx->d_rmax.p, U * 4, cudaMemcpyDeviceToHost));
+    }
+    for (int64_t u = 0; u < U; ++u) {
+        UnitResultDev r = hr[u];
+        const mmrs_grid& g = ctx->grids[ctx->grid_of_unit[u]];
+        mmrs_unit_result& o = out[u];
+        if (r.flags & MMRS_FLAG_DEGENERATE) {
+            o = mmrs_unit_result{-1, g.fallback, 0.0, 0.0f, 0, 0, r.flags};
+            continue;
+        }
+        if (r.flags & MMRS_FLAG_EMPTY) {  // every candidate costs 0.0 -> leftmost wins (process_utils.rs:86-88)
+            o = mmrs_unit_result{0, mmrs_grid_angle(&g, 0), 0.0, 0.0f, 0, (int32_t)g.n_cand, r.flags};
+            continue;
+        }
+        if (r.n_shortlist < 0) {
+            int rc = full_f64_unit(ctx, u, r);
+            if (rc != MMRS_OK) return rc;
+        }
+        o.best_idx = r.best_idx;
+        o.best_angle = mmrs_grid_angle(&g, r.best_idx);
+        o.best_dist = r.best_dist;
+        o.best_dist_f32 = r.best_d32;
+        o.n_shortlist = r.n_shortlist;
+        o.n_ties = r.n_ties;
+        o.flags = r.flags;
+    }
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_sweep_batched(mmrs_ctx* ctx, const mmrs_sweep_batch* batch, const mmrs_sweep_opts* opts,
+                                  mmrs_unit_result* out) {
+    int rc = mmrs_sweep_upload(ctx, batch, opts);
+    if (rc != MMRS_OK) return rc;
+    rc = mmrs_sweep_run(ctx);
+    if (rc != MMRS_OK) return rc;
+    return mmrs_sweep_download(ctx, out);
+}
+
+// ---- diagnostics -----------------------------------------------------------------------
+extern "C" int mmrs_sweep_get_dist32(mmrs_ctx* ctx, int64_t unit, float* out, int64_t cap) {
+    if (!ctx || !ctx->ready || !ctx->ran) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_get_dist32: nothing has been run");
+    if (unit < 0 || unit >= ctx->n_units) return set_err(ctx, MMRS_ERR_ARG, "unit out of range");
+    const UnitDesc& d = ctx->h_units[unit];
+    const int64_t n = std::min<int64_t>(cap, d.n_cand);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > 0)
+        CUDA_TRY(ctx, cudaMemcpy(out, (const float*)ctx->d_dist32.p + d.dist_off, n * 4, cudaMemcpyDeviceToHost));
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_sweep_get_shortlist(mmrs_ctx* ctx, int64_t unit, int64_t* idx_out, double* dist_out, int32_t cap,
+                                        int32_t* n_out) {
+    if (!ctx || !ctx->ready || !ctx->ran)
+        return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_get_shortlist: nothing has been run");
+    if (unit < 0 || unit >= ctx->n_units) return set_err(ctx, MMRS_ERR_ARG, "unit out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    auto ov = ctx->overflow_dist.find(unit);
+    if (ov != ctx->overflow_dist.end()) {  // the whole unit was rechecked
+        const int n = (int)ov->second.size();
+        *n_out = n;
+        for (int i = 0; i < n && i < cap; ++i) {
+            idx_out[i] = i;
+            dist_out[i] = ov->second[i];
+        }
+        return MMRS_OK;
+    }
+    int n = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&n, (const int*)ctx->d_sl_count.p + unit, 4, cudaMemcpyDeviceToHost));
+    if (n < 0) return set_err(ctx, MMRS_ERR_STATE, "shortlist overflowed; call mmrs_sweep_download first");
+    *n_out = n;
+    const int k = std::min(n, cap);
+    std::vector<int> idx(k);
+    if (k > 0) {
+        CUDA_TRY(ctx, cudaMemcpy(idx.data(), (const int*)ctx->d_sl_idx.p + unit * ctx->cap, k * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(dist_out, (const double*)ctx->d_sl_dist.p + unit * ctx->cap, k * 8, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < k; ++i) idx_out[i] = idx[i];
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_last_timings(mmrs_ctx* ctx, float ms_out[4], int32_t* launches_out) {
+    if (!ctx || !ctx->ran) return set_err(ctx, MMRS_ERR_STATE, "mmrs_last_timings: nothing has been run");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 4; ++i) ms_out[i] = 0.f;
+    if (ctx->n_units > 0) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[0], ctx->ev[0], ctx->ev[1]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[1], ctx->ev[1], ctx->ev[2]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[2], ctx->ev[2], ctx->ev[3]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[3], ctx->ev[0], ctx->ev[3]));
+    }
+    if (launches_out) *launches_out = ctx->launches;
+    return MMRS_OK;
+}
+
+// ---- explicit-angle exact evaluation ----------------------------------------------------
+extern "C" int mmrs_eval_exact(mmrs_ctx* ctx, const double* test_xy, int64_t n_test, const double* ref_xy,
+                               int64_t n_ref, double cx, double cy, int32_t mode, const double* angles,
+                               int64_t n_angles, double* dist_out) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_eval_exact: ctx is NULL");
+    if (n_test < 0 || n_ref < 0 || n_angles < 0 || (n_angles > 0 && (!angles || !dist_out)))
+        return set_err(ctx, MMRS_ERR_ARG, "mmrs_eval_exact: bad arguments");
+    if (n_angles == 0) return MMRS_OK;
+    if (n_test == 0 || n_ref == 0) {  // process_utils.rs:86-88
+        for (int64_t i = 0; i < n_angles; ++i) dist_out[i] = 0.0;
+        return MMRS_OK;
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    std::vector<double> cs(2 * n_angles);
+    std::vector<unsigned char> zero(n_angles);
+    for (int64_t i = 0; i < n_angles; ++i) {
+        cs[2 * i] = std::cos(angles[i]);
+        cs[2 * i + 1] = std::sin(angles[i]);
+        zero[i] = (mode == 0 && angles[i] == 0.0) ? 1 : 0;
+    }
+    // private scratch (does not disturb an uploaded batch)
+    const size_t b_pts = (size_t)(n_test + n_ref) * 16, b_cs = (size_t)n_angles * 16, b_out = (size_t)n_angles * 8;
+    const size_t o_cs = (b_pts + 255) / 256 * 256, o_zero = o_cs + (b_cs + 255) / 256 * 256,
+                 o_out = o_zero + ((size_t)n_angles + 255) / 256 * 256, o_unit = o_out + (b_out + 255) / 256 * 256;
+    ENSURE(ctx->d_tmp, o_unit + sizeof(UnitDesc));
+    unsigned char* base = (unsigned char*)ctx->d_tmp.p;
+    UnitDesc d{};
+    d.test_off = 0;
+    d.ref_off = 0;
+    d.n = (int)n_test;
+    d.m = (int)n_ref;
+    d.cx = cx;
+    d.cy = cy;
+    CUDA_TRY(ctx, cudaMemcpyAsync(base, test_xy, (size_t)n_test * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(base + (size_t)n_test * 16, ref_xy, (size_t)n_ref * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(base + o_cs, cs.data(), b_cs, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(base + o_zero, zero.data(), (size_t)n_angles, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(base + o_unit, &d, sizeof(UnitDesc), cudaMemcpyHostToDevice, s));
+    const int max_n = (int)std::max(n_test, n_ref);
+    const int smem = 64 + 2 * max_n * 16;
+    if (smem > 227 * 1024) return set_err(ctx, MMRS_ERR_ARG, "mmrs_eval_exact: point sets too large for shared memory");
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_exact_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = (int)std::min<int64_t>(n_angles, (int64_t)ctx->n_sm * 8);
+    k_exact_dense<<<grid, 256, smem, s>>>((const UnitDesc*)(base + o_unit), 0, (const double*)base,
+                                          (const double*)(base + (size_t)n_test * 16), (const double2*)(base + o_cs),
+                                          (const unsigned char*)(base + o_zero), 0, (int)n_angles,
+                                          (double*)(base + o_out), max_n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(dist_out, base + o_out, b_out, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    ctx->eval_launches += 1;
+    return MMRS_OK;
+}
+
+// ---- FP32 peak probe ------------------------------------------------------------------------
+extern "C" int mmrs_fp32_probe(mmrs_ctx* ctx, int32_t iters, double* tflops_out) {
+    if (!ctx || !tflops_out) return set_err(ctx, MMRS_ERR_ARG, "mmrs_fp32_probe: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->n_sm * 8;
+    ENSURE(ctx->d_tmp, (size_t)blocks * 256 * 4);
+    cudaEvent_t a, b;
+    CUDA_TRY(ctx, cudaEventCreate(&a));
+    CUDA_TRY(ctx, cudaEventCreate(&b));
+    k_fp32_probe<<<blocks, 256, 0, ctx->stream>>>((float*)ctx->d_tmp.p, iters / 4 + 1, 1.0000001f, 1e-9f);  // warm-up
+    CUDA_TRY(ctx, cudaEventRecord(a, ctx->stream));
+    k_fp32_probe<<<blocks, 256, 0, ctx->stream>>>((float*)ctx->d_tmp.p, iters, 1.0000001f, 1e-9f);
+    CUDA_TRY(ctx, cudaEventRecord(b, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(b));
+    CUDA_TRY(ctx, cudaGetLastError());
+    float ms = 0;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    const double flops = (double)blocks * 256 * (double)iters * 16 * 8 * 2;
+    *tflops_out = flops / (ms * 1e-3) / 1e12;
+    return MMRS_OK;
+}

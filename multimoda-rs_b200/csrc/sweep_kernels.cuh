@@ -1,0 +1,478 @@
+// =============================================================================
+// sweep_kernels.cuh — sm_100a device code of the Hausdorff rotation sweep.
+//
+//   K0  k_prep        f64 points -> centred FP32 staging layout (+ Rmax)
+//   K1  k_sweep<TA>   FP32 sweep: one CTA = one unit x one tile of candidate
+//                     angles, one warp = one candidate; reference contour
+//                     staged in shared memory by a TMA bulk copy; test points
+//                     rotated into registers; symmetric directed Hausdorff as
+//                     a register-tiled min-over-M / max-over-N with packed
+//                     f32x2 arithmetic (FADD2/FMUL2/FFMA2), 3-input FMNMX and
+//                     warp REDUX; fused per-unit arg-min on a packed
+//                     (distance, index) 64-bit key with atomicMin.
+//   K2  k_shortlist   candidates within the FP32 error window of the minimum
+//   K3  k_exact       the reference's f64 arithmetic, literally, on those
+//   K4  k_select      leftmost f64 arg-min + tie count per unit
+//
+// Replaces (reference paths): search_range + hausdorff_distance +
+// directed_hausdorff, src/intravascular/processing/process_utils.rs:33-121, and
+// the cost closures align_within.rs:99-105/:200-206, align_between.rs:189-216.
+// =============================================================================
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mmrs_internal.hpp"
+
+namespace mmrs {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+// ---- packed FP32 helpers (Blackwell-only PTX: *.f32x2, 3-input min.f32) --------
+__device__ __forceinline__ uint64_t pk(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) --------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+
+// =============================================================================
+// K0: f64 (x,y) -> centred FP32 staging layout.
+// A block (test points, the set that is rotated; register side of K1):
+//   float4 e = (chunk c, pair k, lane l) at (c*(TA/2)+k)*32 + l holds points
+//   i0 = c*32*TA + 2k*32 + l and i1 = i0 + 32 as (x0, x1, y0, y1).
+// B block (reference points; streamed from shared memory in K1):
+//   float4 j = (bx, bx, by, by), j < 2*m_pairs.
+// Indices past the end repeat the last point (a duplicate never changes a
+// min-over-points or a max-over-points).
+// =============================================================================
+__global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restrict__ test_xy,
+                       const double* __restrict__ ref_xy, float4* __restrict__ lay, unsigned* __restrict__ rmax_bits,
+                       int TA) {
+    const UnitDesc ud = units[blockIdx.x];
+    if (ud.n <= 0 || ud.m <= 0) return;
+    const int half = TA / 2;
+    const int a_elems = ud.n_chunks * half * 32;
+    float4* A = lay + ud.lay_off;
+    float4* B = A + a_elems;
+    float rmax = 0.f;
+    for (int e = threadIdx.x; e < a_elems; e += blockDim.x) {
+        int l = e & 31, ck = e >> 5;
+        int c = ck / half, k = ck - c * half;
+        int i0 = c * 32 * TA + 2 * k * 32 + l, i1 = i0 + 32;
+        i0 = min(i0, ud.n - 1);
+        i1 = min(i1, ud.n - 1);
+        const double* p0 = test_xy + 2 * (ud.test_off + i0);
+        const double* p1 = test_xy + 2 * (ud.test_off + i1);
+        float4 v;
+        v.x = (float)(p0[0] - ud.cx);
+        v.y = (float)(p1[0] - ud.cx);
+        v.z = (float)(p0[1] - ud.cy);
+        v.w = (float)(p1[1] - ud.cy);
+        A[e] = v;
+        rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (int j = threadIdx.x; j < 2 * ud.m_pairs; j += blockDim.x) {
+        int jj = min(j, ud.m - 1);
+        const double* p = ref_xy + 2 * (ud.ref_off + jj);
+        float bx = (float)(p[0] - ud.cx), by = (float)(p[1] - ud.cy);
+        B[j] = make_float4(bx, bx, by, by);
+        rmax = fmaxf(rmax, fmaxf(fabsf(bx), fabsf(by)));
+    }
+    unsigned rb = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
+    if ((threadIdx.x & 31) == 0) atomicMax(&rmax_bits[blockIdx.x], rb);
+}
+
+// f64 (cos, sin) table -> FP32 table for K1.
+__global__ void k_cs32(const double2* __restrict__ cs64, float2* __restrict__ cs32, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) cs32[i] = make_float2((float)cs64[i].x, (float)cs64[i].y);
+}
+
+// =============================================================================
+// K1: the FP32 sweep.
+// =============================================================================
+template <int TA, bool MULTI>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_sweep(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
+            const float2* __restrict__ cs32, float* __restrict__ dist32, unsigned long long* __restrict__ key) {
+    static_assert(TA % 2 == 0 && TA >= 2, "TA must be even");
+    constexpr int H = TA / 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw + 8);
+    float4* sA = reinterpret_cast<float4*>(smem_raw + 16);
+
+    const WorkItem w = work[blockIdx.x];
+    const UnitDesc ud = units[w.unit];
+    const int a_elems = ud.n_chunks * H * 32;
+    const int b_elems = 2 * ud.m_pairs;
+    float4* sB = sA + a_elems;
+    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems);  // MULTI only: [warp][b_elems]
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        *s_key = ~0ull;
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)(a_elems + b_elems) * 16u;
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(sA, lay + ud.lay_off, bytes, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    unsigned long long best = ~0ull;
+    unsigned* my_col = s_col + wid * b_elems;
+    const float INF = __int_as_float(0x7f800000);
+
+    for (int ci = wid; ci < w.count; ci += kWarpsPerCta) {
+        const int c = w.begin + ci;
+        const float2 cs = __ldg(&cs32[ud.cand_off + c]);
+        const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
+        unsigned rowmax = 0u, colmax = 0u;  // bit patterns of non-negative floats order like unsigned ints
+
+        for (int ch = 0; ch < ud.n_chunks; ++ch) {
+            uint64_t AX[H], AY[H];
+            float row[TA];
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const float4 a = sA[(ch * H + k) * 32 + lane];
+                const uint64_t X2 = pk(a.x, a.y), Y2 = pk(a.z, a.w);
+                AX[k] = fma2(Y2, NS2, mul2(X2, C2));  // x' = x cos - y sin
+                AY[k] = fma2(X2, S2, mul2(Y2, C2));   // y' = x sin + y cos
+                row[2 * k] = INF;
+                row[2 * k + 1] = INF;
+            }
+#pragma unroll 1
+            for (int j = 0; j < ud.m_pairs; ++j) {
+                const float4 B0 = sB[2 * j], B1 = sB[2 * j + 1];
+                const uint64_t bx0 = pk(B0.x, B0.y), by0 = pk(B0.z, B0.w);
+                const uint64_t bx1 = pk(B1.x, B1.y), by1 = pk(B1.z, B1.w);
+                float c0 = INF, c1 = INF;
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    const uint64_t dx0 = sub2(AX[k], bx0), dy0 = sub2(AY[k], by0);
+                    const uint64_t dx1 = sub2(AX[k], bx1), dy1 = sub2(AY[k], by1);
+                    const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));  // (|a0-b0|^2, |a1-b0|^2)
+                    const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));  // (|a0-b1|^2, |a1-b1|^2)
+                    float d00, d10, d01, d11;
+                    upk(d0, d00, d10);
+                    upk(d1, d01, d11);
+                    row[2 * k] = min3(row[2 * k], d00, d01);
+                    row[2 * k + 1] = min3(row[2 * k + 1], d10, d11);
+                    c0 = min3(c0, d00, d10);
+                    c1 = min3(c1, d01, d11);
+                }
+                unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
+                unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
+                if (!MULTI) {
+                    colmax = max(colmax, max(r0, r1));
+                } else if (lane == 0) {
+                    if (ch > 0) {
+                        r0 = min(r0, my_col[2 * j]);
+                        r1 = min(r1, my_col[2 * j + 1]);
+                    }
+                    my_col[2 * j] = r0;
+                    my_col[2 * j + 1] = r1;
+                }
+            }
+            float rm = row[0];
+#pragma unroll
+            for (int k = 1; k < TA; ++k) rm = fmaxf(rm, row[k]);
+            rowmax = max(rowmax, __float_as_uint(rm));
+        }
+        if (MULTI) {
+            __syncwarp();
+            for (int j = lane; j < b_elems; j += 32) colmax = max(colmax, my_col[j]);
+            __syncwarp();
+        }
+        const unsigned h2 = __reduce_max_sync(0xffffffffu, max(rowmax, colmax));
+        const float d = sqrtf(__uint_as_float(h2));
+        if (lane == 0) {
+            dist32[ud.dist_off + c] = d;
+            const unsigned long long k64 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c;
+            best = min(best, k64);
+        }
+    }
+    if (lane == 0 && best != ~0ull) atomicMin(s_key, best);
+    __syncthreads();
+    if (threadIdx.x == 0 && *s_key != ~0ull) atomicMin(&key[w.unit], *s_key);
+}
+
+// =============================================================================
+// K2: shortlist = candidates whose FP32 distance lies inside the FP32 error
+// window above the minimum. Appends (unit, slot) items to a global list.
+// =============================================================================
+__global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __restrict__ dist32,
+                            const unsigned long long* __restrict__ key, const unsigned* __restrict__ rmax_bits,
+                            float rel, float abs_scale, int cap, int* __restrict__ sl_idx, int* __restrict__ sl_count,
+                            int2* __restrict__ items, unsigned* __restrict__ n_items) {
+    __shared__ int s_n;
+    __shared__ unsigned s_base;
+    const int u = blockIdx.x;
+    const UnitDesc ud = units[u];
+    if (ud.n_cand <= 0 || ud.n <= 0 || ud.m <= 0) {
+        if (threadIdx.x == 0) sl_count[u] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const float dmin = __uint_as_float((unsigned)(key[u] >> 32));
+    const float thr = dmin * (1.0f + rel) + abs_scale * __uint_as_float(rmax_bits[u]);
+    const float* d = dist32 + ud.dist_off;
+    for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x) {
+        if (d[c] <= thr) {
+            int pos = atomicAdd(&s_n, 1);
+            if (pos < cap) sl_idx[(long long)u * cap + pos] = c;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n > cap) {  // overflow: the host rechecks the whole unit in f64
+        if (threadIdx.x == 0) sl_count[u] = -n;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        sl_count[u] = n;
+        s_base = atomicAdd(n_items, (unsigned)n);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) items[s_base + k] = make_int2(u, k);
+}
+
+// =============================================================================
+// K3: the reference's f64 arithmetic, literally (no FMA contraction: explicit
+// __dmul_rn/__dadd_rn/__dsub_rn; IEEE sqrt). cos/sin come from the HOST's glibc
+// (what Rust's f64::sin/cos call), passed as a table, because CUDA's double
+// sin/cos are not bit-identical to glibc's.
+//   rotate     : contour_point.rs:38-52 (mode 0, identity iff angle == 0.0) /
+//                align_between.rs:193-209 (mode 1)
+//   distances  : process_utils.rs:84-121, both directions, sqrt, max
+// One CTA per (unit, candidate) item; grid-stride over the item list.
+// =============================================================================
+__device__ __forceinline__ double block_max(double v, double* s_red) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = s_red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = fmax(r, s_red[i]);
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ double exact_cost(const UnitDesc& ud, const double* __restrict__ test_xy,
+                                             const double* __restrict__ ref_xy, double cosv, double sinv, bool identity,
+                                             double2* s_rot, double2* s_ref, double* s_red) {
+    for (int i = threadIdx.x; i < ud.n; i += blockDim.x) {
+        const double px = test_xy[2 * (ud.test_off + i)], py = test_xy[2 * (ud.test_off + i) + 1];
+        double rx = px, ry = py;
+        if (!identity) {
+            const double x = __dsub_rn(px, ud.cx), y = __dsub_rn(py, ud.cy);
+            rx = __dadd_rn(__dsub_rn(__dmul_rn(x, cosv), __dmul_rn(y, sinv)), ud.cx);
+            ry = __dadd_rn(__dadd_rn(__dmul_rn(x, sinv), __dmul_rn(y, cosv)), ud.cy);
+        }
+        s_rot[i] = make_double2(rx, ry);
+    }
+    for (int j = threadIdx.x; j < ud.m; j += blockDim.x)
+        s_ref[j] = make_double2(ref_xy[2 * (ud.ref_off + j)], ref_xy[2 * (ud.ref_off + j) + 1]);
+    __syncthreads();
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    // forward: reference -> rotated
+    double lmax = 0.0;
+    for (int i = threadIdx.x; i < ud.m; i += blockDim.x) {
+        const double2 a = s_ref[i];
+        double mn = INF;
+        for (int j = 0; j < ud.n; ++j) {
+            const double2 b = s_rot[j];
+            const double dx = __dsub_rn(a.x, b.x), dy = __dsub_rn(a.y, b.y);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 < mn) mn = d2;
+        }
+        if (isfinite(mn) && mn > lmax) lmax = mn;
+    }
+    const double fwd = block_max(lmax, s_red);
+    // backward: rotated -> reference
+    lmax = 0.0;
+    for (int i = threadIdx.x; i < ud.n; i += blockDim.x) {
+        const double2 a = s_rot[i];
+        double mn = INF;
+        for (int j = 0; j < ud.m; ++j) {
+            const double2 b = s_ref[j];
+            const double dx = __dsub_rn(a.x, b.x), dy = __dsub_rn(a.y, b.y);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 < mn) mn = d2;
+        }
+        if (isfinite(mn) && mn > lmax) lmax = mn;
+    }
+    const double bwd = block_max(lmax, s_red);
+    return fmax(__dsqrt_rn(fwd), __dsqrt_rn(bwd));
+}
+
+__global__ void __launch_bounds__(256)
+    k_exact(const UnitDesc* __restrict__ units, const double* __restrict__ test_xy, const double* __restrict__ ref_xy,
+            const double2* __restrict__ cs64, const unsigned char* __restrict__ zero_flag,
+            const int2* __restrict__ items, const unsigned* __restrict__ n_items, const int* __restrict__ sl_idx,
+            double* __restrict__ sl_dist, int cap, int max_n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_red = reinterpret_cast<double*>(smem_raw);
+    double2* s_rot = reinterpret_cast<double2*>(smem_raw + 64);
+    double2* s_ref = s_rot + max_n;
+    const unsigned total = *n_items;
+    for (unsigned it = blockIdx.x; it < total; it += gridDim.x) {
+        const int2 item = items[it];
+        const UnitDesc ud = units[item.x];
+        const long long slot = (long long)item.x * cap + item.y;
+        const int c = sl_idx[slot];
+        const double2 cs = cs64[ud.cand_off + c];
+        const bool identity = zero_flag[ud.cand_off + c] != 0;
+        const double d = exact_cost(ud, test_xy, ref_xy, cs.x, cs.y, identity, s_rot, s_ref, s_red);
+        if (threadIdx.x == 0) sl_dist[slot] = d;
+        __syncthreads();
+    }
+}
+
+// Dense variant: every candidate [c0, c0+count) of one unit (shortlist overflow
+// path and mmrs_eval_exact).
+__global__ void __launch_bounds__(256)
+    k_exact_dense(const UnitDesc* __restrict__ units, int unit, const double* __restrict__ test_xy,
+                  const double* __restrict__ ref_xy, const double2* __restrict__ cs64,
+                  const unsigned char* __restrict__ zero_flag, long long cs_off, int count, double* __restrict__ out,
+                  int max_n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_red = reinterpret_cast<double*>(smem_raw);
+    double2* s_rot = reinterpret_cast<double2*>(smem_raw + 64);
+    double2* s_ref = s_rot + max_n;
+    const UnitDesc ud = units[unit];
+    for (int c = blockIdx.x; c < count; c += gridDim.x) {
+        const double2 cs = cs64[cs_off + c];
+        const bool identity = zero_flag[cs_off + c] != 0;
+        const double d = exact_cost(ud, test_xy, ref_xy, cs.x, cs.y, identity, s_rot, s_ref, s_red);
+        if (threadIdx.x == 0) out[c] = d;
+        __syncthreads();
+    }
+}
+
+// =============================================================================
+// K4: per unit, leftmost arg-min over the rechecked candidates in f64 (strict <,
+// ties -> lowest candidate index: process_utils.rs:69-74) and the tie count.
+// One warp per unit.
+// =============================================================================
+__global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const int* __restrict__ sl_idx,
+                         const double* __restrict__ sl_dist, const int* __restrict__ sl_count,
+                         const unsigned long long* __restrict__ key, const unsigned* __restrict__ rmax_bits, int cap,
+                         double tie_margin, UnitResultDev* __restrict__ res) {
+    const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (u >= n_units) return;
+    const int n = sl_count[u];
+    UnitResultDev r;
+    r.best_idx = -1;
+    r.best_dist = 0.0;
+    r.best_d32 = __uint_as_float((unsigned)(key[u] >> 32));
+    r.n_shortlist = n;
+    r.n_ties = 0;
+    r.flags = units[u].flags;
+    if (n > 0) {
+        const long long base = (long long)u * cap;
+        double bd = __longlong_as_double(0x7ff0000000000000LL);
+        int bi = 0x7fffffff;
+        for (int k = lane; k < n; k += 32) {
+            const double d = sl_dist[base + k];
+            const int i = sl_idx[base + k];
+            if (d < bd || (d == bd && i < bi)) {
+                bd = d;
+                bi = i;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) {
+                bd = od;
+                bi = oi;
+            }
+        }
+        const double lim = bd + tie_margin * fmax(1.0, (double)__uint_as_float(rmax_bits[u]));
+        int ties = 0;
+        for (int k = lane; k < n; k += 32) ties += (sl_dist[base + k] <= lim) ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
+        r.best_idx = bi;
+        r.best_dist = bd;
+        r.n_ties = ties;
+    }
+    if (lane == 0) res[u] = r;
+}
+
+// =============================================================================
+// FP32 peak probe: 8 independent FFMA chains per thread, all SMs busy.
+// =============================================================================
+__global__ void __launch_bounds__(256) k_fp32_probe(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            x0 = fmaf(x0, a, b);
+            x1 = fmaf(x1, a, b);
+            x2 = fmaf(x2, a, b);
+            x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b);
+            x5 = fmaf(x5, a, b);
+            x6 = fmaf(x6, a, b);
+            x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace mmrs

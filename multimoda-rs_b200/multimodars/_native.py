@@ -1,0 +1,240 @@
+"""ctypes binding of libmmrs_b200.so (the C ABI of include/mmrs_b200.h).
+
+This is what a maintainer's FFI stub binds (INTEGRATION.md shows the Rust
+`extern "C"` block for the same symbols). There is no CPU fallback: importing
+works without a GPU (so symbol checks can run), every compute call raises
+MmrsError when no B200 is present or the library is not built."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG_ROOT = Path(__file__).resolve().parent.parent  # multimoda-rs_b200/
+LIB_PATH = Path(os.environ.get("MMRS_B200_LIB", _PKG_ROOT / "libmmrs_b200.so"))
+
+c_dp = C.POINTER(C.c_double)
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+
+
+class MmrsError(RuntimeError):
+    """Mirrors the reference's PyRuntimeError(format!("{e:#}")) (binding/functions.rs:228)."""
+
+
+class Grid(C.Structure):
+    _fields_ = [("start_rad", C.c_double), ("step_rad", C.c_double), ("n_cand", C.c_int64),
+                ("degenerate", C.c_int32), ("fallback", C.c_double)]
+
+
+class SweepBatch(C.Structure):
+    _fields_ = [("n_units", C.c_int64), ("test_xy", c_dp), ("test_off", c_i64p), ("ref_xy", c_dp),
+                ("ref_off", c_i64p), ("centre_xy", c_dp), ("grids", C.POINTER(Grid)), ("n_grids", C.c_int64),
+                ("grid_of_unit", c_i32p), ("mode", C.c_int32)]
+
+
+class SweepOpts(C.Structure):
+    _fields_ = [("shortlist_rel", C.c_double), ("shortlist_abs", C.c_double), ("shortlist_cap", C.c_int32),
+                ("tie_margin", C.c_double), ("keep_dist32", C.c_int32)]
+
+
+class UnitResult(C.Structure):
+    _fields_ = [("best_idx", C.c_int64), ("best_angle", C.c_double), ("best_dist", C.c_double),
+                ("best_dist_f32", C.c_float), ("n_shortlist", C.c_int32), ("n_ties", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("step_deg", C.c_double), ("range_deg", C.c_double), ("sample_size", C.c_int64),
+                ("smooth", C.c_int32), ("bruteforce", C.c_int32)]
+
+
+RESULT_DTYPE = np.dtype([("best_idx", "<i8"), ("best_angle", "<f8"), ("best_dist", "<f8"), ("best_dist_f32", "<f4"),
+                         ("n_shortlist", "<i4"), ("n_ties", "<i4"), ("flags", "<i4")], align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(UnitResult)
+
+FLAG_DEGENERATE, FLAG_FULL_F64, FLAG_EMPTY = 1, 2, 4
+
+# every symbol include/mmrs_b200.h declares
+EXPORTS = [
+    "mmrs_ctx_create", "mmrs_ctx_destroy", "mmrs_last_error", "mmrs_version", "mmrs_grid_from_reference_params",
+    "mmrs_grid_angle", "mmrs_stage_plan", "mmrs_sweep_batched", "mmrs_sweep_upload", "mmrs_sweep_run",
+    "mmrs_sweep_download", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
+    "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
+    "mmrs_process_cases", "mmrs_process_stats",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise MmrsError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                            f"(multimoda-rs_b200/csrc/build.sh). There is no CPU fallback.")
+        L = C.CDLL(str(LIB_PATH))
+        L.mmrs_last_error.restype = C.c_char_p
+        L.mmrs_last_error.argtypes = [C.c_void_p]
+        L.mmrs_version.restype = C.c_char_p
+        L.mmrs_grid_angle.restype = C.c_double
+        L.mmrs_grid_angle.argtypes = [C.POINTER(Grid), C.c_int64]
+        L.mmrs_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.mmrs_ctx_destroy.argtypes = [C.c_void_p]
+        L.mmrs_free.argtypes = [C.c_void_p]
+        L.mmrs_grid_from_reference_params.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                                      C.POINTER(Grid)]
+        L.mmrs_stage_plan.argtypes = [C.c_double, C.c_double, c_dp, c_dp]
+        L.mmrs_sweep_batched.argtypes = [C.c_void_p, C.POINTER(SweepBatch), C.POINTER(SweepOpts), C.c_void_p]
+        L.mmrs_sweep_upload.argtypes = [C.c_void_p, C.POINTER(SweepBatch), C.POINTER(SweepOpts)]
+        L.mmrs_sweep_run.argtypes = [C.c_void_p]
+        L.mmrs_sweep_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.mmrs_sweep_get_dist32.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int64]
+        L.mmrs_sweep_get_shortlist.argtypes = [C.c_void_p, C.c_int64, c_i64p, c_dp, C.c_int32, c_i32p]
+        L.mmrs_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), c_i32p]
+        L.mmrs_eval_exact.argtypes = [C.c_void_p, c_dp, C.c_int64, c_dp, C.c_int64, C.c_double, C.c_double,
+                                      C.c_int32, c_dp, C.c_int64, c_dp]
+        L.mmrs_fp32_probe.argtypes = [C.c_void_p, C.c_int32, c_dp]
+        L.mmrs_process_stats.argtypes = [C.c_void_p, c_i64p]
+        _lib = L
+    return _lib
+
+
+def _err(ctx_ptr):
+    return lib().mmrs_last_error(ctx_ptr).decode(errors="replace")
+
+
+def make_grid(step_deg, range_deg, center=None, limes_deg=None) -> Grid:
+    """mmrs_grid_from_reference_params: the grid of process_utils.rs:43-67."""
+    g = Grid()
+    limes_deg = range_deg if limes_deg is None else limes_deg
+    rc = lib().mmrs_grid_from_reference_params(step_deg, range_deg, int(center is not None),
+                                               0.0 if center is None else float(center), limes_deg, C.byref(g))
+    if rc:
+        raise MmrsError(_err(None))
+    return g
+
+
+def grid_angle(g: Grid, i: int) -> float:
+    return lib().mmrs_grid_angle(C.byref(g), int(i))
+
+
+def stage_plan(step_deg, range_deg):
+    s = (C.c_double * 4)()
+    w = (C.c_double * 4)()
+    n = lib().mmrs_stage_plan(step_deg, range_deg, s, w)
+    return [(s[i], w[i]) for i in range(n)]
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """Owns one mmrs_ctx (one device, one stream, grow-only device workspaces)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._p = C.c_void_p()
+        rc = lib().mmrs_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._p))
+        if rc:
+            raise MmrsError(_err(None))
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        if self._p:
+            lib().mmrs_ctx_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise MmrsError(_err(self._p))
+
+    # -- sweep --------------------------------------------------------------------
+    def _batch(self, test_xy, test_off, ref_xy, ref_off, centre_xy, grids, grid_of_unit, mode):
+        test_xy, ref_xy, centre_xy = _f64(test_xy).reshape(-1), _f64(ref_xy).reshape(-1), _f64(centre_xy).reshape(-1)
+        test_off = np.ascontiguousarray(test_off, dtype=np.int64)
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+        U = len(test_off) - 1
+        assert len(ref_off) == U + 1 and len(centre_xy) == 2 * U
+        garr = (Grid * max(len(grids), 1))(*grids)
+        gou = None if grid_of_unit is None else np.ascontiguousarray(grid_of_unit, dtype=np.int32)
+        b = SweepBatch(U, test_xy.ctypes.data_as(c_dp), test_off.ctypes.data_as(c_i64p), ref_xy.ctypes.data_as(c_dp),
+                       ref_off.ctypes.data_as(c_i64p), centre_xy.ctypes.data_as(c_dp), garr, len(grids),
+                       None if gou is None else gou.ctypes.data_as(c_i32p), int(mode))
+        self._keep = (test_xy, test_off, ref_xy, ref_off, centre_xy, garr, gou)
+        return b, U
+
+    @staticmethod
+    def _opts(shortlist_rel=0.0, shortlist_abs=0.0, shortlist_cap=0, tie_margin=0.0, keep_dist32=False):
+        return SweepOpts(shortlist_rel, shortlist_abs, shortlist_cap, tie_margin, int(keep_dist32))
+
+    def sweep_batched(self, test_xy, test_off, ref_xy, ref_off, centre_xy, grids, grid_of_unit=None, mode=0, **opts):
+        """Host arrays in, structured result array (RESULT_DTYPE) out."""
+        b, U = self._batch(test_xy, test_off, ref_xy, ref_off, centre_xy, grids, grid_of_unit, mode)
+        o = self._opts(**opts)
+        out = np.zeros(U, dtype=RESULT_DTYPE)
+        self._check(lib().mmrs_sweep_batched(self._p, C.byref(b), C.byref(o), out.ctypes.data_as(C.c_void_p)))
+        self._n_units = U
+        return out
+
+    def sweep_upload(self, test_xy, test_off, ref_xy, ref_off, centre_xy, grids, grid_of_unit=None, mode=0, **opts):
+        b, U = self._batch(test_xy, test_off, ref_xy, ref_off, centre_xy, grids, grid_of_unit, mode)
+        o = self._opts(**opts)
+        self._check(lib().mmrs_sweep_upload(self._p, C.byref(b), C.byref(o)))
+        self._n_units = U
+
+    def sweep_run(self):
+        self._check(lib().mmrs_sweep_run(self._p))
+
+    def sweep_download(self):
+        out = np.zeros(self._n_units, dtype=RESULT_DTYPE)
+        self._check(lib().mmrs_sweep_download(self._p, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dist32(self, unit, n_cand):
+        out = np.empty(n_cand, dtype=np.float32)
+        self._check(lib().mmrs_sweep_get_dist32(self._p, unit, out.ctypes.data_as(C.POINTER(C.c_float)), n_cand))
+        return out
+
+    def shortlist(self, unit, cap=1 << 17):
+        idx = np.empty(cap, dtype=np.int64)
+        d = np.empty(cap, dtype=np.float64)
+        n = C.c_int32()
+        self._check(lib().mmrs_sweep_get_shortlist(self._p, unit, idx.ctypes.data_as(c_i64p), d.ctypes.data_as(c_dp),
+                                                   cap, C.byref(n)))
+        k = min(n.value, cap)
+        return idx[:k].copy(), d[:k].copy()
+
+    def timings(self):
+        ms = (C.c_float * 4)()
+        n = C.c_int32()
+        self._check(lib().mmrs_last_timings(self._p, ms, C.byref(n)))
+        return dict(sweep_ms=ms[0], shortlist_ms=ms[1], recheck_ms=ms[2], total_ms=ms[3], launches=n.value)
+
+    def eval_exact(self, test_xy, ref_xy, centre, mode, angles):
+        t, r, a = _f64(test_xy).reshape(-1, 2), _f64(ref_xy).reshape(-1, 2), _f64(angles).reshape(-1)
+        out = np.empty(len(a), dtype=np.float64)
+        self._check(lib().mmrs_eval_exact(self._p, t.ctypes.data_as(c_dp), len(t), r.ctypes.data_as(c_dp), len(r),
+                                          float(centre[0]), float(centre[1]), int(mode), a.ctypes.data_as(c_dp),
+                                          len(a), out.ctypes.data_as(c_dp)))
+        return out
+
+    def fp32_probe(self, iters=4096):
+        t = C.c_double()
+        self._check(lib().mmrs_fp32_probe(self._p, iters, C.byref(t)))
+        return t.value
+
+    def process_stats(self):
+        s = (C.c_int64 * 5)()
+        self._check(lib().mmrs_process_stats(self._p, s))
+        return dict(units=s[0], evals=s[1], rechecks=s[2], chain_resolved=s[3], launches=s[4])
