@@ -1,8 +1,1412 @@
-// placeholder — replaced by the host-side orchestration (see next commit)
-#include "mmrs_internal.hpp"
+// =============================================================================
+// mmrs_host.cpp — host side of the drop-in: geometry model, ingest, the frame
+// chain, post steps, inter-pullback alignment and the mode orchestration of the
+// reference, re-designed around ONE idea: every rotation search of every
+// pullback of every case in a call is a unit of a BATCHED GPU sweep, one launch
+// sequence per search stage (include/mmrs_b200.h: mmrs_sweep_batched).
+//
+// The reference walks frames serially (align_within.rs:72-134): frame i is
+// matched against the already aligned frame i-1. Hausdorff distance is invariant
+// under a common rigid motion and all rotations share one centre, so the cost
+// curve of frame pair (i-1, i) does not depend on the chain: it is
+// H(P[i-1] - c[i-1], R(theta) (P[i] - c[i])). The sweep therefore runs on
+// "decoupled" units built from the ORIGINAL frames, all at once. Rounding makes
+// the decoupled f64 costs differ from the chain's by ~1e-14 relative, so a unit's
+// arg-min is accepted only when no other rechecked candidate lies within
+// kTieMargin of it ("certified"); otherwise the search of that frame is redone
+// on the chain's own points, in order, with the exact (tie_margin = 0) sweep —
+// which is the reference's arithmetic literally. The chain itself (rigid motions
+// of every contour, logs, cumulative angle) is replayed on the host in f64.
+//
+// Data model: structure-of-arrays contours (x[], y[], z[], ...) so that sample
+// extraction into sweep batches is a strided gather; this is a different layout
+// from the reference's Vec<ContourPoint> (src/types/native/contour_point.rs:55-67)
+// but carries the same fields, and the blob codec maps one to the other.
+// =============================================================================
+#include <algorithm>
+#include <array>
+#include <cerrno>
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mmrs_internal.hpp"
+
+namespace {
+
+using std::size_t;
+constexpr double kPi = 3.14159265358979323846264338327950288;
+// Certification margin (multiplied by max(1, Rmax) on the device): 5 orders of
+// magnitude above the worst-case decoupled-vs-chain rounding gap.
+constexpr double kTieMargin = 1e-9;
+
+struct InputErr : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline double rad2deg(double r) { return r * (180.0 / kPi); }
+inline double rem_euclid(double a, double b) {
+    double r = std::fmod(a, b);
+    return (r < 0.0) ? r + std::fabs(b) : r;
+}
+inline size_t as_usize(double v) {
+    if (!(v == v) || v <= 0.0) return 0;
+    if (v >= 18446744073709551615.0) return std::numeric_limits<size_t>::max();
+    return (size_t)v;
+}
+
+enum Kind : int { kLumen = 0, kEem = 1, kCalc = 2, kSide = 3, kCatheter = 4, kWall = 5 };
+
+// ---- SoA contour ------------------------------------------------------------------
+struct Contour {
+    int kind = kLumen;
+    uint32_t id = 0, original_frame = 0;
+    std::vector<uint32_t> fi, pi;  // frame_index, point_index
+    std::vector<double> x, y, z;
+    std::vector<uint8_t> ao;  // aortic
+    bool has_c = false;
+    double c[3] = {0, 0, 0};
+    bool has_at = false, has_pt = false;
+    double at = 0, pt = 0;  // aortic / pulmonary thickness
+
+    size_t size() const { return x.size(); }
+    void push(uint32_t f, uint32_t p, double px, double py, double pz, bool a) {
+        fi.push_back(f);
+        pi.push_back(p);
+        x.push_back(px);
+        y.push_back(py);
+        z.push_back(pz);
+        ao.push_back(a ? 1 : 0);
+    }
+    void resize(size_t n) {
+        fi.resize(n);
+        pi.resize(n);
+        x.resize(n);
+        y.resize(n);
+        z.resize(n);
+        ao.resize(n);
+    }
+    // Contour::compute_centroid, contour.rs:213-224 (sequential left fold)
+    void centroid() {
+        if (x.empty()) {
+            has_c = false;
+            return;
+        }
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (size_t i = 0; i < x.size(); ++i) {
+            sx = sx + x[i];
+            sy = sy + y[i];
+            sz = sz + z[i];
+        }
+        const double n = (double)x.size();
+        c[0] = sx / n, c[1] = sy / n, c[2] = sz / n;
+        has_c = true;
+    }
+    void shift(double dx, double dy, double dz) {  // contour_point.rs:29-36
+        for (size_t i = 0; i < x.size(); ++i) {
+            x[i] = x[i] + dx;
+            y[i] = y[i] + dy;
+            z[i] = z[i] + dz;
+        }
+    }
+    void spin(double angle, double cx, double cy) {  // contour_point.rs:38-52, cos/sin hoisted (same values)
+        if (angle == 0.0) return;
+        const double ca = std::cos(angle), sa = std::sin(angle);
+        for (size_t i = 0; i < x.size(); ++i) {
+            const double px = x[i] - cx, py = y[i] - cy;
+            x[i] = px * ca - py * sa + cx;
+            y[i] = px * sa + py * ca + cy;
+        }
+    }
+    void permute(const std::vector<size_t>& order) {
+        Contour t = *this;
+        for (size_t i = 0; i < order.size(); ++i) {
+            const size_t s = order[i];
+            fi[i] = t.fi[s], pi[i] = t.pi[s], x[i] = t.x[s], y[i] = t.y[s], z[i] = t.z[s], ao[i] = t.ao[s];
+        }
+    }
+    // Contour::sort_contour_points, contour.rs:368-405: stable ascending atan2 about the
+    // mean, the LAST highest-y point rotated to the front, point_index = position.
+    void sort_ccw() {
+        const size_t n = x.size();
+        if (n == 0) return;
+        double sx = 0.0, sy = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            sx = sx + x[i];
+            sy = sy + y[i];
+        }
+        const double mx = sx / (double)n, my = sy / (double)n;
+        std::vector<double> key(n);
+        for (size_t i = 0; i < n; ++i) key[i] = std::atan2(y[i] - my, x[i] - mx);
+        std::vector<size_t> order(n);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key[a] < key[b]; });
+        size_t start = 0;
+        for (size_t i = 1; i < n; ++i)
+            if (!(y[order[i]] < y[order[start]])) start = i;
+        std::rotate(order.begin(), order.begin() + start, order.end());
+        permute(order);
+        for (size_t i = 0; i < n; ++i) pi[i] = (uint32_t)i;
+    }
+};
+
+struct RefPoint {
+    uint32_t fi = 0, pi = 0;
+    double x = 0, y = 0, z = 0;
+    bool ao = false;
+};
+
+struct Frame {
+    uint32_t id = 0;
+    double c[3] = {0, 0, 0};
+    Contour lumen;
+    std::map<int, Contour> extras;
+    bool has_ref = false;
+    RefPoint ref;
+
+    Contour* extra(int k) {
+        auto it = extras.find(k);
+        return it == extras.end() ? nullptr : &it->second;
+    }
+    const Contour* extra(int k) const {
+        auto it = extras.find(k);
+        return it == extras.end() ? nullptr : &it->second;
+    }
+    void shift(double dx, double dy, double dz) {  // Frame::translate, frame.rs:18-38
+        lumen.shift(dx, dy, dz);
+        lumen.centroid();
+        for (auto& kv : extras) {
+            kv.second.shift(dx, dy, dz);
+            kv.second.centroid();
+        }
+        if (has_ref) {
+            ref.x = ref.x + dx;
+            ref.y = ref.y + dy;
+            ref.z = ref.z + dz;
+        }
+        c[0] += dx, c[1] += dy, c[2] += dz;
+    }
+    void spin(double angle, double cx, double cy) {  // Frame::rotate, frame.rs:40-63
+        if (angle == 0.0) return;
+        lumen.spin(angle, cx, cy);
+        for (auto& kv : extras) kv.second.spin(angle, cx, cy);
+        const double ca = std::cos(angle), sa = std::sin(angle);
+        if (has_ref) {
+            const double px = ref.x - cx, py = ref.y - cy;
+            ref.x = px * ca - py * sa + cx;
+            ref.y = px * sa + py * ca + cy;
+        }
+        const double px = c[0] - cx, py = c[1] - cy;
+        c[0] = px * ca - py * sa + cx;
+        c[1] = px * sa + py * ca + cy;
+    }
+    void sort_points() {
+        lumen.sort_ccw();
+        for (auto& kv : extras) kv.second.sort_ccw();
+    }
+};
+
+struct Geometry {
+    std::vector<Frame> frames;
+    std::string label;
+    size_t proximal_idx() const {  // geometry.rs:42-60
+        const size_t n = frames.size();
+        if (n == 0) return 0;
+        if (n == 1) return frames[0].lumen.id;
+        return frames[0].lumen.original_frame > frames[n - 1].lumen.original_frame ? frames[0].lumen.id
+                                                                                  : frames[n - 1].lumen.id;
+    }
+    size_t ref_or_proximal() const {  // find_ref_frame_idx().unwrap_or(find_proximal_end_idx())
+        for (auto& f : frames)
+            if (f.has_ref) return f.id;
+        return proximal_idx();
+    }
+    void shift_all(double dx, double dy, double dz) {  // translate_geometry, geometry.rs:278-283
+        for (auto& f : frames) f.shift(dx, dy, dz);
+    }
+    void renumber() {  // tail of insert_frame, geometry.rs:299-322
+        for (size_t i = 0; i < frames.size(); ++i) {
+            Frame& f = frames[i];
+            const uint32_t id = (uint32_t)i;
+            f.id = id;
+            f.lumen.id = id;
+            std::fill(f.lumen.fi.begin(), f.lumen.fi.end(), id);
+            for (auto& kv : f.extras) {
+                kv.second.id = id;
+                std::fill(kv.second.fi.begin(), kv.second.fi.end(), id);
+            }
+            if (f.has_ref) f.ref.fi = id;
+        }
+    }
+};
+
+// ---- blob codec (layout: include/mmrs_b200.h "geometry blob") -----------------------
+struct Reader {
+    const double* p;
+    const double* e;
+    double get() {
+        if (p >= e) throw InputErr("geometry blob truncated");
+        return *p++;
+    }
+};
+Contour read_contour(Reader& r) {
+    Contour c;
+    c.kind = (int)r.get();
+    c.id = (uint32_t)r.get();
+    c.original_frame = (uint32_t)r.get();
+    c.has_c = r.get() != 0.0;
+    c.c[0] = r.get(), c.c[1] = r.get(), c.c[2] = r.get();
+    c.has_at = r.get() != 0.0;
+    c.at = r.get();
+    c.has_pt = r.get() != 0.0;
+    c.pt = r.get();
+    const size_t n = (size_t)r.get();
+    if ((size_t)(r.e - r.p) < 6 * n) throw InputErr("geometry blob truncated");
+    c.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        c.fi[i] = (uint32_t)r.p[0], c.pi[i] = (uint32_t)r.p[1];
+        c.x[i] = r.p[2], c.y[i] = r.p[3], c.z[i] = r.p[4];
+        c.ao[i] = r.p[5] != 0.0;
+        r.p += 6;
+    }
+    return c;
+}
+Geometry decode(const double* data, int64_t len) {
+    if (!data || len < 1) throw InputErr("geometry blob is empty");
+    Reader r{data, data + len};
+    Geometry g;
+    const size_t nf = (size_t)r.get();
+    g.frames.reserve(nf);
+    for (size_t k = 0; k < nf; ++k) {
+        Frame f;
+        f.id = (uint32_t)r.get();
+        f.c[0] = r.get(), f.c[1] = r.get(), f.c[2] = r.get();
+        f.has_ref = r.get() != 0.0;
+        f.ref.fi = (uint32_t)r.get(), f.ref.pi = (uint32_t)r.get();
+        f.ref.x = r.get(), f.ref.y = r.get(), f.ref.z = r.get();
+        f.ref.ao = r.get() != 0.0;
+        const size_t nc = (size_t)r.get();
+        for (size_t q = 0; q < nc; ++q) {
+            Contour c = read_contour(r);
+            if (q == 0)
+                f.lumen = std::move(c);
+            else
+                f.extras[c.kind] = std::move(c);
+        }
+        g.frames.push_back(std::move(f));
+    }
+    return g;
+}
+void write_contour(std::vector<double>& o, const Contour& c) {
+    const double h[12] = {(double)c.kind, (double)c.id,        (double)c.original_frame, c.has_c ? 1.0 : 0.0,
+                          c.has_c ? c.c[0] : 0.0, c.has_c ? c.c[1] : 0.0, c.has_c ? c.c[2] : 0.0, c.has_at ? 1.0 : 0.0,
+                          c.has_at ? c.at : 0.0, c.has_pt ? 1.0 : 0.0, c.has_pt ? c.pt : 0.0, (double)c.size()};
+    o.insert(o.end(), h, h + 12);
+    for (size_t i = 0; i < c.size(); ++i) {
+        const double p[6] = {(double)c.fi[i], (double)c.pi[i], c.x[i], c.y[i], c.z[i], c.ao[i] ? 1.0 : 0.0};
+        o.insert(o.end(), p, p + 6);
+    }
+}
+std::vector<double> encode(const Geometry& g) {
+    std::vector<double> o;
+    o.push_back((double)g.frames.size());
+    for (auto& f : g.frames) {
+        const double h[11] = {(double)f.id, f.c[0], f.c[1], f.c[2], f.has_ref ? 1.0 : 0.0,
+                              f.has_ref ? (double)f.ref.fi : 0.0, f.has_ref ? (double)f.ref.pi : 0.0,
+                              f.has_ref ? f.ref.x : 0.0, f.has_ref ? f.ref.y : 0.0, f.has_ref ? f.ref.z : 0.0,
+                              (f.has_ref && f.ref.ao) ? 1.0 : 0.0};
+        o.insert(o.end(), h, h + 11);
+        o.push_back((double)(1 + f.extras.size()));
+        write_contour(o, f.lumen);
+        for (auto& kv : f.extras) write_contour(o, kv.second);
+    }
+    return o;
+}
+double* to_malloc(const std::vector<double>& v) {
+    double* p = (double*)std::malloc(std::max<size_t>(v.size(), 1) * sizeof(double));
+    if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(double));
+    return p;
+}
+
+// =============================================================================
+// Ingest (io/input.rs, io/build.rs, geometry.rs reorder / proximal, integrity_check.rs)
+// =============================================================================
+struct RawPoint {
+    uint32_t frame;
+    double x, y, z;
+    bool aortic;
+};
+struct Rec {
+    uint32_t frame;
+    bool diastole_phase, systole_phase;
+    bool has1, has2;
+    double m1, m2;
+};
+struct Input {
+    std::vector<RawPoint> lumen;
+    bool has_eem = false, has_calc = false, has_side = false, has_rec = false;
+    std::vector<RawPoint> eem, calc, side;
+    std::vector<Rec> rec;
+    RawPoint ref{};
+};
+
+std::string strip(const std::string& s) {
+    const size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+std::vector<std::string> fields_of(const std::string& line, char delim) {
+    std::vector<std::string> out(1);
+    for (char ch : line) {
+        if (ch == delim)
+            out.emplace_back();
+        else if (ch != '\r')
+            out.back().push_back(ch);
+    }
+    return out;
+}
+bool to_u32(const std::string& s, uint32_t& v) {
+    if (s.empty() || s[0] == '-' || s[0] == '+') return false;
+    char* end = nullptr;
+    errno = 0;
+    const unsigned long long t = std::strtoull(s.c_str(), &end, 10);
+    if (errno || *end || t > 0xffffffffull) return false;
+    v = (uint32_t)t;
+    return true;
+}
+bool to_f64(const std::string& s, double& v) {
+    if (s.empty()) return false;
+    char* end = nullptr;
+    v = std::strtod(s.c_str(), &end);
+    return *end == '\0';
+}
+bool exists(const std::string& p) { return (bool)std::ifstream(p); }
+char sniff(const std::string& path) {  // input.rs:149-170
+    std::ifstream f(path);
+    if (!f) throw InputErr("failed to open file for delimiter sniffing: \"" + path + "\"");
+    std::string first;
+    std::getline(f, first);
+    return std::count(first.begin(), first.end(), '\t') > std::count(first.begin(), first.end(), ',') ? '\t' : ',';
+}
+bool row_to_point(const std::vector<std::string>& f, RawPoint& p) {
+    if (f.size() < 4 || f.size() > 5) return false;
+    if (!to_u32(strip(f[0]), p.frame) || !to_f64(strip(f[1]), p.x) || !to_f64(strip(f[2]), p.y) ||
+        !to_f64(strip(f[3]), p.z))
+        return false;
+    p.aortic = false;
+    if (f.size() == 5) {
+        const std::string b = strip(f[4]);
+        if (b == "true")
+            p.aortic = true;
+        else if (b != "false")
+            return false;
+    }
+    return true;
+}
+std::vector<RawPoint> read_points(const std::string& path) {  // input.rs:172-194
+    const char d = sniff(path);
+    std::ifstream f(path);
+    std::vector<RawPoint> out;
+    std::string line;
+    size_t width = 0;
+    while (std::getline(f, line)) {
+        if (strip(line).empty()) continue;
+        auto fl = fields_of(line, d);
+        if (!width) width = fl.size();
+        RawPoint p;
+        if (fl.size() == width && row_to_point(fl, p)) out.push_back(p);
+    }
+    return out;
+}
+Input read_directory(const std::string& dir, bool diastole) {  // input.rs:62-147 + build.rs:20-27
+    Input in;
+    const std::string phase = diastole ? "diastolic" : "systolic";
+    const std::string cp = dir + "/" + phase + "_contours.csv";
+    if (!exists(cp)) throw InputErr("required contours file missing: \"" + cp + "\"");
+    in.lumen = read_points(cp);
+    const std::string rp = dir + "/" + phase + "_reference_points.csv";
+    if (!exists(rp)) throw InputErr("required reference-point file missing: \"" + rp + "\"");
+    {
+        const char d = sniff(rp);
+        std::ifstream f(rp);
+        std::string line;
+        bool got = false;
+        while (std::getline(f, line)) {
+            if (strip(line).empty()) continue;
+            if (!row_to_point(fields_of(line, d), in.ref))
+                throw InputErr("reading " + rp + ": failed to deserialize first reference-point record");
+            got = true;
+            break;
+        }
+        if (!got) throw InputErr("reference-point file \"" + rp + "\" was empty — this data is required");
+    }
+    auto optional = [&](const char* prefix, std::vector<RawPoint>& dst, bool& has) {
+        const std::string p = dir + "/" + prefix + "_" + phase + "_contours.csv";
+        if (exists(p)) {
+            dst = read_points(p);
+            has = true;
+        }
+    };
+    optional("branch", in.side, in.has_side);
+    optional("calcium", in.calc, in.has_calc);
+    optional("eem", in.eem, in.has_eem);
+    std::string rec = dir + "/combined_sorted_manual.csv";
+    if (!exists(rec)) rec = dir + "/diastolic_systolic_records.csv";
+    if (exists(rec)) {  // input.rs:237-251, Record (record.rs:3-11) by header name
+        const char d = sniff(rec);
+        std::ifstream f(rec);
+        std::string line;
+        if (std::getline(f, line)) {
+            auto hdr = fields_of(line, d);
+            int cf = -1, cph = -1, c1 = -1, c2 = -1;
+            for (size_t i = 0; i < hdr.size(); ++i) {
+                const std::string h = strip(hdr[i]);
+                if (h == "frame") cf = (int)i;
+                if (h == "phase") cph = (int)i;
+                if (h == "measurement_1") c1 = (int)i;
+                if (h == "measurement_2") c2 = (int)i;
+            }
+            if (cf < 0 || cph < 0 || c1 < 0 || c2 < 0) throw InputErr("reading " + rec + ": missing field");
+            while (std::getline(f, line)) {
+                if (strip(line).empty()) continue;
+                auto fl = fields_of(line, d);
+                if (fl.size() != hdr.size()) throw InputErr("reading " + rec + ": unequal record length");
+                Rec r{};
+                if (!to_u32(strip(fl[cf]), r.frame)) throw InputErr("reading " + rec + ": invalid frame");
+                r.diastole_phase = fl[cph] == "D";
+                r.systole_phase = fl[cph] == "S";
+                r.has1 = to_f64(strip(fl[c1]), r.m1);
+                r.has2 = to_f64(strip(fl[c2]), r.m2);
+                in.rec.push_back(r);
+            }
+        }
+        in.has_rec = true;
+    }
+    return in;
+}
+
+void integrity(const Geometry& g) {  // integrity_check.rs:8-247
+    if (g.frames.empty()) throw InputErr("Geometry has no frames");
+    for (size_t i = 0; i < g.frames.size(); ++i)
+        if (g.frames[i].id != i)
+            throw InputErr("Frame IDs are not consecutive. Expected ID " + std::to_string(i) + ", found ID " +
+                           std::to_string(g.frames[i].id));
+    auto near = [](double a, double b) { return std::fabs(a - b) < 1e-6; };
+    for (auto& f : g.frames) {
+        double l[3] = {0, 0, 0};
+        if (f.lumen.has_c)
+            std::copy(f.lumen.c, f.lumen.c + 3, l);
+        else {
+            Contour t = f.lumen;
+            t.centroid();
+            if (t.has_c) std::copy(t.c, t.c + 3, l);
+        }
+        if (!(near(f.c[0], l[0]) && near(f.c[1], l[1]) && near(f.c[2], l[2])))
+            throw InputErr("Frame centroid does not match lumen centroid in frame " + std::to_string(f.id));
+    }
+    for (auto& f : g.frames) {
+        if (f.lumen.size() == 0) throw InputErr("Lumen contour has no points in frame " + std::to_string(f.id));
+        if (f.lumen.kind != kLumen) throw InputErr("Lumen contour has incorrect type in frame " + std::to_string(f.id));
+    }
+    size_t nref = 0;
+    for (auto& f : g.frames) nref += f.has_ref;
+    if (nref != 1) throw InputErr("Expected exactly one reference point, found " + std::to_string(nref));
+    std::map<int, size_t> want;
+    for (auto& f : g.frames) {
+        auto chk = [&](int k, size_t n) {
+            auto it = want.find(k);
+            if (it == want.end())
+                want[k] = n;
+            else if (it->second != n)
+                throw InputErr("contour point count mismatch in frame " + std::to_string(f.id) + ". Expected " +
+                               std::to_string(it->second) + ", found " + std::to_string(n));
+        };
+        chk(kLumen, f.lumen.size());
+        for (auto& kv : f.extras) chk(kv.second.kind, kv.second.size());
+    }
+    for (auto& f : g.frames) {
+        for (auto& kv : f.extras)
+            if (kv.second.original_frame != f.lumen.original_frame)
+                throw InputErr("Original frame mismatch in frame " + std::to_string(f.id));
+        if (f.has_ref && f.ref.fi != f.lumen.original_frame)
+            throw InputErr("Reference point original frame mismatch in frame " + std::to_string(f.id));
+    }
+    size_t min_idx = 0;
+    double min_z = std::numeric_limits<double>::infinity();
+    for (size_t i = 0; i < g.frames.size(); ++i)
+        if (g.frames[i].c[2] < min_z) min_z = g.frames[i].c[2], min_idx = i;
+    if (g.proximal_idx() != min_idx)
+        throw InputErr("Proximal end index is " + std::to_string(g.proximal_idx()) +
+                       ", but frame with minimum z is " + std::to_string(min_idx));
+    if (g.frames.front().c[2] > g.frames.back().c[2]) throw InputErr("First frame has higher z-coords than last frame");
+}
+
+Geometry build_geometry(const Input& in, const std::string& label, bool diastole, double icx, double icy, double radius,
+                        uint32_t n_points) {  // build.rs:9-205
+    std::set<uint32_t> seen;
+    for (auto& p : in.lumen) seen.insert(p.frame);
+    if (in.has_eem)
+        for (auto& p : in.eem) seen.insert(p.frame);
+    if (in.has_calc)
+        for (auto& p : in.calc) seen.insert(p.frame);
+    if (in.has_side)
+        for (auto& p : in.side) seen.insert(p.frame);
+    seen.insert(in.ref.frame);
+    std::map<uint32_t, uint32_t> slot;  // original frame -> sequential id
+    for (uint32_t f : seen) slot.emplace(f, (uint32_t)slot.size());
+
+    // group by original frame (Contour::build_contour_with_mapping, contour.rs:158-211)
+    auto group = [&](const std::vector<RawPoint>& pts, int kind) {
+        std::map<uint32_t, Contour> by;
+        for (auto& p : pts) {
+            Contour& c = by[p.frame];
+            c.push(p.frame, 0, p.x, p.y, p.z, p.aortic);
+        }
+        for (auto& kv : by) {
+            auto s = slot.find(kv.first);
+            if (s == slot.end()) throw InputErr("No mapping found for original frame " + std::to_string(kv.first));
+            kv.second.kind = kind;
+            kv.second.id = s->second;
+            kv.second.original_frame = kv.first;
+        }
+        return by;
+    };
+    std::map<uint32_t, Frame> by_id;
+    {
+        auto lum = group(in.lumen, kLumen);
+        std::map<uint32_t, const Rec*> meas;
+        if (in.has_rec)
+            for (auto& r : in.rec) meas[r.frame] = &r;  // later rows overwrite earlier ones
+        for (auto& kv : lum) {
+            Contour& c = kv.second;
+            auto m = meas.find(kv.first);
+            if (m != meas.end()) {
+                c.has_at = m->second->has1, c.at = m->second->m1;
+                c.has_pt = m->second->has2, c.pt = m->second->m2;
+            }
+            c.centroid();
+            Frame f;
+            f.id = c.id;
+            if (c.has_c) std::copy(c.c, c.c + 3, f.c);
+            auto rs = slot.find(in.ref.frame);
+            if (rs != slot.end() && rs->second == f.id) {
+                f.has_ref = true;
+                f.ref = RefPoint{in.ref.frame, 0, in.ref.x, in.ref.y, in.ref.z, in.ref.aortic};
+            }
+            f.lumen = std::move(c);
+            by_id[f.id] = std::move(f);
+        }
+    }
+    auto attach = [&](const std::vector<RawPoint>& pts, int kind) {
+        for (auto& kv : group(pts, kind)) {
+            kv.second.centroid();
+            auto it = by_id.find(kv.second.id);
+            if (it != by_id.end()) it->second.extras[kind] = std::move(kv.second);
+        }
+    };
+    if (in.has_eem) attach(in.eem, kEem);
+    if (in.has_calc) attach(in.calc, kCalc);
+    if (in.has_side) attach(in.side, kSide);
+    if (n_points > 0) {  // Frame::create_catheter_points, frame.rs:163-204
+        std::map<uint32_t, double> z_of;
+        for (auto& kv : by_id) {
+            const Contour& l = kv.second.lumen;
+            for (size_t i = 0; i < l.size(); ++i) z_of.emplace(l.fi[i], l.z[i]);
+        }
+        std::vector<RawPoint> cath;
+        for (auto& kv : z_of)
+            for (uint32_t i = 0; i < n_points; ++i) {
+                const double a = 2.0 * kPi * (double)i / (double)n_points;
+                cath.push_back(RawPoint{kv.first, icx + radius * std::cos(a), icy + radius * std::sin(a), kv.second, false});
+            }
+        auto by = group(cath, kCatheter);
+        for (auto& kv : by) {
+            for (size_t i = 0; i < kv.second.size(); ++i) kv.second.pi[i] = (uint32_t)i;
+            kv.second.centroid();
+            auto it = by_id.find(kv.second.id);
+            if (it != by_id.end()) it->second.extras[kCatheter] = std::move(kv.second);
+        }
+    }
+    Geometry g;
+    g.label = label;
+    for (auto& kv : by_id) g.frames.push_back(std::move(kv.second));
+
+    if (in.has_rec) {  // Geometry::reorder_frames, geometry.rs:72-155
+        std::map<uint32_t, double> z_orig;
+        for (auto& f : g.frames)
+            if (f.lumen.size()) z_orig.emplace(f.lumen.original_frame, f.lumen.z[0]);
+        std::map<uint32_t, Frame> pool;
+        for (auto& f : g.frames) pool[f.lumen.original_frame] = std::move(f);
+        std::vector<Frame> ordered;
+        for (auto& r : in.rec) {
+            if (!(diastole ? r.diastole_phase : r.systole_phase)) continue;
+            auto it = pool.find(r.frame);
+            if (it != pool.end()) {
+                ordered.push_back(std::move(it->second));
+                pool.erase(it);
+            }
+        }
+        for (auto& kv : pool) ordered.push_back(std::move(kv.second));
+        for (size_t i = 0; i < ordered.size(); ++i) {
+            Frame& f = ordered[i];
+            const uint32_t id = (uint32_t)i;
+            auto zi = z_orig.find(f.lumen.original_frame);
+            const double z = zi != z_orig.end() ? zi->second : (double)id;
+            f.id = id;
+            auto fix = [&](Contour& c) {
+                c.id = id;
+                std::fill(c.fi.begin(), c.fi.end(), id);
+                std::fill(c.z.begin(), c.z.end(), z);
+                if (c.has_c) c.c[2] = z;
+            };
+            fix(f.lumen);
+            for (auto& kv : f.extras) fix(kv.second);
+            if (f.has_ref) f.ref.z = z;
+            f.c[2] = z;
+        }
+        g.frames = std::move(ordered);
+    }
+    for (auto& f : g.frames) f.sort_points();
+    {  // ensure_proximal_at_position_zero, geometry.rs:325-381
+        const size_t n = g.frames.size();
+        if (n) {
+            if (std::min(g.proximal_idx(), n - 1) != 0) std::reverse(g.frames.begin(), g.frames.end());
+            std::vector<double> zs;
+            for (auto& f : g.frames) zs.push_back(f.c[2]);
+            std::stable_sort(zs.begin(), zs.end());
+            for (size_t i = 0; i < n; ++i) {
+                Frame& f = g.frames[i];
+                f.id = (uint32_t)i;
+                f.c[2] = zs[i];
+                auto fix = [&](Contour& c) {
+                    c.id = (uint32_t)i;  // final value after Frame::set_value(Some(id)), build.rs:190-193
+                    std::fill(c.z.begin(), c.z.end(), zs[i]);
+                    if (c.has_c) c.c[2] = zs[i];
+                };
+                fix(f.lumen);
+                for (auto& kv : f.extras) fix(kv.second);
+                if (f.has_ref) f.ref.z = zs[i];
+            }
+        }
+    }
+    integrity(g);
+    return g;
+}
+
+// =============================================================================
+// Sweep plumbing
+// =============================================================================
+struct SweepUnits {
+    std::vector<double> test, ref, centre;
+    std::vector<int64_t> toff{0}, roff{0};
+    size_t count() const { return toff.size() - 1; }
+    void close_unit(double cx, double cy) {
+        toff.push_back((int64_t)test.size() / 2);
+        roff.push_back((int64_t)ref.size() / 2);
+        centre.push_back(cx);
+        centre.push_back(cy);
+    }
+};
+
+struct Searcher {
+    mmrs_ctx* ctx;
+    int64_t* stats;
+    void check(int rc) {
+        if (rc != MMRS_OK) throw std::runtime_error(mmrs_last_error(ctx));
+    }
+    // One stage for a batch of units. `centres` empty => centre None for every unit
+    // (one shared grid); otherwise one grid per unit. Returns per-unit results.
+    std::vector<mmrs_unit_result> stage(const SweepUnits& u, int mode, double step_deg, double window_deg,
+                                        double limes_deg, const std::vector<double>& centres, double tie_margin) {
+        const size_t U = u.count();
+        std::vector<mmrs_unit_result> out(U);
+        if (U == 0) return out;
+        std::vector<mmrs_grid> grids;
+        std::vector<int32_t> which;
+        if (centres.empty()) {
+            grids.resize(1);
+            check(mmrs_grid_from_reference_params(step_deg, window_deg, 0, 0.0, limes_deg, &grids[0]));
+        } else {
+            grids.resize(U);
+            which.resize(U);
+            for (size_t i = 0; i < U; ++i) {
+                check(mmrs_grid_from_reference_params(step_deg, window_deg, 1, centres[i], limes_deg, &grids[i]));
+                which[i] = (int32_t)i;
+            }
+        }
+        mmrs_sweep_batch b{};
+        b.n_units = (int64_t)U;
+        b.test_xy = u.test.data();
+        b.test_off = u.toff.data();
+        b.ref_xy = u.ref.data();
+        b.ref_off = u.roff.data();
+        b.centre_xy = u.centre.data();
+        b.grids = grids.data();
+        b.n_grids = (int64_t)grids.size();
+        b.grid_of_unit = which.empty() ? nullptr : which.data();
+        b.mode = mode;
+        mmrs_sweep_opts o{};
+        o.tie_margin = tie_margin;
+        check(mmrs_sweep_batched(ctx, &b, &o, out.data()));
+        stats[0] += (int64_t)U;
+        for (size_t i = 0; i < U; ++i) {
+            stats[1] += grids[which.empty() ? 0 : i].degenerate ? 0 : grids[which.empty() ? 0 : i].n_cand;
+            stats[2] += out[i].n_shortlist > 0 ? out[i].n_shortlist : 0;
+        }
+        stats[4] += ctx->launches + ctx->upload_launches;
+        return out;
+    }
+};
+
+// The stage list of a search: brute force = one stage (step, range, None); otherwise
+// find_best_rotation's plan (align_within.rs:208-246 == align_between.rs:219-257).
+struct Plan {
+    int n = 0;
+    double step[4], window[4];
+};
+Plan make_plan(double step_deg, double range_deg, bool bruteforce) {
+    Plan p;
+    if (bruteforce) {
+        p.n = 1;
+        p.step[0] = step_deg;
+        p.window[0] = range_deg;
+    } else {
+        p.n = mmrs_stage_plan(step_deg, range_deg, p.step, p.window);
+    }
+    return p;
+}
+
+// downsample_contour_points, contour.rs:47-58
+std::vector<size_t> stride_pick(size_t len, size_t n) {
+    std::vector<size_t> idx;
+    if (len <= n) {
+        idx.resize(len);
+        std::iota(idx.begin(), idx.end(), 0);
+        return idx;
+    }
+    const double step = (double)len / (double)n;
+    idx.resize(n);
+    for (size_t i = 0; i < n; ++i) idx[i] = as_usize((double)i * step);
+    return idx;
+}
+
+// catheter_lumen_vec_from_frames, align_within.rs:173-191 — appended as (x - ox, y - oy)
+void gather_frame_sample(const Frame& f, size_t n_lumen, bool use_cath, size_t n_cath, double ox, double oy,
+                         std::vector<double>& dst) {
+    for (size_t i : stride_pick(f.lumen.size(), n_lumen)) {
+        dst.push_back(f.lumen.x[i] - ox);
+        dst.push_back(f.lumen.y[i] - oy);
+    }
+    if (use_cath)
+        if (const Contour* c = f.extra(kCatheter))
+            for (size_t i : stride_pick(c->size(), n_cath)) {
+                dst.push_back(c->x[i] - ox);
+                dst.push_back(c->y[i] - oy);
+            }
+}
+
+// =============================================================================
+// Post steps of align_frames_in_geometry (align_within.rs:136-158)
+// =============================================================================
+double dist3(const Contour& c, size_t i, size_t j) {
+    const double dx = c.x[i] - c.x[j], dy = c.y[i] - c.y[j], dz = c.z[i] - c.z[j];
+    return std::sqrt(dx * dx + dy * dy + dz * dz);
+}
+void farthest_pair(const Contour& c, size_t& bi, size_t& bj, double& best) {  // contour.rs:227-243
+    best = 0.0, bi = 0, bj = 0;
+    for (size_t i = 0; i < c.size(); ++i)
+        for (size_t j = i + 1; j < c.size(); ++j) {
+            const double d = dist3(c, i, j);
+            if (d > best) best = d, bi = i, bj = j;
+        }
+}
+double elliptic_ratio(const Contour& c) {  // contour.rs:313-343
+    size_t i, j;
+    double major;
+    farthest_pair(c, i, j, major);
+    const size_t n = c.size();
+    if (n <= 2) throw InputErr("Need at least 3 points");
+    double minor = std::numeric_limits<double>::max();
+    for (size_t a = 0; a < n; ++a) minor = std::min(minor, dist3(c, a, (a + n / 2) % n));
+    return major < minor ? minor / major : major / minor;
+}
+
+Contour blend(const Contour& a, const Contour& b, double t, bool average, uint32_t id, uint32_t of) {
+    // average: avg_contour (align_within.rs:476-497); else fill_frame_gap (:573-598)
+    Contour o;
+    o.kind = a.kind;
+    o.id = id;
+    o.original_frame = of;
+    const size_t n = std::min(a.size(), b.size());
+    for (size_t i = 0; i < n; ++i) {
+        if (average)
+            o.push(of, (uint32_t)i, (a.x[i] + b.x[i]) / 2.0, (a.y[i] + b.y[i]) / 2.0, (a.z[i] + b.z[i]) / 2.0,
+                   a.ao[i] || b.ao[i]);
+        else
+            o.push(of, (uint32_t)i, a.x[i] + (b.x[i] - a.x[i]) * t, a.y[i] + (b.y[i] - a.y[i]) * t,
+                   a.z[i] + (b.z[i] - a.z[i]) * t, a.ao[i] || b.ao[i]);
+    }
+    if (a.has_c && b.has_c) {
+        o.has_c = true;
+        for (int k = 0; k < 3; ++k) o.c[k] = average ? (a.c[k] + b.c[k]) / 2.0 : a.c[k] + (b.c[k] - a.c[k]) * t;
+    } else if (a.has_c || b.has_c) {
+        o.has_c = true;
+        std::copy(a.has_c ? a.c : b.c, (a.has_c ? a.c : b.c) + 3, o.c);
+    }
+    auto mix = [&](bool ha, double va, bool hb, double vb, bool& ho, double& vo) {
+        if (ha && hb)
+            ho = true, vo = average ? (va + vb) / 2.0 : va + (vb - va) * t;
+        else if (ha)
+            ho = true, vo = va;
+        else if (hb)
+            ho = true, vo = vb;
+    };
+    mix(a.has_at, a.at, b.has_at, b.at, o.has_at, o.at);
+    mix(a.has_pt, a.pt, b.has_pt, b.pt, o.has_pt, o.pt);
+    return o;
+}
+Frame bridge(const Frame& a, const Frame& b, double t, bool average) {
+    // average: fix_one_frame_hole (:499-543); else create_interpolated_frame (:600-651)
+    Frame o;
+    for (int k = 0; k < 3; ++k) o.c[k] = average ? (a.c[k] + b.c[k]) / 2.0 : a.c[k] + (b.c[k] - a.c[k]) * t;
+    o.lumen = blend(a.lumen, b.lumen, t, average, b.lumen.id, b.lumen.original_frame);
+    std::set<int> kinds;
+    for (auto& kv : a.extras) kinds.insert(kv.first);
+    for (auto& kv : b.extras) kinds.insert(kv.first);
+    for (int k : kinds) {
+        const Contour *ca = a.extra(k), *cb = b.extra(k);
+        o.extras[k] = (ca && cb) ? blend(*ca, *cb, t, average, cb->id, cb->original_frame) : (ca ? *ca : *cb);
+    }
+    if (!average) {
+        if (a.has_ref && b.has_ref) {
+            o.has_ref = true;
+            o.ref = RefPoint{b.id, 0, a.ref.x + (b.ref.x - a.ref.x) * t, a.ref.y + (b.ref.y - a.ref.y) * t,
+                             a.ref.z + (b.ref.z - a.ref.z) * t, a.ref.ao || b.ref.ao};
+        } else if (a.has_ref || b.has_ref) {
+            o.has_ref = true;
+            o.ref = a.has_ref ? a.ref : b.ref;
+        }
+    }
+    o.id = b.id;
+    return o;
+}
+void fill_holes(Geometry& g) {  // align_within.rs:348-449
+    std::vector<double> gaps;
+    for (size_t i = 1; i < g.frames.size(); ++i) gaps.push_back(std::fabs(g.frames[i].c[2] - g.frames[i - 1].c[2]));
+    if (gaps.empty()) return;
+    std::vector<double> s = gaps;
+    std::sort(s.begin(), s.end());
+    const size_t n = s.size();
+    const double base = (n % 2) ? s[n / 2] : (s[n / 2 - 1] + s[n / 2]) / 2.0;
+    if (base <= std::numeric_limits<double>::epsilon()) return;
+    if (!std::any_of(gaps.begin(), gaps.end(), [&](double d) { return d >= 1.5 * base; })) return;
+    auto insert = [&](Frame f, size_t pos) {
+        g.frames.insert(g.frames.begin() + pos, std::move(f));
+        g.renumber();
+    };
+    size_t i = 1;
+    while (i < g.frames.size()) {
+        const Frame prev = g.frames[i - 1], cur = g.frames[i];
+        const double ratio = std::fabs(cur.c[2] - prev.c[2]) / base;
+        if (ratio < 1.5) {
+            i += 1;
+        } else if (ratio < 2.5) {
+            insert(bridge(prev, cur, 0.5, true), i);
+            i += 2;
+        } else if (ratio < 3.5) {
+            insert(bridge(prev, cur, 1.0 / 3.0, false), i);
+            insert(bridge(prev, cur, 2.0 / 3.0, false), i + 1);
+            i += 3;
+        } else {
+            const size_t missing = as_usize(std::fmax(std::floor(ratio - 1.0), 1.0));
+            for (size_t k = 1; k <= missing; ++k)
+                insert(bridge(prev, cur, (double)k / (double)(missing + 1), false), i + k - 1);
+            i += missing + 1;
+        }
+    }
+}
+double ref_point_to_right(const Frame& f, bool anomalous) {  // align_within.rs:256-317
+    if (!f.has_ref) throw InputErr("No reference point found in frame");
+    double p1[2], p2[2];
+    if (anomalous) {
+        size_t i, j;
+        double d;
+        farthest_pair(f.lumen, i, j, d);
+        p1[0] = f.lumen.x[i], p1[1] = f.lumen.y[i], p2[0] = f.lumen.x[j], p2[1] = f.lumen.y[j];
+    } else {
+        p1[0] = f.c[0], p1[1] = f.c[1], p2[0] = f.ref.x, p2[1] = f.ref.y;
+    }
+    const double line = std::atan2(p2[1] - p1[1], p2[0] - p1[0]);
+    double rot = rem_euclid((anomalous ? kPi / 2.0 : 0.0) - line, 2.0 * kPi);
+    const double ca = std::cos(rot), sa = std::sin(rot);
+    auto rx = [&](double px, double py) {  // x of rotate2(pt, center = p1, rot)
+        const double dx = px - p1[0], dy = py - p1[1];
+        return (dx * ca - dy * sa) + p1[0];
+    };
+    const double ref_x = rx(f.ref.x, f.ref.y);
+    const double eps = std::numeric_limits<double>::epsilon();
+    bool ok = true;
+    for (const double* op : {p1, p2}) {
+        if (std::fabs(op[0] - f.ref.x) <= eps && std::fabs(op[1] - f.ref.y) <= eps) continue;
+        if (ref_x <= rx(op[0], op[1])) {
+            ok = false;
+            break;
+        }
+    }
+    if (!ok) rot = rem_euclid(rot + kPi, 2.0 * kPi);
+    return rot;
+}
+Contour pushed_out(const Contour& src, double dist, bool ranged, uint32_t lo, uint32_t hi) {  // wall.rs:52-103
+    Contour c = src;
+    c.centroid();
+    Contour o = c;
+    o.kind = kWall;
+    for (size_t i = 0; i < c.size(); ++i) {
+        if (ranged && !(c.pi[i] >= lo && c.pi[i] <= hi)) continue;
+        const double dx = c.x[i] - c.c[0], dy = c.y[i] - c.c[1], dz = c.z[i] - c.c[2];
+        const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
+        if (len > std::numeric_limits<double>::epsilon()) {
+            o.x[i] += dx / len * dist;
+            o.y[i] += dy / len * dist;
+            o.z[i] += dz / len * dist;
+        }
+    }
+    return o;
+}
+Contour aortic_wall(const Contour& c) {  // wall.rs:112-210
+    const size_t n = c.size(), q1 = n / 4, half = n / 2, q3 = q1 * 3;
+    if (q3 >= n || half >= n) throw InputErr("index out of bounds (create_aortic_wall)");
+    const double outer_x = c.x[q3] + c.at, z = c.z[q3];
+    const double up_mid[2] = {c.x[0], c.y[0] + 1.0}, up_right[2] = {outer_x, up_mid[1]};
+    const double low_mid[2] = {c.x[half], c.y[half] - 1.0}, low_right[2] = {outer_x, low_mid[1]};
+    const double d_up = std::fabs(up_right[0] - up_mid[0]), d_right = std::fabs(up_right[1] - low_right[1]),
+                 d_low = std::fabs(low_right[0] - low_mid[0]);
+    const double total = d_up + d_right + d_low;
+    const size_t n_up = as_usize(std::round(d_up / total * (double)half));
+    const size_t n_mid = as_usize(std::round(d_right / total * (double)half));
+    if (n_up + n_mid > half) throw InputErr("attempt to subtract with overflow (create_aortic_wall)");
+    const size_t n_low = half - n_up - n_mid;
+    std::vector<double> rxs, rys;
+    for (size_t i = 0; i < n_low; ++i) {
+        const double t = (double)i / (double)(n_low - 1);
+        rxs.push_back(low_mid[0] + t * (low_right[0] - low_mid[0]));
+        rys.push_back(low_mid[1]);
+    }
+    for (size_t i = 0; i < n_mid; ++i) {
+        const double t = (double)i / (double)(n_mid - 1);
+        rxs.push_back(low_right[0]);
+        rys.push_back(low_right[1] + t * (up_right[1] - low_right[1]));
+    }
+    for (size_t i = 0; i < n_up; ++i) {
+        const double t = (double)i / (double)(std::max<size_t>(n_up, 1) - 1);
+        rxs.push_back(up_right[0] - t * (up_right[0] - up_mid[0]));
+        rys.push_back(up_right[1]);
+    }
+    Contour o = pushed_out(c, 1.0, true, 0, (uint32_t)half);
+    o.has_c = c.has_c;
+    std::copy(c.c, c.c + 3, o.c);
+    const size_t left = std::min(o.size(), (o.size() % 2) ? half + 1 : half);
+    o.resize(left);
+    for (size_t i = 0; i < rxs.size(); ++i) {
+        const size_t s = left + i;
+        if (s >= c.size()) throw InputErr("Index out of bounds (create_aortic_wall)");
+        o.push(c.fi[s], c.pi[s], rxs[i], rys[i], z, c.ao[s]);
+    }
+    return o;
+}
+void add_walls(Geometry& g, bool anomalous) {  // wall.rs:7-43
+    for (auto& f : g.frames) {
+        const Contour* eem = f.extra(kEem);
+        const Contour& base = (anomalous || !eem) ? f.lumen : *eem;
+        if (base.has_at)
+            f.extras[kWall] = aortic_wall(base);
+        else {
+            Contour w = pushed_out(base, 1.0, false, 0, 0);
+            f.extras[kWall] = std::move(w);
+        }
+    }
+}
+void smooth(Geometry& g) {  // Geometry::smooth_frames, geometry.rs:165-239
+    const std::vector<Frame> old = g.frames;
+    const size_t nf = old.size();
+    for (size_t i = 0; i < nf; ++i) {
+        const Frame& prev = old[i == 0 ? i : i - 1];
+        const Frame& next = old[i == nf - 1 ? i : i + 1];
+        const size_t count = old[i].lumen.size();
+        auto avg3 = [&](const Contour& cur, const Contour& p, const Contour& n) {
+            if (cur.size() < count || p.size() < count || n.size() < count)
+                throw InputErr("index out of bounds (smooth_frames)");
+            Contour o = cur;
+            o.resize(count);
+            for (size_t j = 0; j < count; ++j) {
+                o.x[j] = (p.x[j] + cur.x[j] + n.x[j]) / 3.0;
+                o.y[j] = (p.y[j] + cur.y[j] + n.y[j]) / 3.0;
+            }
+            o.centroid();
+            return o;
+        };
+        g.frames[i].lumen = avg3(old[i].lumen, prev.lumen, next.lumen);
+        for (int k : {(int)kEem, (int)kWall}) {
+            const Contour *c = old[i].extra(k), *p = prev.extra(k), *n = next.extra(k);
+            if (c && p && n) g.frames[i].extras[k] = avg3(*c, *p, *n);
+        }
+    }
+}
+
+// =============================================================================
+// Intrapullback alignment of MANY pullbacks at once (align_within.rs:24-171)
+// =============================================================================
+struct WithinOut {
+    std::vector<double> logs;  // n x 7
+    bool anomalous = false;
+};
+
+void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_align_params& P,
+                       std::vector<WithinOut>& outs) {
+    const size_t G = geoms.size();
+    outs.assign(G, WithinOut{});
+    struct Meta {
+        size_t first_unit = 0, ref_idx = 0;
+        bool use_cath = false;
+        size_t n_cath = 0;
+    };
+    std::vector<Meta> meta(G);
+    const size_t sample = (size_t)std::max<int64_t>(P.sample_size, 0);
+    // guards (align_within.rs:32-40) and sampling parameters (:42-59)
+    for (size_t g = 0; g < G; ++g) {
+        Geometry& geo = *geoms[g];
+        if (geo.frames.empty()) throw InputErr("Geometry contains no frames");
+        if (geo.frames[0].lumen.size() == 0) throw InputErr("Lumen contours have no points");
+        if (P.sample_size <= 0) throw InputErr("sample_size must be > 0");
+        meta[g].ref_idx = geo.ref_or_proximal();
+        const double ratio = (double)sample / (double)geo.frames[0].lumen.size();
+        if (const Contour* c = geo.frames[0].extra(kCatheter)) {
+            meta[g].use_cath = true;
+            meta[g].n_cath = as_usize(std::ceil((double)c->size() * ratio));
+        }
+    }
+    // 1. decoupled units from the ORIGINAL frames, each centred on its own frame centroid
+    SweepUnits units;
+    for (size_t g = 0; g < G; ++g) {
+        Geometry& geo = *geoms[g];
+        meta[g].first_unit = units.count();
+        for (size_t i = 1; i < geo.frames.size(); ++i) {
+            const Frame &cur = geo.frames[i], &prev = geo.frames[i - 1];
+            gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, cur.c[0], cur.c[1], units.test);
+            gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, prev.c[0], prev.c[1], units.ref);
+            units.close_unit(0.0, 0.0);
+        }
+    }
+    const size_t U = units.count();
+    const Plan plan = make_plan(P.step_deg, P.range_deg, P.bruteforce != 0);
+    // 2. stage-by-stage batched search; a unit stays "certified" while every stage has a unique
+    //    winner by more than kTieMargin
+    std::vector<double> angle(U, 0.0);
+    std::vector<int> good_stages(U, 0);  // number of leading stages certified
+    {
+        std::vector<size_t> live(U);
+        std::iota(live.begin(), live.end(), 0);
+        for (int s = 0; s < plan.n && !live.empty(); ++s) {
+            SweepUnits sub;
+            const SweepUnits* use = &units;
+            std::vector<double> centres;
+            if (live.size() != U) {  // compact the still-certified units
+                for (size_t u : live) {
+                    sub.test.insert(sub.test.end(), units.test.begin() + 2 * units.toff[u],
+                                    units.test.begin() + 2 * units.toff[u + 1]);
+                    sub.ref.insert(sub.ref.end(), units.ref.begin() + 2 * units.roff[u],
+                                   units.ref.begin() + 2 * units.roff[u + 1]);
+                    sub.close_unit(0.0, 0.0);
+                }
+                use = &sub;
+            }
+            if (s > 0)
+                for (size_t u : live) centres.push_back(angle[u]);
+            auto res = S.stage(*use, 0, plan.step[s], plan.window[s], P.range_deg, centres, kTieMargin);
+            std::vector<size_t> next;
+            for (size_t k = 0; k < live.size(); ++k) {
+                const size_t u = live[k];
+                const bool unique = (res[k].flags & MMRS_FLAG_DEGENERATE) || res[k].n_ties == 1;
+                if (unique) {
+                    angle[u] = res[k].best_angle;
+                    good_stages[u] = s + 1;
+                    next.push_back(u);
+                }
+            }
+            live.swap(next);
+        }
+    }
+    // 3. replay the chain on the host; re-search uncertified frames on the chain's own points
+    for (size_t g = 0; g < G; ++g) {
+        Geometry& geo = *geoms[g];
+        double cumulative = 0.0;
+        for (size_t i = 1; i < geo.frames.size(); ++i) {
+            const size_t u = meta[g].first_unit + (i - 1);
+            const Frame& prev = geo.frames[i - 1];
+            Frame& cur = geo.frames[i];
+            if (cumulative != 0.0) cur.spin(cumulative, cur.c[0], cur.c[1]);
+            const double tx = prev.c[0] - cur.c[0], ty = prev.c[1] - cur.c[1];
+            cur.shift(tx, ty, 0.0);
+            double best = angle[u];
+            if (good_stages[u] < plan.n) {
+                SweepUnits one;
+                gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.test);
+                gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.ref);
+                one.close_unit(cur.c[0], cur.c[1]);
+                for (int s = good_stages[u]; s < plan.n; ++s) {
+                    std::vector<double> centres;
+                    if (s > 0) centres.push_back(best);
+                    best = S.stage(one, 0, plan.step[s], plan.window[s], P.range_deg, centres, 0.0)[0].best_angle;
+                }
+                S.stats[3] += 1;
+            }
+            cur.spin(best, cur.c[0], cur.c[1]);
+            cumulative += best;
+            const double row[7] = {(double)cur.id, (double)prev.id, rad2deg(best), tx, ty, cur.c[0], cur.c[1]};
+            outs[g].logs.insert(outs[g].logs.end(), row, row + 7);
+        }
+        // 4. post steps (align_within.rs:136-158)
+        fill_holes(geo);
+        if (meta[g].ref_idx >= geo.frames.size()) throw InputErr("index out of bounds: reference frame");
+        const Frame& rf = geo.frames[meta[g].ref_idx];
+        const bool anomalous = elliptic_ratio(rf.lumen) > 2.0 || rf.lumen.has_at || rf.lumen.has_pt;
+        const double extra = ref_point_to_right(rf, anomalous);
+        if (extra != 0.0)  // Geometry::rotate_geometry, geometry.rs:241-250
+            for (auto& f : geo.frames) {
+                f.spin(extra, f.c[0], f.c[1]);
+                f.sort_points();
+            }
+        if (anomalous)  // assign_aortic, :319-331
+            for (auto& f : geo.frames) {
+                const size_t len = f.lumen.size();
+                for (size_t k = 0; k < len; ++k) f.lumen.ao[k] = k >= len / 2;
+            }
+        add_walls(geo, anomalous);
+        if (P.smooth) smooth(geo);
+        outs[g].anomalous = anomalous;
+    }
+}
+
+// =============================================================================
+// Inter-pullback alignment of MANY pairs at once (align_between.rs:11-92)
+// =============================================================================
+void sample_cloud(const Geometry& g, size_t sample, std::vector<double>& dst) {  // :154-178
+    size_t total = 0;
+    for (auto& f : g.frames) total += f.lumen.size();
+    const double ratio = (double)sample / (double)total;
+    for (auto& f : g.frames) {
+        const size_t k = std::max<size_t>(as_usize(std::ceil((double)f.lumen.size() * ratio)), 1);
+        for (size_t i : stride_pick(f.lumen.size(), k)) {
+            dst.push_back(f.lumen.x[i]);
+            dst.push_back(f.lumen.y[i]);
+        }
+    }
+}
+
+void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>>& pairs, const mmrs_align_params& P) {
+    const size_t N = pairs.size();
+    if (!N) return;
+    const size_t sample = std::max<size_t>((size_t)std::max<int64_t>(P.sample_size, 0), 500);
+    std::vector<std::array<double, 2>> pivot(N);
+    SweepUnits units;
+    for (size_t k = 0; k < N; ++k) {
+        Geometry &a = *pairs[k].first, &b = *pairs[k].second;
+        if (a.frames.empty() || b.frames.empty()) throw InputErr("index out of bounds: empty geometry");
+        const size_t ia = a.ref_or_proximal(), ib = b.ref_or_proximal();
+        if (ia >= a.frames.size() || ib >= b.frames.size()) throw InputErr("index out of bounds: reference frame");
+        const Frame &fa = a.frames[ia], &fb = b.frames[ib];
+        pivot[k] = {fa.c[0], fa.c[1]};
+        b.shift_all(fa.c[0] - fb.c[0], fa.c[1] - fb.c[1], fa.c[2] - fb.c[2]);
+        const size_t r0 = units.ref.size();
+        sample_cloud(a, sample, units.ref);
+        sample_cloud(b, sample, units.test);
+        // calculate_global_centroid of the reference cloud, :260-271 (x then y, sequential sums)
+        double sx = 0.0, sy = 0.0;
+        const size_t cnt = (units.ref.size() - r0) / 2;
+        for (size_t i = 0; i < cnt; ++i) sx += units.ref[r0 + 2 * i];
+        for (size_t i = 0; i < cnt; ++i) sy += units.ref[r0 + 2 * i + 1];
+        units.close_unit(cnt ? sx / (double)cnt : 0.0, cnt ? sy / (double)cnt : 0.0);
+    }
+    // there is no brute-force switch on this path (align_between.rs:219-257)
+    const Plan plan = make_plan(P.step_deg, P.range_deg, false);
+    std::vector<double> angle(N, 0.0);
+    for (int s = 0; s < plan.n; ++s) {
+        std::vector<double> centres;
+        if (s > 0) centres = angle;
+        auto res = S.stage(units, 1, plan.step[s], plan.window[s], P.range_deg, centres, 0.0);
+        for (size_t k = 0; k < N; ++k) angle[k] = res[k].best_angle;
+    }
+    for (size_t k = 0; k < N; ++k) {
+        Geometry &a = *pairs[k].first, &b = *pairs[k].second;
+        // rotate_geometry_around_point, :95-145 (contour centroids rotate too, unlike Frame::rotate)
+        const double ca = std::cos(angle[k]), sa = std::sin(angle[k]), cx = pivot[k][0], cy = pivot[k][1];
+        auto rot = [&](double& x, double& y) {
+            const double tx = x - cx, ty = y - cy;
+            const double rx = tx * ca - ty * sa, ry = tx * sa + ty * ca;
+            x = rx + cx;
+            y = ry + cy;
+        };
+        for (auto& f : b.frames) {
+            for (size_t i = 0; i < f.lumen.size(); ++i) rot(f.lumen.x[i], f.lumen.y[i]);
+            rot(f.c[0], f.c[1]);
+            for (auto& kv : f.extras) {
+                for (size_t i = 0; i < kv.second.size(); ++i) rot(kv.second.x[i], kv.second.y[i]);
+                if (kv.second.has_c) rot(kv.second.c[0], kv.second.c[1]);
+            }
+            if (f.has_ref) rot(f.ref.x, f.ref.y);
+        }
+        const Frame &fa = a.frames.at(a.ref_or_proximal()), &fb = b.frames.at(b.ref_or_proximal());
+        b.shift_all(fa.c[0] - fb.c[0], fa.c[1] - fb.c[1], fa.c[2] - fb.c[2]);
+    }
+}
+
+template <class F>
+int guarded(mmrs_ctx* ctx, F&& f) {
+    try {
+        f();
+        return MMRS_OK;
+    } catch (const InputErr& e) {
+        return mmrs::set_err(ctx, MMRS_ERR_INPUT, e.what());
+    } catch (const std::exception& e) {
+        return mmrs::set_err(ctx, MMRS_ERR_CUDA, e.what());
+    }
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
 extern "C" void mmrs_free(void* p) { std::free(p); }
-extern "C" int mmrs_geometry_from_dir(mmrs_ctx* ctx, const char*, const char*, int, double, double, double, uint32_t, double**, int64_t*) { return mmrs::set_err(ctx, MMRS_ERR_STATE, "not built yet"); }
-extern "C" int mmrs_geometry_from_arrays(mmrs_ctx* ctx, const double*, int64_t, const double*, int64_t, const double*, int64_t, const double*, int64_t, const double*, int64_t, const double*, int, const char*, double, double, double, uint32_t, double**, int64_t*) { return mmrs::set_err(ctx, MMRS_ERR_STATE, "not built yet"); }
-extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t, int64_t, const double* const*, const int64_t*, const mmrs_align_params*, double**, int64_t*, double**, int64_t*, int32_t*) { return mmrs::set_err(ctx, MMRS_ERR_STATE, "not built yet"); }
-extern "C" int mmrs_process_stats(mmrs_ctx* ctx, int64_t s[5]) { for (int i = 0; i < 5; ++i) s[i] = ctx ? ctx->stats[i] : 0; return 0; }
+
+extern "C" int mmrs_geometry_from_dir(mmrs_ctx* ctx, const char* path, const char* label, int diastole, double icx,
+                                      double icy, double radius, uint32_t n_points, double** blob_out,
+                                      int64_t* len_out) {
+    if (!path || !label || !blob_out || !len_out) return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_geometry_from_dir: NULL argument");
+    return guarded(ctx, [&] {
+        const Input in = read_directory(path, diastole != 0);
+        const auto v = encode(build_geometry(in, label, diastole != 0, icx, icy, radius, n_points));
+        *blob_out = to_malloc(v);
+        *len_out = (int64_t)v.size();
+    });
+}
+
+extern "C" int mmrs_geometry_from_arrays(mmrs_ctx* ctx, const double* lumen, int64_t n_lumen, const double* eem,
+                                         int64_t n_eem, const double* calc, int64_t n_calc, const double* side,
+                                         int64_t n_side, const double* records, int64_t n_rec, const double* ref_point,
+                                         int diastole, const char* label, double icx, double icy, double radius,
+                                         uint32_t n_points, double** blob_out, int64_t* len_out) {
+    if (!lumen || !ref_point || !label || !blob_out || !len_out)
+        return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_geometry_from_arrays: NULL argument");
+    return guarded(ctx, [&] {
+        auto conv = [](const double* a, int64_t n) {
+            std::vector<RawPoint> v((size_t)n);
+            for (int64_t i = 0; i < n; ++i) v[i] = RawPoint{(uint32_t)a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], false};
+            return v;
+        };
+        Input in;
+        in.lumen = conv(lumen, n_lumen);
+        if (eem) in.eem = conv(eem, n_eem), in.has_eem = true;
+        if (calc) in.calc = conv(calc, n_calc), in.has_calc = true;
+        if (side) in.side = conv(side, n_side), in.has_side = true;
+        if (records) {
+            in.has_rec = true;
+            for (int64_t i = 0; i < n_rec; ++i) {
+                Rec r{};
+                r.frame = (uint32_t)records[4 * i];
+                r.diastole_phase = records[4 * i + 1] != 0.0;
+                r.systole_phase = !r.diastole_phase;
+                r.has1 = records[4 * i + 2] == records[4 * i + 2];
+                r.m1 = records[4 * i + 2];
+                r.has2 = records[4 * i + 3] == records[4 * i + 3];
+                r.m2 = records[4 * i + 3];
+                in.rec.push_back(r);
+            }
+        }
+        in.ref = conv(ref_point, 1)[0];
+        const auto v = encode(build_geometry(in, label, diastole != 0, icx, icy, radius, n_points));
+        *blob_out = to_malloc(v);
+        *len_out = (int64_t)v.size();
+    });
+}
+
+extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, const double* const* blobs,
+                                  const int64_t* blob_lens, const mmrs_align_params* params, double** out_blobs,
+                                  int64_t* out_lens, double** out_logs, int64_t* out_nlogs, int32_t* out_anomalous) {
+    if (!ctx) return mmrs::set_err(nullptr, MMRS_ERR_ARG, "mmrs_process_cases: ctx is NULL (a CUDA context is required)");
+    if (mode < 1 || mode > 4 || n_cases < 0 || !params || (n_cases > 0 && (!blobs || !blob_lens || !out_blobs || !out_lens || !out_logs || !out_nlogs)))
+        return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_process_cases: bad arguments");
+    const int n_in = mode >= 3 ? 4 : mode;
+    const int n_out = mode == 4 ? 8 : mode == 3 ? 4 : mode;
+    for (int i = 0; i < 5; ++i) ctx->stats[i] = 0;
+    return guarded(ctx, [&] {
+        Searcher S{ctx, ctx->stats};
+        std::vector<Geometry> geo((size_t)n_cases * n_in);
+        for (size_t k = 0; k < geo.size(); ++k) geo[k] = decode(blobs[k], blob_lens[k]);
+        // intrapullback: every pullback of every case in one batch per stage (entry.rs:140-203)
+        std::vector<Geometry*> all;
+        for (auto& g : geo) all.push_back(&g);
+        std::vector<WithinOut> w;
+        align_within_many(S, all, *params, w);
+        for (size_t k = 0; k < geo.size(); ++k) {
+            out_logs[k] = to_malloc(w[k].logs);
+            out_nlogs[k] = (int64_t)w[k].logs.size() / 7;
+            if (out_anomalous) out_anomalous[k] = w[k].anomalous ? 1 : 0;
+        }
+        auto emit = [&](int64_t c, int slot, const Geometry& g) {
+            const auto v = encode(g);
+            out_blobs[c * n_out + slot] = to_malloc(v);
+            out_lens[c * n_out + slot] = (int64_t)v.size();
+        };
+        if (mode == 1) {
+            for (int64_t c = 0; c < n_cases; ++c) emit(c, 0, geo[c]);
+            return;
+        }
+        // inter-pullback level 1: A<-B (and C<-D), every case at once (entry.rs:206-240, :617-666)
+        std::vector<std::pair<Geometry*, Geometry*>> level;
+        for (int64_t c = 0; c < n_cases; ++c) {
+            Geometry* g = &geo[c * n_in];
+            level.push_back({g + 0, g + 1});
+            if (mode >= 3) level.push_back({g + 2, g + 3});
+        }
+        align_between_many(S, level, *params);
+        for (int64_t c = 0; c < n_cases; ++c) {
+            Geometry* g = &geo[c * n_in];
+            emit(c, 0, g[0]);
+            emit(c, 1, g[1]);
+            if (mode >= 3) {
+                emit(c, 2, g[2]);  // pair CD holds C as it was BEFORE A<-C moves it
+                emit(c, 3, g[3]);  // ... and D before B<-D moves it again
+            }
+        }
+        if (mode != 4) return;
+        // level 2: A<-C and B<-D on the already moved B and D (entry.rs:243-277)
+        level.clear();
+        for (int64_t c = 0; c < n_cases; ++c) {
+            Geometry* g = &geo[c * n_in];
+            level.push_back({g + 0, g + 2});
+            level.push_back({g + 1, g + 3});
+        }
+        align_between_many(S, level, *params);
+        for (int64_t c = 0; c < n_cases; ++c) {
+            Geometry* g = &geo[c * n_in];
+            emit(c, 4, g[0]);
+            emit(c, 5, g[2]);
+            emit(c, 6, g[1]);
+            emit(c, 7, g[3]);
+        }
+    });
+}
+
+extern "C" int mmrs_process_stats(mmrs_ctx* ctx, int64_t s[5]) {
+    if (!ctx || !s) return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_process_stats: NULL argument");
+    for (int i = 0; i < 5; ++i) s[i] = ctx->stats[i];
+    return MMRS_OK;
+}

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256)
             const double2* __restrict__ cs64, const unsigned char* __restrict__ zero_flag,
             const int2* __restrict__ items, const unsigned* __restrict__ n_items, const int* __restrict__ sl_idx,
             double* __restrict__ sl_dist, int cap, int max_n) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_red = reinterpret_cast<double*>(smem_raw);
     double2* s_rot = reinterpret_cast<double2*>(smem_raw + 64);
     double2* s_ref = s_rot + max_n;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256)
                   const double* __restrict__ ref_xy, const double2* __restrict__ cs64,
                   const unsigned char* __restrict__ zero_flag, long long cs_off, int count, double* __restrict__ out,
                   int max_n) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_red = reinterpret_cast<double*>(smem_raw);
     double2* s_rot = reinterpret_cast<double2*>(smem_raw + 64);
     double2* s_ref = s_rot + max_n;

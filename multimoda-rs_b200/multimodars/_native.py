@@ -238,3 +238,82 @@ class Context:
         s = (C.c_int64 * 5)()
         self._check(lib().mmrs_process_stats(self._p, s))
         return dict(units=s[0], evals=s[1], rechecks=s[2], chain_resolved=s[3], launches=s[4])
+
+
+# ---- geometry-level entry points ---------------------------------------------------
+def _take_blob(ptr, n):
+    arr = np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].copy()
+    lib().mmrs_free(ptr)
+    return arr
+
+
+def geometry_from_dir(path, label, diastole, image_center=(4.5, 4.5), radius=0.5, n_points=20, ctx: Context | None = None):
+    """mmrs_geometry_from_dir -> geometry blob (host-only; replaces io/build.rs:9-205 + io/input.rs:62-147)."""
+    L = lib()
+    L.mmrs_geometry_from_dir.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_double,
+                                         C.c_double, C.c_uint32, C.POINTER(c_dp), c_i64p]
+    blob, n = c_dp(), C.c_int64()
+    p = ctx._p if ctx is not None else None
+    rc = L.mmrs_geometry_from_dir(p, os.fsencode(str(path)), label.encode(), int(diastole), image_center[0],
+                                  image_center[1], radius, int(n_points), C.byref(blob), C.byref(n))
+    if rc:
+        raise MmrsError(_err(p))
+    return _take_blob(blob, n.value)
+
+
+def geometry_from_arrays(lumen, ref_point, eem=None, calc=None, side=None, records=None, diastole=True, label="geom",
+                         image_center=(4.5, 4.5), radius=0.5, n_points=20, ctx: Context | None = None):
+    """mmrs_geometry_from_arrays -> geometry blob. Arrays are (N,4) [frame, x, y, z]."""
+    L = lib()
+    L.mmrs_geometry_from_arrays.argtypes = [C.c_void_p, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64, c_dp,
+                                            C.c_int64, c_dp, C.c_int64, c_dp, C.c_int, C.c_char_p, C.c_double,
+                                            C.c_double, C.c_double, C.c_uint32, C.POINTER(c_dp), c_i64p]
+
+    def arr(a):
+        if a is None:
+            return None, None, 0
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, 4))
+        return a, a.ctypes.data_as(c_dp), a.shape[0]
+
+    keep = [arr(lumen), arr(eem), arr(calc), arr(side), arr(records)]
+    rp = np.ascontiguousarray(np.asarray(ref_point, dtype=np.float64).reshape(4))
+    blob, n = c_dp(), C.c_int64()
+    p = ctx._p if ctx is not None else None
+    args = []
+    for k in keep:
+        args += [k[1], k[2]]
+    rc = L.mmrs_geometry_from_arrays(p, *args, rp.ctypes.data_as(c_dp), int(diastole), label.encode(),
+                                     image_center[0], image_center[1], radius, int(n_points), C.byref(blob),
+                                     C.byref(n))
+    if rc:
+        raise MmrsError(_err(p))
+    return _take_blob(blob, n.value)
+
+
+N_IN = {4: 4, 3: 4, 2: 2, 1: 1}
+N_OUT = {4: 8, 3: 4, 2: 2, 1: 1}
+
+
+def process_cases(ctx: Context, mode, blobs, step_deg, range_deg, sample_size, smooth, bruteforce):
+    """mmrs_process_cases for len(blobs)/N_IN[mode] cases. Returns (out_blobs, logs, anomalous)."""
+    L = lib()
+    n_in, n_out = N_IN[mode], N_OUT[mode]
+    assert len(blobs) % n_in == 0
+    n_cases = len(blobs) // n_in
+    arrs = [np.ascontiguousarray(b, dtype=np.float64) for b in blobs]
+    ptrs = (c_dp * max(len(arrs), 1))(*[a.ctypes.data_as(c_dp) for a in arrs])
+    lens = (C.c_int64 * max(len(arrs), 1))(*[len(a) for a in arrs])
+    ob = (c_dp * max(n_cases * n_out, 1))()
+    ol = (C.c_int64 * max(n_cases * n_out, 1))()
+    lg = (c_dp * max(len(arrs), 1))()
+    nl = (C.c_int64 * max(len(arrs), 1))()
+    an = (C.c_int32 * max(len(arrs), 1))()
+    prm = AlignParams(step_deg, range_deg, int(sample_size), int(smooth), int(bruteforce))
+    L.mmrs_process_cases.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(c_dp), c_i64p,
+                                     C.POINTER(AlignParams), C.POINTER(c_dp), c_i64p, C.POINTER(c_dp), c_i64p, c_i32p]
+    rc = L.mmrs_process_cases(ctx._p, int(mode), n_cases, ptrs, lens, C.byref(prm), ob, ol, lg, nl, an)
+    if rc:
+        raise MmrsError(_err(ctx._p))
+    outs = [_take_blob(ob[i], ol[i]) for i in range(n_cases * n_out)]
+    logs = [_take_blob(lg[i], nl[i] * 7).reshape(-1, 7) for i in range(len(arrs))]
+    return outs, logs, [bool(an[i]) for i in range(len(arrs))]

@@ -1,0 +1,149 @@
+"""GPU parity of the mode orchestration (mmrs_process_cases behind from_file_* / from_array_*)
+against the CPU oracle and the committed goldens: per-frame rotation / translation logs and every
+output geometry must be BIT-IDENTICAL (north_star: "selected rotation angle and translation per
+frame must match the reference's path exactly")."""
+import numpy as np
+import pytest
+
+import multimodars as mm
+from multimodars import _native as nat
+from oracle import oracle_py as ora
+from tests import fixtures as fx
+from tests import golden_io as gio
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_blobs(pack, names_dia):
+    out = []
+    for name, dia in names_dia:
+        a = gio.phase_arrays(pack, name, dia)
+        out.append(ora.build_geometry_from_arrays(a["lumen"], a["ref_point"], a["eem"], a["calc"], a["side"],
+                                                  a["records"], dia, name))
+    return out
+
+
+FULL = [("rest", True), ("rest", False), ("stress", True), ("stress", False)]
+
+
+def logs_array(logs):
+    return np.array(logs, dtype=np.float64).reshape(-1, 7)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("default", dict(step_rotation_deg=0.5, range_rotation_deg=90.0, bruteforce=False, smooth=True)),
+    ("brute0p5", dict(step_rotation_deg=0.5, range_rotation_deg=90.0, bruteforce=True, smooth=False)),
+    ("hier0p05", dict(step_rotation_deg=0.05, range_rotation_deg=90.0, bruteforce=False, smooth=False)),
+])
+def test_config1_from_array_full_matches_golden_and_oracle(tag, kw):
+    """BASELINE config 1: examples ivus_rest + ivus_stress, 4-phase full mode."""
+    pack, gold = gio.inputs(), gio.oracle_outputs()
+    ins = [gio.py_input(mm, pack, n, d, f"{n}_{'dia' if d else 'sys'}") for n, d in FULL]
+    ab, cd, ac, bd, logs = mm.from_array_full(*ins, sample_size=500, write_obj=False, postprocessing=False, **kw)
+    for i in range(4):
+        assert np.array_equal(logs_array(logs[i]), gold[f"cfg1_{tag}_logs_{i}"]), (tag, i)
+    outs = [ab.geom_a, ab.geom_b, cd.geom_a, cd.geom_b, ac.geom_a, ac.geom_b, bd.geom_a, bd.geom_b]
+    for i, g in enumerate(outs):
+        assert gio.sha(g.to_blob()) == str(gold[f"cfg1_{tag}_out_sha_{i}"]), (tag, i)
+    assert ab.label == "rest_dia - rest_sys" and bd.label == "rest_sys - stress_sys"
+    assert isinstance(ab, mm.PyGeometryPair) and isinstance(logs[0][0], tuple) and len(logs[0][0]) == 7
+    st = mm.get_context().process_stats()
+    assert st["units"] > 0 and st["evals"] > 0 and st["launches"] > 0
+
+
+def test_config1_from_file_full(tmp_path):
+    pack, gold = gio.inputs(), gio.oracle_outputs()
+    rest, stress = gio.write_dir(pack, "rest", tmp_path / "ivus_rest"), gio.write_dir(pack, "stress", tmp_path / "ivus_stress")
+    ab, cd, ac, bd, logs = mm.from_file_full(str(rest), str(stress), write_obj=False, postprocessing=False)
+    for i in range(4):
+        assert np.array_equal(logs_array(logs[i]), gold[f"cfg1_default_logs_{i}"])
+    assert gio.sha(bd.geom_b.to_blob()) == str(gold["cfg1_default_out_sha_7"])
+    assert ab.geom_a.label == "ivus_rest" and cd.label == "ivus_stress - ivus_stress"
+
+
+@pytest.mark.parametrize("mode", [3, 2, 1])
+def test_other_modes_match_oracle(mode):
+    pack = gio.inputs()
+    n_in = nat.N_IN[mode]
+    names = FULL[:n_in]
+    blobs = oracle_blobs(pack, names)
+    want_out, want_logs = ora.process(mode, blobs, 0.5, 90.0, True, False, 500, threads=8)
+    ins = [gio.py_input(mm, pack, n, d, n) for n, d in names]
+    kw = dict(step_rotation_deg=0.5, range_rotation_deg=90.0, sample_size=500, write_obj=False)
+    if mode == 3:
+        ab, cd, logs = mm.from_array_doublepair(*ins, postprocessing=False, **kw)
+        got = [ab.geom_a, ab.geom_b, cd.geom_a, cd.geom_b]
+    elif mode == 2:
+        pair, logs = mm.from_array_singlepair(*ins, postprocessing=False, **kw)
+        got = [pair.geom_a, pair.geom_b]
+    else:
+        g, l0 = mm.from_array_single(ins[0], **kw)
+        got, logs = [g], (l0,)
+    for i in range(n_in):
+        assert np.array_equal(logs_array(logs[i]), want_logs[i])
+    for g, w in zip(got, want_out):
+        assert np.array_equal(g.to_blob(), w)
+
+
+def test_idealized_fixture_within_kat():
+    """align_within.rs:855-887 through the product: |rot| = 15 +- 1, tx = -0.01 k, ty = +0.01 k, anomalous."""
+    pack, gold = gio.inputs(), gio.oracle_outputs()
+    inp = gio.py_input(mm, pack, "ideal", True, "stress")
+    g, logs = mm.from_array_single(inp, step_rotation_deg=0.01, range_rotation_deg=20.0, sample_size=200, smooth=True)
+    la = logs_array(logs)
+    assert np.array_equal(la, gold["ideal_within_logs"])
+    assert gio.sha(g.to_blob()) == str(gold["ideal_within_out_sha"])
+    for k, row in enumerate(la):
+        assert abs(abs(row[2]) - 15.0) <= 1.0
+        assert row[3] == pytest.approx(-0.01 * (k + 1), abs=1e-3) and row[4] == pytest.approx(0.01 * (k + 1), abs=1e-3)
+
+
+def test_rust_kat_simple_geometry_through_product():
+    """align_within.rs:791-830 (dummy hexagon chain): rot = -15, tx = ty = -k. The 6-point polygon is
+    full of exact ties, so this also exercises the chain-resolve path."""
+    ctx = mm.get_context()
+    blob = ora.encode_geometry(fx.dummy_geometry())
+    want_out, want_logs, _ = ora.align_within(blob, 0.01, 30.0, False, False, 6)
+    out, logs, _ = nat.process_cases(ctx, 1, [blob], 0.01, 30.0, 6, False, False)
+    assert np.array_equal(logs[0], want_logs)
+    assert np.array_equal(out[0], want_out)
+    for i, row in enumerate(logs[0]):
+        assert row[2] == pytest.approx(-15.0, abs=1e-6) and row[3] == pytest.approx(-(i + 1.0), abs=1e-6)
+
+
+def test_between_kat_through_product():
+    """align_between.rs:281-303: B = A rotated by 15 deg per frame -> found rotation -15 deg."""
+    ctx = mm.get_context()
+    a = ora.encode_geometry(fx.dummy_geometry_aligned_long())
+    want_pairs, want_logs = ora.process(2, [a, a], 0.01, 30.0, False, False, 6)
+    out, logs, _ = nat.process_cases(ctx, 2, [a, a], 0.01, 30.0, 6, False, False)
+    for g, w in zip(out, want_pairs):
+        assert np.array_equal(g, w)
+    for l, w in zip(logs, want_logs):
+        assert np.array_equal(l, w)
+
+
+def test_synthetic_batch_of_cases_matches_oracle():
+    """Several independent synthetic cases in ONE call (the batch axis the GPU design adds): every case
+    must equal what the oracle returns for it alone."""
+    ctx = mm.get_context()
+    blobs = []
+    for case in range(3):
+        for ph in range(2):
+            lumen, rp = fx.synthetic_pullback(12, 120, seed=1000 * case + ph)
+            blobs.append(nat.geometry_from_arrays(lumen, rp, diastole=(ph == 0), label=f"c{case}p{ph}"))
+    out, logs, _ = nat.process_cases(ctx, 2, blobs, 0.1, 45.0, 100, True, False)
+    for case in range(3):
+        want_out, want_logs = ora.process(2, blobs[2 * case:2 * case + 2], 0.1, 45.0, True, False, 100, threads=8)
+        for k in range(2):
+            assert np.array_equal(logs[2 * case + k], want_logs[k]), (case, k)
+            assert np.array_equal(out[2 * case + k], want_out[k]), (case, k)
+
+
+def test_reference_guards_surface_as_errors():
+    ctx = mm.get_context()
+    blob = ora.encode_geometry(fx.dummy_geometry())
+    with pytest.raises(nat.MmrsError, match="sample_size must be > 0"):   # align_within.rs:38-40
+        nat.process_cases(ctx, 1, [blob], 0.5, 30.0, 0, False, False)
+    with pytest.raises(nat.MmrsError, match="Geometry contains no frames"):  # :32-34
+        nat.process_cases(ctx, 1, [np.array([0.0])], 0.5, 30.0, 6, False, False)
