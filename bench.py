@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — Hausdorff candidate evaluations / second on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1], "synthetic single-pair: 1 pullback pair,
+200 frames x 500 points/contour, 0.01 deg rotation sweep over 360 deg" — per rank 398 intrapullback
+frame-pair units (N = M = 520 points: 500 lumen + 20 catheter), 36 000 candidate angles each,
+brute force. One "step" = one pass of the hot path over that batch.
+
+  value  evals/s with the batch resident in HBM (mmrs_sweep_run: FP32 sweep + shortlist + f64
+         recheck + arg-min), CUDA events on the launching stream, max over ranks.
+  e2e    the same through the C ABI call a host binds (mmrs_sweep_batched) with HOST buffers:
+         pinned H2D of the points, all kernels, D2H of the per-unit results, every step.
+  N > 1  weak scaling: every rank sweeps its own pullback pair (units are independent,
+         SURVEY.md §8e); the only exchange is an NCCL all-gather of the per-unit
+         (index, distance) results, inside the timed region.
+
+`--impl reference` times the CPU oracle (oracle/, the restatement of the reference's
+rayon path; the Rust reference cannot be built in this image) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path[:0] = [str(ROOT), str(ROOT / "multimoda-rs_b200")]
+
+METRIC = "hausdorff_candidate_evals_per_sec"
+UNIT = "evals/s"
+N_FRAMES, N_POINTS, N_CATH = 200, 500, 20
+STEP_DEG, RANGE_DEG = 0.01, 180.0
+WORKLOAD = ("BASELINE configs[1]: synthetic single-pair, 2 pullbacks x 200 frames x 500 pts (+20 catheter pts), "
+            "brute-force 0.01 deg sweep over +-180 deg (36000 candidates), per rank")
+
+
+def flops_per_eval(n, m):
+    """two directed passes x N*M pairs x 5 FP32 FLOPs + 6 N for the rotation."""
+    return 10.0 * n * m + 6.0 * n
+
+
+# ---- synthetic pullback pair -> sweep units (what align_within_many builds on the host) -------------
+def synthetic_pullback(n_frames, n_points, seed):
+    """SURVEY.md §8(d) generator: smooth random-walk lumen shape, cumulative rotation N(0, 4 deg),
+    centroid jitter 0.3 mm about (4.5, 4.5), 5 um point noise. Returns (frames, n_points, 2)."""
+    rng = np.random.default_rng(seed)
+    phi = np.linspace(0.0, 2.0 * np.pi, n_points, endpoint=False)
+    r0, e, psi = rng.uniform(1.5, 3.0), rng.uniform(0.05, 0.35), rng.uniform(0, np.pi)
+    ak, pk = rng.uniform(0, 0.04, 4), rng.uniform(0, 2 * np.pi, 4)
+    cum, out = 0.0, []
+    for _ in range(n_frames):
+        r0 = float(np.clip(r0 + rng.normal(0, 0.02), 1.2, 3.2))
+        e = float(np.clip(e + rng.normal(0, 0.01), 0.03, 0.4))
+        ak = np.clip(ak + rng.normal(0, 0.002, 4), 0, 0.05)
+        cum += np.deg2rad(rng.normal(0, 4.0))
+        r = r0 * (1 + e * np.cos(2 * (phi - psi)) + sum(ak[k] * np.cos((k + 3) * phi + pk[k]) for k in range(4)))
+        c = 4.5 + rng.normal(0, 0.3, 2)
+        out.append(np.stack([r * np.cos(phi + cum) + c[0], r * np.sin(phi + cum) + c[1]], 1)
+                   + rng.normal(0, 0.005, (n_points, 2)))
+    return np.stack(out)
+
+
+def make_units(seed):
+    """398 decoupled frame-pair units of one pullback pair, centred like the host does."""
+    th = 2.0 * np.pi * np.arange(N_CATH) / N_CATH
+    cath = np.stack([4.5 + 0.5 * np.cos(th), 4.5 + 0.5 * np.sin(th)], 1)
+    tests, refs = [], []
+    for pb in range(2):
+        fr = synthetic_pullback(N_FRAMES, N_POINTS, seed + pb)
+        pts = [np.concatenate([f, cath]) - f.mean(axis=0) for f in fr]   # centred on the frame (lumen) centroid
+        for i in range(1, N_FRAMES):
+            tests.append(pts[i])
+            refs.append(pts[i - 1])
+    U = len(tests)
+    n = N_POINTS + N_CATH
+    off = np.arange(U + 1, dtype=np.int64) * n
+    return np.concatenate(tests), off, np.concatenate(refs), off.copy(), np.zeros((U, 2)), U, n
+
+
+# ---- clocks ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
+        # median over the busiest half (the samples taken while kernels were running)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    sm_max = 1965.0
+    src = "fallback sm_max_mhz 1965 (B200_PROFILING.md)"
+    if p.exists():
+        try:
+            sm_max = float(json.loads(p.read_text())["sm_max_mhz"])
+            src = "MEASURED_PEAKS.json sm_max_mhz"
+        except Exception:
+            pass
+    return 148 * 128 * 2 * sm_max * 1e6 / 1e12, src
+
+
+# ---- reference arm: the CPU oracle on the host cores -------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as ora
+
+    ora.build()
+    cores = os.cpu_count() or 1
+    txy, toff, rxy, roff, cen, U, n = make_units(20261018)
+    sample_units = 1
+    sl = slice(0, sample_units * n)
+    t_off, r_off = toff[:sample_units + 1], roff[:sample_units + 1]
+    ncand = len(ora.search_grid(STEP_DEG, RANGE_DEG, None, RANGE_DEG)[0])
+
+    def step():
+        t0 = time.perf_counter()
+        ora.sweep_batch(txy[sl], t_off, rxy[sl], r_off, cen[:sample_units], 0, STEP_DEG, RANGE_DEG, RANGE_DEG, threads=cores)
+        return time.perf_counter() - t0
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    times = [step() for _ in range(args.steps)]
+    evals = sample_units * ncand
+    v = evals * len(times) / sum(times)
+    sample = f"{sample_units} frame pair x {ncand} candidates (N=M={n}) per step, {cores} threads over candidates"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU oracle = C++ f64 restatement of the reference's rayon path (threads over candidate angles, "
+                    "serial N x M inside; process_utils.rs:69-118); the Rust reference cannot be built in this image"}
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip the from_array_singlepair wall-time leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from multimodars import _native as nat
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    stream = torch.cuda.current_stream()
+    ctx = nat.Context(local, stream.cuda_stream)
+    txy, toff, rxy, roff, cen, U, n = make_units(20261018 + 1000 * rank)
+    grid = nat.make_grid(STEP_DEG, RANGE_DEG)
+    ncand = int(grid.n_cand)
+    evals_rank = U * ncand
+    F = flops_per_eval(n, n)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    gather_buf = [torch.empty(U, 2, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(res):
+        if world > 1:
+            mine = torch.from_numpy(np.stack([res["best_idx"].astype(np.float64), res["best_dist"]], 1)).cuda()
+            dist.all_gather(gather_buf, mine)
+
+    # ---- value: batch resident in HBM ------------------------------------------------------------------
+    ctx.sweep_upload(txy, toff, rxy, roff, cen, [grid], mode=0)
+    for _ in range(W):
+        ctx.sweep_run()
+        gather(ctx.sweep_download())
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    dev_ms, k1_ms, launches = [], [], 0
+    for _ in range(K):
+        flush.fill_(1)                      # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.sweep_run()
+        res = ctx.sweep_download()          # D2H of 40 B per unit (stream sync inside)
+        gather(res)
+        e1.record(stream)
+        e1.synchronize()
+        dev_ms.append(e0.elapsed_time(e1))
+        t = ctx.timings()
+        k1_ms.append(t["sweep_ms"])
+        launches += t["launches"]
+    barrier()
+    clk = clocks.stop()
+    total_ms = torch.tensor([sum(dev_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = evals_rank * world * K / (total_ms * 1e-3)
+
+    # ---- e2e: C ABI call with host buffers (pinned), H2D + kernels + D2H every step ------------------------
+    pin = [torch.from_numpy(a).pin_memory() for a in (txy, rxy)]
+    h_t, h_r = pin[0].numpy(), pin[1].numpy()
+    for _ in range(2):
+        ctx.sweep_batched(h_t, toff, h_r, roff, cen, [grid], mode=0)
+    barrier()
+    e2e_ms = []
+    for _ in range(K):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = ctx.sweep_batched(h_t, toff, h_r, roff, cen, [grid], mode=0)
+        gather(res)
+        e1.record(stream)
+        e1.synchronize()
+        e2e_ms.append(e0.elapsed_time(e1))
+    barrier()
+    e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_value = evals_rank * world * K / (float(e2e_total.item()) * 1e-3)
+    h2d = txy.nbytes + rxy.nbytes + toff.nbytes + roff.nbytes + cen.nbytes + ncand * 17 + U * 72
+    d2h = U * 40
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_sweep) ------------------------------------------------------------
+    peak, peak_src = peaks()
+    k1 = float(np.mean(k1_ms))
+    achieved = evals_rank * F / (k1 * 1e-3) / 1e12
+    probe = ctx.fp32_probe(4096)
+    traffic = None
+    tp = ROOT / "profiles" / "sweep_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch_config2")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_sweep<18,false>", "kernel_ms": k1,
+                "kernel_share_of_step": k1 / float(np.mean(dev_ms)),
+                "peak_source": f"148 SM x 128 FP32 lanes x 2 x {peak_src} (no FP32 figure in MEASURED_PEAKS.json)",
+                "ffma_probe_tflops": probe, "frac_of_ffma_probe": achieved / probe,
+                "algorithmic_flops_per_eval": F,
+                "executed_flops_per_eval": 5.0 * n * 576 + 6.0 * 576,
+                "note": "achieved counts the reference's arithmetic (10 N M + 6 N per evaluation); the kernel computes "
+                        "each pair distance once for both directed passes, so it executes about half of that"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on a bounded sample ---------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle_py as ora
+
+        ora.build()
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        bi, _ = ora.sweep_batch(txy[:n], toff[:2], rxy[:n], roff[:2], cen[:1], 0, STEP_DEG, RANGE_DEG, RANGE_DEG, threads=cores)
+        dt = time.perf_counter() - t0
+        assert int(bi[0]) == int(res["best_idx"][0]), "GPU and CPU oracle disagree on unit 0"
+        cpu = {"value": ncand / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 of {U} frame pairs x {ncand} candidates (N=M={n}), {cores} threads over candidates, {dt:.1f} s"}
+
+    # ---- wall time of the public API call on the same workload ---------------------------------------------------
+    api = None
+    if world == 1 and not args.no_api:
+        import multimodars as mm
+
+        def inp(seed, dia):
+            fr = synthetic_pullback(N_FRAMES, N_POINTS, seed)
+            z = 0.5 * (N_FRAMES - 1 - np.arange(N_FRAMES))
+            rows = np.concatenate([np.column_stack([np.full(N_POINTS, float(i)), f, np.full(N_POINTS, z[i])])
+                                   for i, f in enumerate(fr)])
+            last = rows[rows[:, 0] == N_FRAMES - 1][0]
+            return mm.numpy_to_inputdata(rows, np.array([N_FRAMES - 1, last[1] + 0.1, last[2], last[3]]), dia,
+                                         label="dia" if dia else "sys")
+
+        a, b = inp(20261018, True), inp(20261019, False)
+        t0 = time.perf_counter()
+        mm.from_array_singlepair(a, b, step_rotation_deg=STEP_DEG, range_rotation_deg=RANGE_DEG, sample_size=500,
+                                 write_obj=False, bruteforce=True, smooth=True, postprocessing=False)
+        wall = time.perf_counter() - t0
+        st = mm.get_context().process_stats()
+        api = {"call": "from_array_singlepair(bruteforce=True, step 0.01, range 180)", "align_wall_s": wall,
+               "evals": st["evals"], "evals_per_s": st["evals"] / wall, "units": st["units"],
+               "chain_resolved_units": st["chain_resolved"], "f64_rechecks": st["rechecks"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "units_per_rank": U, "candidates_per_unit": ncand, "points": [n, n],
+                       "parallelism": f"units sharded x{world} (one pullback pair per rank)",
+                       "l2": "256 MB device buffer rewritten between timed iterations", "recheck": "f64 on-device"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "call": "mmrs_sweep_batched (host buffers in, host results out)"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "api": api}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
