@@ -16,7 +16,7 @@ struct UnitDesc {
     double cx, cy;                // rotation centre
     long long lay_off;            // float4 offset of this unit's staging block (A then B)
     int n_chunks;                 // A is stored as n_chunks x (TA/2) x 32 float4
-    int m_pairs;                  // B is stored as 2*m_pairs float4 (bx,bx,by,by)
+    int m_pairs;                  // B is stored as m_pairs float4 (bx0,by0,bx1,by1)
     long long cand_off;           // offset of this unit's grid in the cos/sin tables
     int n_cand;
     int flags;

@@ -332,7 +332,7 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
         if (d.n > 0 && d.m > 0) {
             d.n_chunks = (d.n + 32 * TA - 1) / (32 * TA);
             d.m_pairs = (d.m + 1) / 2;
-            const long long a_elems = (long long)d.n_chunks * (TA / 2) * 32, b_elems = 2ll * d.m_pairs;
+            const long long a_elems = (long long)d.n_chunks * (TA / 2) * 32, b_elems = d.m_pairs;
             lay_off += a_elems + b_elems;
             if (d.n_chunks > 1) multi = true;
             smem_max = std::max(smem_max, (size_t)(a_elems + b_elems) * 16);

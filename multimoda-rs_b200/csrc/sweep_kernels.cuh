@@ -93,7 +93,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 //   float4 e = (chunk c, pair k, lane l) at (c*(TA/2)+k)*32 + l holds points
 //   i0 = c*32*TA + 2k*32 + l and i1 = i0 + 32 as (x0, x1, y0, y1).
 // B block (reference points; streamed from shared memory in K1):
-//   float4 j = (bx, bx, by, by), j < 2*m_pairs.
+//   float4 j = (bx0, by0, bx1, by1) = reference points 2j and 2j+1, j < m_pairs. The packed f32x2
+//   instructions take these as scalar operands broadcast to both halves (one 32-bit register
+//   read instead of a 64-bit pair: the sweep is register-file-bandwidth bound).
 // Indices past the end repeat the last point (a duplicate never changes a
 // min-over-points or a max-over-points).
 // =============================================================================
@@ -123,12 +125,14 @@ __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restr
         A[e] = v;
         rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    for (int j = threadIdx.x; j < 2 * ud.m_pairs; j += blockDim.x) {
-        int jj = min(j, ud.m - 1);
-        const double* p = ref_xy + 2 * (ud.ref_off + jj);
-        float bx = (float)(p[0] - ud.cx), by = (float)(p[1] - ud.cy);
-        B[j] = make_float4(bx, bx, by, by);
-        rmax = fmaxf(rmax, fmaxf(fabsf(bx), fabsf(by)));
+    for (int j = threadIdx.x; j < ud.m_pairs; j += blockDim.x) {
+        const int j0 = min(2 * j, ud.m - 1), j1 = min(2 * j + 1, ud.m - 1);
+        const double* p0 = ref_xy + 2 * (ud.ref_off + j0);
+        const double* p1 = ref_xy + 2 * (ud.ref_off + j1);
+        const float4 v = make_float4((float)(p0[0] - ud.cx), (float)(p0[1] - ud.cy), (float)(p1[0] - ud.cx),
+                                     (float)(p1[1] - ud.cy));
+        B[j] = v;
+        rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
     unsigned rb = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
     if ((threadIdx.x & 31) == 0) atomicMax(&rmax_bits[blockIdx.x], rb);
@@ -157,9 +161,10 @@ __global__ void __launch_bounds__(kThreads, 2)
     const WorkItem w = work[blockIdx.x];
     const UnitDesc ud = units[w.unit];
     const int a_elems = ud.n_chunks * H * 32;
-    const int b_elems = 2 * ud.m_pairs;
+    const int b_elems = ud.m_pairs;          // float4 per PAIR of reference points
+    const int b_pts = 2 * ud.m_pairs;
     float4* sB = sA + a_elems;
-    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems);  // MULTI only: [warp][b_elems]
+    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems);  // MULTI only: [warp][b_pts]
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     mbar_wait(bar, 0);
 
     unsigned long long best = ~0ull;
-    unsigned* my_col = s_col + wid * b_elems;
+    unsigned* my_col = s_col + wid * b_pts;
     const float INF = __int_as_float(0x7f800000);
 
     for (int ci = wid; ci < w.count; ci += kWarpsPerCta) {
@@ -196,9 +201,9 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
 #pragma unroll 1
             for (int j = 0; j < ud.m_pairs; ++j) {
-                const float4 B0 = sB[2 * j], B1 = sB[2 * j + 1];
-                const uint64_t bx0 = pk(B0.x, B0.y), by0 = pk(B0.z, B0.w);
-                const uint64_t bx1 = pk(B1.x, B1.y), by1 = pk(B1.z, B1.w);
+                const float4 B = sB[j];  // (bx0, by0, bx1, by1)
+                const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y);
+                const uint64_t bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
                 float c0 = INF, c1 = INF;
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
         if (MULTI) {
             __syncwarp();
-            for (int j = lane; j < b_elems; j += 32) colmax = max(colmax, my_col[j]);
+            for (int j = lane; j < b_pts; j += 32) colmax = max(colmax, my_col[j]);
             __syncwarp();
         }
         const unsigned h2 = __reduce_max_sync(0xffffffffu, max(rowmax, colmax));

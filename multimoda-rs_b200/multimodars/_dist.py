@@ -1,0 +1,102 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on the GPU box, gloo in CPU tests).
+
+The path shards on independent units: cases / pullback pairs / frame pairs are dealt
+to ranks in contiguous balanced blocks with NO data-path collective; only the tiny per-unit results
+(index, distance) and the per-frame log rows are exchanged, with all_gather. A single huge unit can
+instead be split along the candidate axis; its partial arg-mins are combined with the reference's
+tie rule (lowest distance, then lowest global candidate index; process_utils.rs:69-74)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int) -> range:
+    """Contiguous balanced block of `n` items for `rank` (first n % world ranks get one extra)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def candidate_shard(n_cand: int, rank: int, world: int):
+    """Contiguous candidate sub-range [lo, hi) of one unit, so that rank order == index order."""
+    r = shard_range(n_cand, rank, world)
+    return r.start, r.stop
+
+
+def _dev():
+    import torch
+    import torch.distributed as dist
+
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def all_gather_rows(local: np.ndarray, group=None) -> np.ndarray:
+    """all_gather of a (k_r, c) float64 array with rank-dependent k_r; returns the rows of all ranks in
+    rank order. Two collectives: the row counts, then the padded payload."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    c = local.shape[1]
+    dev = _dev()
+    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    sizes = [int(x.item()) for x in cnts]
+    pad = max(max(sizes), 1)
+    buf = torch.zeros(pad, c, dtype=torch.float64, device=dev)
+    if local.shape[0]:
+        buf[:local.shape[0]] = torch.from_numpy(local).to(dev)
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    return np.concatenate([o[:k].cpu().numpy() for o, k in zip(out, sizes)], axis=0)
+
+
+def gather_unit_results(best_idx: np.ndarray, best_dist: np.ndarray, group=None):
+    """Unit-sharded sweep: every rank contributes its units' (index, distance); all ranks get all units."""
+    rows = all_gather_rows(np.stack([best_idx.astype(np.float64), best_dist.astype(np.float64)], axis=1), group)
+    return rows[:, 0].astype(np.int64), rows[:, 1]
+
+
+def combine_angle_sharded(local_best_idx: int, local_best_dist: float, cand_lo: int, group=None):
+    """Angle-sharded sweep of ONE unit: each rank swept candidates [cand_lo, cand_hi) and holds its local
+    leftmost arg-min. Returns the global (index, distance): minimum distance, ties -> lowest global index."""
+    rows = all_gather_rows(np.array([[float(cand_lo + local_best_idx), float(local_best_dist),
+                                      1.0 if local_best_idx >= 0 else 0.0]]), group)
+    best = None
+    for gi, d, ok in rows:
+        if not ok:
+            continue
+        if best is None or d < best[1] or (d == best[1] and gi < best[0]):
+            best = (gi, d)
+    return (-1, 0.0) if best is None else (int(best[0]), float(best[1]))
+
+
+def process_cases_sharded(mode, blobs, step_deg, range_deg, sample_size, smooth, bruteforce, run_local, group=None):
+    """Deals whole cases to ranks, runs `run_local(mode, blobs_of_my_cases, ...)` (mmrs_process_cases on this
+    rank's GPU) and all-gathers the per-frame log rows. Returns {case: [log arrays per pullback]} for ALL cases
+    on every rank; geometries stay on the rank that computed them (returned as the second value)."""
+    import torch.distributed as dist
+
+    from ._native import N_IN
+
+    n_in = N_IN[mode]
+    n_cases = len(blobs) // n_in
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = shard_range(n_cases, rank, world)
+    my_blobs = [b for c in mine for b in blobs[c * n_in:(c + 1) * n_in]]
+    outs, logs = ([], [])
+    if len(mine):
+        outs, logs, _ = run_local(mode, my_blobs, step_deg, range_deg, sample_size, smooth, bruteforce)
+    rows = []
+    for k, c in enumerate(mine):
+        for p in range(n_in):
+            l = logs[k * n_in + p]
+            rows.append(np.column_stack([np.full(len(l), float(c)), np.full(len(l), float(p)), l]))
+    local = np.concatenate(rows, axis=0) if rows else np.zeros((0, 9))
+    allrows = all_gather_rows(local, group)
+    table = {c: [allrows[(allrows[:, 0] == c) & (allrows[:, 1] == p)][:, 2:] for p in range(n_in)]
+             for c in range(n_cases)}
+    return table, {c: outs[k * len(outs) // max(len(mine), 1):(k + 1) * len(outs) // max(len(mine), 1)]
+                   for k, c in enumerate(mine)}
