@@ -218,18 +218,19 @@ static bool launch_sweep(int TA, bool multi, int grid, size_t smem, cudaStream_t
     case T:                                                                         \
         launch_sweep_ta<T>(multi, grid, smem, s, units, work, lay, cs32, dist32, key); \
         return true;
-        CASE(2) CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(14) CASE(16) CASE(18)
+        CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+            CASE(15) CASE(16) CASE(17) CASE(18)
 #undef CASE
     }
     return false;
 }
 
-// Choose the register tile: TA even in [2,18] minimising the padded work
+// Choose the register tile: TA in [2,18] minimising the padded work
 // sum_u ceil(n_u / (32 TA)) * 32 TA, ties -> larger TA (fewer chunks).
 static int choose_ta(const std::vector<int>& ns) {
     int best_ta = 2;
     double best_cost = 1e300;
-    for (int ta = 2; ta <= 18; ta += 2) {
+    for (int ta = 2; ta <= 18; ++ta) {
         double cost = 0;
         for (int n : ns) {
             if (n <= 0) continue;
@@ -332,7 +333,7 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
         if (d.n > 0 && d.m > 0) {
             d.n_chunks = (d.n + 32 * TA - 1) / (32 * TA);
             d.m_pairs = (d.m + 1) / 2;
-            const long long a_elems = (long long)d.n_chunks * (TA / 2) * 32, b_elems = d.m_pairs;
+            const long long a_elems = (long long)d.n_chunks * ((TA + 1) / 2) * 32, b_elems = d.m_pairs;
             lay_off += a_elems + b_elems;
             if (d.n_chunks > 1) multi = true;
             smem_max = std::max(smem_max, (size_t)(a_elems + b_elems) * 16);

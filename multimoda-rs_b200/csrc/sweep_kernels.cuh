@@ -90,8 +90,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 // =============================================================================
 // K0: f64 (x,y) -> centred FP32 staging layout.
 // A block (test points, the set that is rotated; register side of K1):
-//   float4 e = (chunk c, pair k, lane l) at (c*(TA/2)+k)*32 + l holds points
-//   i0 = c*32*TA + 2k*32 + l and i1 = i0 + 32 as (x0, x1, y0, y1).
+//   S = ceil(TA/2) float4 slots per lane and chunk; slot k < TA/2 at (c*S+k)*32 + l holds the
+//   points i0 = c*32*TA + 2k*32 + l and i1 = i0 + 32 as (x0, x1, y0, y1); for odd TA the last
+//   slot holds the single point i0 = c*32*TA + (TA-1)*32 + l as (x, x, y, y).
 // B block (reference points; streamed from shared memory in K1):
 //   float4 j = (bx0, by0, bx1, by1) = reference points 2j and 2j+1, j < m_pairs. The packed f32x2
 //   instructions take these as scalar operands broadcast to both halves (one 32-bit register
@@ -104,7 +105,7 @@ __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restr
                        int TA) {
     const UnitDesc ud = units[blockIdx.x];
     if (ud.n <= 0 || ud.m <= 0) return;
-    const int half = TA / 2;
+    const int half = (TA + 1) / 2, pairs = TA / 2;
     const int a_elems = ud.n_chunks * half * 32;
     float4* A = lay + ud.lay_off;
     float4* B = A + a_elems;
@@ -112,7 +113,7 @@ __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restr
     for (int e = threadIdx.x; e < a_elems; e += blockDim.x) {
         int l = e & 31, ck = e >> 5;
         int c = ck / half, k = ck - c * half;
-        int i0 = c * 32 * TA + 2 * k * 32 + l, i1 = i0 + 32;
+        int i0 = c * 32 * TA + 2 * k * 32 + l, i1 = (k < pairs) ? i0 + 32 : i0;
         i0 = min(i0, ud.n - 1);
         i1 = min(i1, ud.n - 1);
         const double* p0 = test_xy + 2 * (ud.test_off + i0);
@@ -151,8 +152,10 @@ template <int TA, bool MULTI>
 __global__ void __launch_bounds__(kThreads, 2)
     k_sweep(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
             const float2* __restrict__ cs32, float* __restrict__ dist32, unsigned long long* __restrict__ key) {
-    static_assert(TA % 2 == 0 && TA >= 2, "TA must be even");
-    constexpr int H = TA / 2;
+    static_assert(TA >= 2 && TA <= 18, "register tile out of range");
+    constexpr int H = TA / 2;          // packed pairs of test points per lane
+    constexpr bool TAIL = (TA & 1);    // plus one unpaired point when TA is odd
+    constexpr int S = H + (TAIL ? 1 : 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw + 8);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 
     const WorkItem w = work[blockIdx.x];
     const UnitDesc ud = units[w.unit];
-    const int a_elems = ud.n_chunks * H * 32;
+    const int a_elems = ud.n_chunks * S * 32;
     const int b_elems = ud.m_pairs;          // float4 per PAIR of reference points
     const int b_pts = 2 * ud.m_pairs;
     float4* sB = sA + a_elems;
@@ -190,9 +193,16 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (int ch = 0; ch < ud.n_chunks; ++ch) {
             uint64_t AX[H], AY[H];
             float row[TA];
+            float tx = 0.f, ty = 0.f;
+            if (TAIL) {
+                const float4 a = sA[(ch * S + H) * 32 + lane];
+                tx = fmaf(a.z, -cs.y, a.x * cs.x);
+                ty = fmaf(a.x, cs.y, a.z * cs.x);
+                row[TA - 1] = INF;
+            }
 #pragma unroll
             for (int k = 0; k < H; ++k) {
-                const float4 a = sA[(ch * H + k) * 32 + lane];
+                const float4 a = sA[(ch * S + k) * 32 + lane];
                 const uint64_t X2 = pk(a.x, a.y), Y2 = pk(a.z, a.w);
                 AX[k] = fma2(Y2, NS2, mul2(X2, C2));  // x' = x cos - y sin
                 AY[k] = fma2(X2, S2, mul2(Y2, C2));   // y' = x sin + y cos
@@ -205,6 +215,12 @@ __global__ void __launch_bounds__(kThreads, 2)
                 const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y);
                 const uint64_t bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
                 float c0 = INF, c1 = INF;
+                if (TAIL) {  // scalar FP32 ops for the unpaired point; its distances seed the column minima
+                    const float ex0 = tx - B.x, ey0 = ty - B.y, ex1 = tx - B.z, ey1 = ty - B.w;
+                    c0 = fmaf(ex0, ex0, ey0 * ey0);
+                    c1 = fmaf(ex1, ex1, ey1 * ey1);
+                    row[TA - 1] = min3(row[TA - 1], c0, c1);
+                }
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
                     const uint64_t dx0 = sub2(AX[k], bx0), dy0 = sub2(AY[k], by0);
