@@ -1,0 +1,19 @@
+"""Times k_sweep for every multimoda-rs_b200/variants/libmmrs_*.so (experimental builds; not shipped)."""
+import os, subprocess, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+if len(sys.argv) > 1 and sys.argv[1] == "--one":
+    sys.path[:0] = [str(ROOT), str(ROOT / "multimoda-rs_b200")]
+    import numpy as np
+    from multimodars import _native as nat
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import quick_bench as qb
+    ctx = nat.Context(0)
+    qb.run(ctx, 40, 520, 0.01, 180.0)
+    qb.run(ctx, 40, 510, 0.01, 180.0)
+    qb.run(ctx, 4, 2020, 0.05, 180.0)
+else:
+    for lib in sorted((ROOT / "multimoda-rs_b200" / "variants").glob("libmmrs_*.so")):
+        print("==", lib.name, flush=True)
+        env = dict(os.environ, MMRS_B200_LIB=str(lib))
+        subprocess.run([sys.executable, __file__, "--one"], env=env)
