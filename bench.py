@@ -223,6 +223,7 @@ def main():
 
     # ---- value: batch resident in HBM ------------------------------------------------------------------
     ctx.sweep_upload(txy, toff, rxy, roff, cen, [grid], mode=0)
+    plan = ctx.plan()
     for _ in range(W):
         ctx.sweep_run()
         gather(ctx.sweep_download())
@@ -293,12 +294,12 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_sweep<18,false>", "kernel_ms": k1,
+                "traffic": traffic, "kernel": f"k_sweep<{plan['TA']},{str(plan['multi']).lower()}>", "kernel_ms": k1,
                 "kernel_share_of_step": k1 / float(np.mean(dev_ms)),
                 "peak_source": f"148 SM x 128 FP32 lanes x 2 x {peak_src} (no FP32 figure in MEASURED_PEAKS.json)",
                 "ffma_probe_tflops": probe, "frac_of_ffma_probe": achieved / probe,
                 "algorithmic_flops_per_eval": F,
-                "executed_flops_per_eval": 5.0 * n * 576 + 6.0 * 576,
+                "executed_flops_per_eval": 5.0 * n * 32 * plan["TA"] + 6.0 * 32 * plan["TA"],
                 "note": "achieved counts the reference's arithmetic (10 N M + 6 N per evaluation); the kernel computes "
                         "each pair distance once for both directed passes, so it executes about half of that"}
 

@@ -102,8 +102,11 @@ typedef struct mmrs_sweep_opts {
      * (2e-6 and 2e-6, twice the analysed FP32 error bound).    */
     double shortlist_rel;
     double shortlist_abs;
-    int32_t shortlist_cap; /* per unit; <= 0 selects 64. Overflow => the unit is
-                              rechecked over ALL its candidates in f64.        */
+    int32_t shortlist_cap; /* AVERAGE recheck budget per unit (<= 0 selects 64): the units
+                              share one pool of max(n_units * shortlist_cap, 65536)
+                              items, a single unit may take any share of it. A unit
+                              that does not fit is rechecked over ALL its candidates
+                              in f64 (MMRS_FLAG_FULL_F64).                        */
     /* n_ties = number of rechecked candidates whose f64 distance is
      * <= best + tie_margin * max(1, Rmax). 0 = exact ties only.               */
     double tie_margin;
@@ -112,7 +115,7 @@ typedef struct mmrs_sweep_opts {
 } mmrs_sweep_opts;
 
 #define MMRS_FLAG_DEGENERATE 1 /* grid degenerate: best_angle = fallback, nothing evaluated */
-#define MMRS_FLAG_FULL_F64 2   /* shortlist overflowed: all candidates rechecked in f64     */
+#define MMRS_FLAG_FULL_F64 2   /* recheck pool exhausted: all candidates rechecked in f64   */
 #define MMRS_FLAG_EMPTY 4      /* empty point set: every candidate costs 0.0 (ref :86-88)   */
 
 typedef struct mmrs_unit_result {
@@ -135,6 +138,11 @@ int mmrs_sweep_batched(mmrs_ctx* ctx, const mmrs_sweep_batch* batch, const mmrs_
 int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* batch, const mmrs_sweep_opts* opts);
 int mmrs_sweep_run(mmrs_ctx* ctx);
 int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out);
+
+/* Launch plan of the uploaded batch: [0] register tile TA (test points per lane of the sweep
+ * kernel), [1] 1 if the test set is walked in several register chunks, [2] CTAs of the sweep
+ * launch, [3] dynamic shared memory per CTA in bytes.                                      */
+int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[4]);
 
 /* Diagnostics on the last run (valid until the next upload).                 */
 /* FP32 distance of every candidate of `unit` (needs opts.keep_dist32).       */
@@ -194,14 +202,17 @@ typedef struct mmrs_align_params {
     int64_t sample_size;
     int32_t smooth;
     int32_t bruteforce;
+    int32_t postprocessing; /* != 0: postprocess_geom_pair on every pair (modes 2-4),
+                               src/intravascular/processing/postprocessing.rs:12-87, tolerance 0.03 mm
+                               (binding/entry.rs:21) */
 } mmrs_align_params;
 
 /* Replaces the *_processing_rs orchestration of
  * src/intravascular/binding/entry.rs for a batch of `n_cases` independent
  * cases (patients): mode 4 = full_processing_rs (:71-361), 3 =
  * double_pair_processing_rs (:363-570), 2 = pair_processing_rs (:572-689),
- * 1 = single_processing_rs (:691-780); each with postprocessing = false and
- * write_obj = false (both out of scope). Input: n_cases *
+ * 1 = single_processing_rs (:691-780); each with write_obj = false (OBJ export is
+ * out of scope). Input: n_cases *
  * n_in(mode) geometry blobs (n_in = 4,4,2,1). Output: n_cases * n_out(mode)
  * blobs (8,4,2,1: pair ab = (a,b), cd, ac, bd) and n_cases * n_in log arrays.
  * All intrapullback sweeps of all cases run as ONE batch per search stage, all

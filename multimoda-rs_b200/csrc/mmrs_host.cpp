@@ -1267,6 +1267,195 @@ void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>
     }
 }
 
+// =============================================================================
+// Pair post-processing (processing/postprocessing.rs:12-87): equalise the z-sampling of the two
+// pullbacks of a pair, put the reference frames at the same z, trim to the common span around the
+// reference frame, optionally rebuild the aortic walls with a shared thickness. Host-only f64.
+// =============================================================================
+double mean_z_step(const Geometry& g) {  // get_avg_z_diff, :100-114
+    if (g.frames.size() < 2) return 0.0;
+    double sum = 0.0;
+    for (size_t i = 1; i < g.frames.size(); ++i) sum += g.frames[i].c[2] - g.frames[i - 1].c[2];
+    return sum / (double)(g.frames.size() - 1);
+}
+void set_frame_z(Frame& f, double z) {  // Frame::set_value(None, None, None, Some(z)), frame.rs:95-118
+    auto fix = [z](Contour& c) {
+        std::fill(c.z.begin(), c.z.end(), z);
+        if (c.has_c) c.c[2] = z;
+    };
+    fix(f.lumen);
+    for (auto& kv : f.extras) fix(kv.second);
+    if (f.has_ref) f.ref.z = z;
+    f.c[2] = z;
+}
+bool find_ref(const Geometry& g, size_t& idx) {  // find_ref_frame_idx, geometry.rs:62-69
+    for (auto& f : g.frames)
+        if (f.has_ref) {
+            idx = f.id;
+            return true;
+        }
+    return false;
+}
+Geometry respace(const Geometry& src, double step) {  // resample_by_diff, :116-140
+    Geometry g = src;
+    if (g.frames.empty()) throw InputErr("index out of bounds: resample_by_diff on an empty geometry");
+    size_t lo = 0;
+    for (size_t i = 1; i < g.frames.size(); ++i)
+        if (g.frames[i].c[2] < g.frames[lo].c[2]) lo = i;
+    if (lo) std::rotate(g.frames.begin(), g.frames.begin() + lo, g.frames.end());
+    const double z0 = g.frames[0].c[2];
+    for (size_t i = 1; i < g.frames.size(); ++i) set_frame_z(g.frames[i], z0 + (double)i * step);
+    return g;
+}
+std::vector<double> z_ladder(double ref_z, double start, double stop, double step) {  // predict_z_positions, :142-195
+    std::vector<double> z;
+    if (!std::isfinite(step) || step == 0.0) return z;
+    const double eps = 1e-9;
+    auto walk = [&](double cur, double inc, bool up, double limit) {
+        while (up ? cur <= limit + eps : cur >= limit - eps) {
+            z.push_back(cur);
+            cur += inc;
+            if (!std::isfinite(cur)) break;
+        }
+    };
+    if (std::fabs(ref_z - start) > eps && std::fabs(ref_z - stop) > eps) {
+        walk(ref_z, -step, false, start);
+        std::stable_sort(z.begin(), z.end());
+        walk(ref_z + step, step, true, stop);
+    } else if (stop >= start && step > 0.0) {
+        walk(start, step, true, stop);
+    } else if (stop <= start && step < 0.0) {
+        walk(start, step, false, stop);
+    }
+    return z;
+}
+Contour lerp_contour(const Contour& a, const Contour& b, double t) {  // blend_contour, :302-340
+    Contour o = a;
+    const size_t n = std::min(a.size(), b.size());
+    o.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        o.x[i] = a.x[i] + t * (b.x[i] - a.x[i]);
+        o.y[i] = a.y[i] + t * (b.y[i] - a.y[i]);
+    }
+    o.has_c = a.has_c && b.has_c;
+    if (o.has_c)
+        for (int k = 0; k < 3; ++k) o.c[k] = a.c[k] + t * (b.c[k] - a.c[k]);
+    o.has_at = a.has_at && b.has_at;
+    o.at = o.has_at ? a.at + t * (b.at - a.at) : 0.0;
+    o.has_pt = a.has_pt && b.has_pt;
+    o.pt = o.has_pt ? a.pt + t * (b.pt - a.pt) : 0.0;
+    return o;
+}
+Geometry resample_at(const Geometry& g, std::vector<double> zs) {  // new_frames_by_sample_rate, :197-300
+    if (g.frames.empty()) throw InputErr("index out of bounds: new_frames_by_sample_rate on an empty geometry");
+    std::stable_sort(zs.begin(), zs.end());
+    const double top = g.frames.back().c[2];
+    Geometry o;
+    o.label = g.label;
+    for (double z : zs) {
+        if (z > top) break;
+        auto hit = std::find_if(g.frames.begin(), g.frames.end(), [z](const Frame& f) { return std::fabs(f.c[2] - z) < 1e-9; });
+        if (hit != g.frames.end()) {
+            o.frames.push_back(*hit);
+            continue;
+        }
+        size_t k = 0;
+        while (k + 1 < g.frames.size() && !(g.frames[k].c[2] <= z && g.frames[k + 1].c[2] >= z)) ++k;
+        if (k + 1 >= g.frames.size()) throw InputErr("Cannot find frames to interpolate between");
+        const Frame &lo = g.frames[k], &up = g.frames[k + 1];
+        const double t = (z - lo.c[2]) / (up.c[2] - lo.c[2]);
+        Frame f;
+        f.id = lo.id;
+        f.lumen = lerp_contour(lo.lumen, up.lumen, t);
+        for (int kind : {(int)kEem, (int)kCalc, (int)kSide, (int)kCatheter, (int)kWall}) {
+            const Contour *a = lo.extra(kind), *b = up.extra(kind);
+            if (a && b) f.extras[kind] = lerp_contour(*a, *b, t);
+        }
+        f.c[0] = lo.c[0] + t * (up.c[0] - lo.c[0]);
+        f.c[1] = lo.c[1] + t * (up.c[1] - lo.c[1]);
+        f.c[2] = z;
+        o.frames.push_back(std::move(f));
+    }
+    std::stable_sort(o.frames.begin(), o.frames.end(), [](const Frame& a, const Frame& b) { return a.c[2] < b.c[2]; });
+    for (size_t i = 0; i < o.frames.size(); ++i) {
+        Frame& f = o.frames[i];
+        f.id = (uint32_t)i;
+        f.lumen.id = (uint32_t)i;
+        std::fill(f.lumen.z.begin(), f.lumen.z.end(), f.c[2]);
+        if (f.lumen.has_c) f.lumen.c[2] = f.c[2];
+        for (auto& kv : f.extras) {
+            kv.second.id = (uint32_t)i;
+            std::fill(kv.second.z.begin(), kv.second.z.end(), f.c[2]);
+        }
+        if (f.has_ref) f.ref.z = f.c[2];
+    }
+    return o;
+}
+void postprocess_pair(Geometry& ga, Geometry& gb, double tol, bool anomalous) {  // postprocess_geom_pair, :12-87
+    const double da = mean_z_step(ga), db = mean_z_step(gb);
+    size_t ra, rb;
+    if (!find_ref(ga, ra) || !find_ref(gb, rb)) throw InputErr("No reference point found in any frame");
+    const double ref_za = ga.frames.at(ra).c[2], ref_zb = gb.frames.at(rb).c[2];
+    auto span = [](const Geometry& g) {
+        const double a = g.frames.front().c[2], b = g.frames.back().c[2];
+        return a < b ? std::make_pair(a, b) : std::make_pair(b, a);
+    };
+    Geometry na, nb;
+    if ((da - db) < tol) {  // sic: signed difference (:93)
+        const double mean = (da + db) / 2.0;
+        na = respace(ga, mean);
+        nb = respace(gb, mean);
+    } else if (da < db) {
+        const auto s = span(gb);
+        nb = resample_at(gb, z_ladder(ref_zb, s.first, s.second, da));
+        na = respace(ga, da);
+    } else {
+        const auto s = span(ga);
+        na = resample_at(ga, z_ladder(ref_za, s.first, s.second, db));
+        nb = respace(gb, db);
+    }
+    size_t ra2, rb2;
+    if (!find_ref(na, ra2) || !find_ref(nb, rb2)) throw InputErr("No reference point found in any frame");
+    if (ra2 >= ga.frames.size() || rb2 >= gb.frames.size()) throw InputErr("index out of bounds: postprocess_geom_pair");
+    na.shift_all(0.0, 0.0, ga.frames[ra2].c[2] - gb.frames[rb2].c[2]);  // sic: indexes the ORIGINAL pair (:76-77)
+    // trim_geom_pair, :342-409
+    size_t ta = 0, tb = 0;
+    find_ref(na, ta);
+    find_ref(nb, tb);
+    if (ta > na.frames.size() || tb > nb.frames.size()) throw InputErr("attempt to subtract with overflow (trim_geom_pair)");
+    const size_t before = std::min(ta, tb), after = std::min(na.frames.size() - ta, nb.frames.size() - tb);
+    auto cut = [&](Geometry& g, size_t ref) {
+        const size_t lo = ref - before, hi = ref + after;
+        if (lo < hi && hi <= g.frames.size()) g.frames = std::vector<Frame>(g.frames.begin() + lo, g.frames.begin() + hi);
+        for (size_t i = 0; i < g.frames.size(); ++i) {
+            g.frames[i].id = (uint32_t)i;
+            g.frames[i].lumen.id = (uint32_t)i;
+            for (auto& kv : g.frames[i].extras) kv.second.id = (uint32_t)i;
+        }
+    };
+    cut(na, ta);
+    cut(nb, tb);
+    if (anomalous) {  // adjust_walls_anomalous_geom_pair, :411-470 (zip => the shorter length)
+        const size_t n = std::min(na.frames.size(), nb.frames.size());
+        na.frames.resize(n);
+        nb.frames.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            Contour &la = na.frames[i].lumen, &lb = nb.frames[i].lumen;
+            if (la.has_at || lb.has_at) {
+                const double t = (la.has_at && lb.has_at) ? (la.at + lb.at) / 2.0 : (la.has_at ? la.at : lb.at);
+                la.has_at = lb.has_at = true;
+                la.at = lb.at = t;
+            }
+        }
+        add_walls(na, true);
+        add_walls(nb, true);
+    }
+    na.label = ga.label;
+    nb.label = gb.label;
+    ga = std::move(na);
+    gb = std::move(nb);
+}
+
 template <class F>
 int guarded(mmrs_ctx* ctx, F&& f) {
     try {
@@ -1365,6 +1554,21 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
             out_blobs[c * n_out + slot] = to_malloc(v);
             out_lens[c * n_out + slot] = (int64_t)v.size();
         };
+        // a pair leaves as clones; maybe_postprocess (entry.rs:56-69) works on those clones with the
+        // case-wide anomalous flag (entry.rs:279-289)
+        auto emit_pair = [&](int64_t c, int slot, const Geometry& a, const Geometry& b) {
+            if (!params->postprocessing) {
+                emit(c, slot, a);
+                emit(c, slot + 1, b);
+                return;
+            }
+            bool anomalous = false;
+            for (int k = 0; k < n_in; ++k) anomalous = anomalous || w[c * n_in + k].anomalous;
+            Geometry ca = a, cb = b;
+            postprocess_pair(ca, cb, 0.03, anomalous);
+            emit(c, slot, ca);
+            emit(c, slot + 1, cb);
+        };
         if (mode == 1) {
             for (int64_t c = 0; c < n_cases; ++c) emit(c, 0, geo[c]);
             return;
@@ -1379,12 +1583,8 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
         align_between_many(S, level, *params);
         for (int64_t c = 0; c < n_cases; ++c) {
             Geometry* g = &geo[c * n_in];
-            emit(c, 0, g[0]);
-            emit(c, 1, g[1]);
-            if (mode >= 3) {
-                emit(c, 2, g[2]);  // pair CD holds C as it was BEFORE A<-C moves it
-                emit(c, 3, g[3]);  // ... and D before B<-D moves it again
-            }
+            emit_pair(c, 0, g[0], g[1]);
+            if (mode >= 3) emit_pair(c, 2, g[2], g[3]);  // pair CD holds C and D as they were BEFORE level 2 moves them
         }
         if (mode != 4) return;
         // level 2: A<-C and B<-D on the already moved B and D (entry.rs:243-277)
@@ -1397,10 +1597,8 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
         align_between_many(S, level, *params);
         for (int64_t c = 0; c < n_cases; ++c) {
             Geometry* g = &geo[c * n_in];
-            emit(c, 4, g[0]);
-            emit(c, 5, g[2]);
-            emit(c, 6, g[1]);
-            emit(c, 7, g[3]);
+            emit_pair(c, 4, g[0], g[2]);
+            emit_pair(c, 6, g[1], g[3]);
         }
     });
 }

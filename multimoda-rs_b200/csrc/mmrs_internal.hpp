@@ -66,6 +66,7 @@ struct mmrs_ctx {
     long long total_cands = 0;
     double opt_rel = 2e-6, opt_abs = 2e-6, tie_margin = 0.0;
     int cap = 64;
+    unsigned pool_cap = 0;
     int launches = 0, upload_launches = 0;
     long long eval_launches = 0;
     std::vector<mmrs_grid> grids;
@@ -79,7 +80,7 @@ struct mmrs_ctx {
     void* h_res = nullptr;  // pinned
     size_t h_res_cap = 0;
 
-    mmrs::DevBuf d_test, d_ref, d_units, d_work, d_lay, d_cs64, d_cs32, d_zero, d_dist32, d_key, d_rmax, d_sl_idx,
+    mmrs::DevBuf d_test, d_ref, d_units, d_work, d_lay, d_cs64, d_cs32, d_zero, d_dist32, d_key, d_rmax, d_sl_base,
         d_sl_dist, d_sl_count, d_items, d_nitems, d_res, d_tmp;
 
     // counters of the last mmrs_process_cases call

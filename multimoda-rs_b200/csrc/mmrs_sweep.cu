@@ -168,7 +168,7 @@ extern "C" void mmrs_ctx_destroy(mmrs_ctx* ctx) {
 
 void mmrs_ctx::free_all() {
     for (DevBuf* b : {&d_test, &d_ref, &d_units, &d_work, &d_lay, &d_cs64, &d_cs32, &d_zero, &d_dist32, &d_key,
-                      &d_rmax, &d_sl_idx, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp}) {
+                      &d_rmax, &d_sl_base, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr;
         b->cap = 0;
@@ -382,10 +382,13 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
     ENSURE(ctx->d_dist32, (size_t)dist_off * 4);
     ENSURE(ctx->d_key, U * 8);
     ENSURE(ctx->d_rmax, U * 4);
-    ENSURE(ctx->d_sl_idx, (size_t)U * ctx->cap * 4);
-    ENSURE(ctx->d_sl_dist, (size_t)U * ctx->cap * 8);
+    // item pool shared by all units: `cap` per unit on average, never less than 64 Ki items
+    ctx->pool_cap = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((unsigned long long)U * ctx->cap, 1ull << 16),
+                                                           0x7fffffffull);
+    ENSURE(ctx->d_sl_base, U * 4);
+    ENSURE(ctx->d_sl_dist, (size_t)ctx->pool_cap * 8);
     ENSURE(ctx->d_sl_count, U * 4);
-    ENSURE(ctx->d_items, (size_t)U * ctx->cap * 8);
+    ENSURE(ctx->d_items, (size_t)ctx->pool_cap * 8);
     ENSURE(ctx->d_nitems, 16);
     ENSURE(ctx->d_res, U * sizeof(UnitResultDev));
     if ((size_t)U > ctx->h_res_cap) {
@@ -480,24 +483,25 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
     k_shortlist<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p,
                                             (const unsigned long long*)ctx->d_key.p, (const unsigned*)ctx->d_rmax.p,
-                                            (float)ctx->opt_rel, (float)ctx->opt_abs, ctx->cap, (int*)ctx->d_sl_idx.p,
-                                            (int*)ctx->d_sl_count.p, (int2*)ctx->d_items.p, (unsigned*)ctx->d_nitems.p);
+                                            (float)ctx->opt_rel, (float)ctx->opt_abs, ctx->pool_cap,
+                                            (int*)ctx->d_sl_count.p, (unsigned*)ctx->d_sl_base.p, (int2*)ctx->d_items.p,
+                                            (unsigned*)ctx->d_nitems.p);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     {
         const int smem = exact_smem(ctx);
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const long long max_items = (long long)U * ctx->cap;
-        const int grid = (int)std::max<long long>(1, std::min<long long>(max_items, (long long)ctx->n_sm * 8));
+        const int grid = ctx->n_sm * 8;
         k_exact<<<grid, 256, smem, s>>>(units, (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
                                         (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
-                                        (const int2*)ctx->d_items.p, (const unsigned*)ctx->d_nitems.p,
-                                        (const int*)ctx->d_sl_idx.p, (double*)ctx->d_sl_dist.p, ctx->cap, ctx->max_pts);
+                                        (const int2*)ctx->d_items.p, (const unsigned*)ctx->d_nitems.p, ctx->pool_cap,
+                                        (double*)ctx->d_sl_dist.p, ctx->max_pts);
         CUDA_TRY(ctx, cudaGetLastError());
-        k_select<<<(unsigned)((U + 7) / 8), 256, 0, s>>>(units, (int)U, (const int*)ctx->d_sl_idx.p,
+        k_select<<<(unsigned)((U + 7) / 8), 256, 0, s>>>(units, (int)U, (const int2*)ctx->d_items.p,
                                                          (const double*)ctx->d_sl_dist.p, (const int*)ctx->d_sl_count.p,
+                                                         (const unsigned*)ctx->d_sl_base.p,
                                                          (const unsigned long long*)ctx->d_key.p,
-                                                         (const unsigned*)ctx->d_rmax.p, ctx->cap, ctx->tie_margin,
+                                                         (const unsigned*)ctx->d_rmax.p, ctx->tie_margin,
                                                          (UnitResultDev*)ctx->d_res.p);
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -592,16 +596,28 @@ extern "C" int mmrs_sweep_get_shortlist(mmrs_ctx* ctx, int64_t unit, int64_t* id
         return MMRS_OK;
     }
     int n = 0;
+    unsigned base = 0;
     CUDA_TRY(ctx, cudaMemcpy(&n, (const int*)ctx->d_sl_count.p + unit, 4, cudaMemcpyDeviceToHost));
-    if (n < 0) return set_err(ctx, MMRS_ERR_STATE, "shortlist overflowed; call mmrs_sweep_download first");
+    CUDA_TRY(ctx, cudaMemcpy(&base, (const unsigned*)ctx->d_sl_base.p + unit, 4, cudaMemcpyDeviceToHost));
+    if (n < 0) return set_err(ctx, MMRS_ERR_STATE, "shortlist pool overflowed; call mmrs_sweep_download first");
     *n_out = n;
     const int k = std::min(n, cap);
-    std::vector<int> idx(k);
+    std::vector<int2> it(k);
     if (k > 0) {
-        CUDA_TRY(ctx, cudaMemcpy(idx.data(), (const int*)ctx->d_sl_idx.p + unit * ctx->cap, k * 4, cudaMemcpyDeviceToHost));
-        CUDA_TRY(ctx, cudaMemcpy(dist_out, (const double*)ctx->d_sl_dist.p + unit * ctx->cap, k * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(it.data(), (const int2*)ctx->d_items.p + base, (size_t)k * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(dist_out, (const double*)ctx->d_sl_dist.p + base, (size_t)k * 8, cudaMemcpyDeviceToHost));
     }
-    for (int i = 0; i < k; ++i) idx_out[i] = idx[i];
+    for (int i = 0; i < k; ++i) idx_out[i] = it[i].y;
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[4]) {
+    if (!ctx || !plan_out) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_plan: NULL argument");
+    if (!ctx->ready) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_plan: no batch uploaded");
+    plan_out[0] = ctx->TA;
+    plan_out[1] = ctx->multi ? 1 : 0;
+    plan_out[2] = (int64_t)ctx->h_work.size();
+    plan_out[3] = (int64_t)ctx->smem_sweep;
     return MMRS_OK;
 }
 

@@ -303,44 +303,52 @@ __global__ void __launch_bounds__(kThreads, 2)
 }
 
 // =============================================================================
-// K2: shortlist = candidates whose FP32 distance lies inside the FP32 error
-// window above the minimum. Appends (unit, slot) items to a global list.
+// K2: shortlist = candidates whose FP32 distance lies inside the FP32 error window above the
+// minimum. Two scans of the unit's FP32 row (L2-resident): count, reserve a contiguous range of
+// the global item pool with one atomicAdd, then write (unit, candidate) items. A unit may take
+// any number of items; only when the POOL is exhausted is it flagged for the dense f64 path.
 // =============================================================================
 __global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __restrict__ dist32,
                             const unsigned long long* __restrict__ key, const unsigned* __restrict__ rmax_bits,
-                            float rel, float abs_scale, int cap, int* __restrict__ sl_idx, int* __restrict__ sl_count,
-                            int2* __restrict__ items, unsigned* __restrict__ n_items) {
-    __shared__ int s_n;
+                            float rel, float abs_scale, unsigned pool_cap, int* __restrict__ sl_count,
+                            unsigned* __restrict__ sl_base, int2* __restrict__ items, unsigned* __restrict__ n_items) {
+    __shared__ int s_n, s_pos;
     __shared__ unsigned s_base;
     const int u = blockIdx.x;
     const UnitDesc ud = units[u];
     if (ud.n_cand <= 0 || ud.n <= 0 || ud.m <= 0) {
-        if (threadIdx.x == 0) sl_count[u] = 0;
+        if (threadIdx.x == 0) {
+            sl_count[u] = 0;
+            sl_base[u] = 0;
+        }
         return;
     }
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x == 0) s_n = 0, s_pos = 0;
     __syncthreads();
     const float dmin = __uint_as_float((unsigned)(key[u] >> 32));
     const float thr = dmin * (1.0f + rel) + abs_scale * __uint_as_float(rmax_bits[u]);
     const float* d = dist32 + ud.dist_off;
-    for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x) {
-        if (d[c] <= thr) {
-            int pos = atomicAdd(&s_n, 1);
-            if (pos < cap) sl_idx[(long long)u * cap + pos] = c;
-        }
-    }
+    int mine = 0;
+    for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x) mine += (d[c] <= thr) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_n, mine);
     __syncthreads();
     const int n = s_n;
-    if (n > cap) {  // overflow: the host rechecks the whole unit in f64
-        if (threadIdx.x == 0) sl_count[u] = -n;
+    if (threadIdx.x == 0) s_base = atomicAdd(n_items, (unsigned)n);
+    __syncthreads();
+    const unsigned base = s_base;
+    const bool fits = (unsigned long long)base + (unsigned)n <= pool_cap;
+    if (threadIdx.x == 0) {
+        sl_base[u] = base;
+        sl_count[u] = fits ? n : -n;  // negative: pool exhausted, the host rechecks the whole unit in f64
+    }
+    if (!fits) {  // neutralise the part of the reservation that lies inside the pool
+        for (unsigned k = base + threadIdx.x; k < pool_cap && k < base + (unsigned)n; k += blockDim.x)
+            items[k] = make_int2(-1, 0);
         return;
     }
-    if (threadIdx.x == 0) {
-        sl_count[u] = n;
-        s_base = atomicAdd(n_items, (unsigned)n);
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += blockDim.x) items[s_base + k] = make_int2(u, k);
+    for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x)
+        if (d[c] <= thr) items[base + atomicAdd(&s_pos, 1)] = make_int2(u, c);
 }
 
 // =============================================================================
@@ -414,22 +422,22 @@ __device__ __forceinline__ double exact_cost(const UnitDesc& ud, const double* _
 __global__ void __launch_bounds__(256)
     k_exact(const UnitDesc* __restrict__ units, const double* __restrict__ test_xy, const double* __restrict__ ref_xy,
             const double2* __restrict__ cs64, const unsigned char* __restrict__ zero_flag,
-            const int2* __restrict__ items, const unsigned* __restrict__ n_items, const int* __restrict__ sl_idx,
-            double* __restrict__ sl_dist, int cap, int max_n) {
+            const int2* __restrict__ items, const unsigned* __restrict__ n_items, unsigned pool_cap,
+            double* __restrict__ sl_dist, int max_n) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_red = reinterpret_cast<double*>(smem_raw);
     double2* s_rot = reinterpret_cast<double2*>(smem_raw + 64);
     double2* s_ref = s_rot + max_n;
-    const unsigned total = *n_items;
+    const unsigned total = min(*n_items, pool_cap);
     for (unsigned it = blockIdx.x; it < total; it += gridDim.x) {
         const int2 item = items[it];
+        if (item.x < 0) continue;  // uniform per CTA
         const UnitDesc ud = units[item.x];
-        const long long slot = (long long)item.x * cap + item.y;
-        const int c = sl_idx[slot];
+        const int c = item.y;
         const double2 cs = cs64[ud.cand_off + c];
         const bool identity = zero_flag[ud.cand_off + c] != 0;
         const double d = exact_cost(ud, test_xy, ref_xy, cs.x, cs.y, identity, s_rot, s_ref, s_red);
-        if (threadIdx.x == 0) sl_dist[slot] = d;
+        if (threadIdx.x == 0) sl_dist[it] = d;
         __syncthreads();
     }
 }
@@ -460,10 +468,10 @@ __global__ void __launch_bounds__(256)
 // ties -> lowest candidate index: process_utils.rs:69-74) and the tie count.
 // One warp per unit.
 // =============================================================================
-__global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const int* __restrict__ sl_idx,
+__global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const int2* __restrict__ items,
                          const double* __restrict__ sl_dist, const int* __restrict__ sl_count,
-                         const unsigned long long* __restrict__ key, const unsigned* __restrict__ rmax_bits, int cap,
-                         double tie_margin, UnitResultDev* __restrict__ res) {
+                         const unsigned* __restrict__ sl_base, const unsigned long long* __restrict__ key,
+                         const unsigned* __restrict__ rmax_bits, double tie_margin, UnitResultDev* __restrict__ res) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (u >= n_units) return;
@@ -476,12 +484,12 @@ __global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const 
     r.n_ties = 0;
     r.flags = units[u].flags;
     if (n > 0) {
-        const long long base = (long long)u * cap;
+        const unsigned base = sl_base[u];
         double bd = __longlong_as_double(0x7ff0000000000000LL);
         int bi = 0x7fffffff;
         for (int k = lane; k < n; k += 32) {
             const double d = sl_dist[base + k];
-            const int i = sl_idx[base + k];
+            const int i = items[base + k].y;
             if (d < bd || (d == bd && i < bi)) {
                 bd = d;
                 bi = i;

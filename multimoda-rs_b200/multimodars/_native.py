@@ -48,7 +48,7 @@ class UnitResult(C.Structure):
 
 class AlignParams(C.Structure):
     _fields_ = [("step_deg", C.c_double), ("range_deg", C.c_double), ("sample_size", C.c_int64),
-                ("smooth", C.c_int32), ("bruteforce", C.c_int32)]
+                ("smooth", C.c_int32), ("bruteforce", C.c_int32), ("postprocessing", C.c_int32)]
 
 
 RESULT_DTYPE = np.dtype([("best_idx", "<i8"), ("best_angle", "<f8"), ("best_dist", "<f8"), ("best_dist_f32", "<f4"),
@@ -61,7 +61,7 @@ FLAG_DEGENERATE, FLAG_FULL_F64, FLAG_EMPTY = 1, 2, 4
 EXPORTS = [
     "mmrs_ctx_create", "mmrs_ctx_destroy", "mmrs_last_error", "mmrs_version", "mmrs_grid_from_reference_params",
     "mmrs_grid_angle", "mmrs_stage_plan", "mmrs_sweep_batched", "mmrs_sweep_upload", "mmrs_sweep_run",
-    "mmrs_sweep_download", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
+    "mmrs_sweep_download", "mmrs_sweep_plan", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
     "mmrs_process_cases", "mmrs_process_stats",
 ]
@@ -92,6 +92,7 @@ def lib():
         L.mmrs_sweep_upload.argtypes = [C.c_void_p, C.POINTER(SweepBatch), C.POINTER(SweepOpts)]
         L.mmrs_sweep_run.argtypes = [C.c_void_p]
         L.mmrs_sweep_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.mmrs_sweep_plan.argtypes = [C.c_void_p, c_i64p]
         L.mmrs_sweep_get_dist32.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int64]
         L.mmrs_sweep_get_shortlist.argtypes = [C.c_void_p, C.c_int64, c_i64p, c_dp, C.c_int32, c_i32p]
         L.mmrs_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), c_i32p]
@@ -201,6 +202,11 @@ class Context:
         self._check(lib().mmrs_sweep_download(self._p, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def plan(self):
+        p = (C.c_int64 * 4)()
+        self._check(lib().mmrs_sweep_plan(self._p, p))
+        return dict(TA=p[0], multi=bool(p[1]), ctas=p[2], smem_bytes=p[3])
+
     def dist32(self, unit, n_cand):
         out = np.empty(n_cand, dtype=np.float32)
         self._check(lib().mmrs_sweep_get_dist32(self._p, unit, out.ctypes.data_as(C.POINTER(C.c_float)), n_cand))
@@ -294,7 +300,7 @@ N_IN = {4: 4, 3: 4, 2: 2, 1: 1}
 N_OUT = {4: 8, 3: 4, 2: 2, 1: 1}
 
 
-def process_cases(ctx: Context, mode, blobs, step_deg, range_deg, sample_size, smooth, bruteforce):
+def process_cases(ctx: Context, mode, blobs, step_deg, range_deg, sample_size, smooth, bruteforce, postprocessing=False):
     """mmrs_process_cases for len(blobs)/N_IN[mode] cases. Returns (out_blobs, logs, anomalous)."""
     L = lib()
     n_in, n_out = N_IN[mode], N_OUT[mode]
@@ -308,7 +314,7 @@ def process_cases(ctx: Context, mode, blobs, step_deg, range_deg, sample_size, s
     lg = (c_dp * max(len(arrs), 1))()
     nl = (C.c_int64 * max(len(arrs), 1))()
     an = (C.c_int32 * max(len(arrs), 1))()
-    prm = AlignParams(step_deg, range_deg, int(sample_size), int(smooth), int(bruteforce))
+    prm = AlignParams(step_deg, range_deg, int(sample_size), int(smooth), int(bruteforce), int(postprocessing))
     L.mmrs_process_cases.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(c_dp), c_i64p,
                                      C.POINTER(AlignParams), C.POINTER(c_dp), c_i64p, C.POINTER(c_dp), c_i64p, c_i32p]
     rc = L.mmrs_process_cases(ctx._p, int(mode), n_cases, ptrs, lens, C.byref(prm), ob, ol, lg, nl, an)

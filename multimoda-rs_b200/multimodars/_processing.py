@@ -2,8 +2,8 @@
 src/intravascular/binding/functions.rs:143-1433), same names, argument order, defaults and
 return shapes, running on the B200 through libmmrs_b200.so (mmrs_process_cases).
 
-Out of scope in this build: `postprocessing=True` and `write_obj=True` raise
-NotImplementedError instead of silently doing something else; pass False for both, as the
+Out of scope in this build: `write_obj=True` (OBJ/MTL/texture export) raises
+NotImplementedError instead of silently doing something else; pass write_obj=False, as the
 reference's own benchmarks do (benchmarks/benchmark_bruteforce_stepsize.py:30-57)."""
 from __future__ import annotations
 
@@ -31,10 +31,7 @@ def _default_contour_types():
     return [PyContourType.Lumen, PyContourType.Catheter, PyContourType.Wall]
 
 
-def _unsupported(write_obj, postprocessing):
-    if postprocessing:
-        raise NotImplementedError("postprocessing=True (postprocess_geom_pair, processing/postprocessing.rs:12-87) "
-                                  "is outside this build's scope; pass postprocessing=False")
+def _unsupported(write_obj, postprocessing=False):
     if write_obj:
         raise NotImplementedError("write_obj=True (OBJ/MTL export, to_object/process.rs:13) is outside this "
                                   "build's scope; pass write_obj=False")
@@ -64,9 +61,9 @@ def _pair(out, i, label_a, label_b):
                           f"{label_a} - {label_b}")
 
 
-def _run(mode, blobs, labels, step, rng, sample_size, smooth, bruteforce):
+def _run(mode, blobs, labels, step, rng, sample_size, smooth, bruteforce, postprocessing=False):
     ctx = get_context()
-    out, logs, _ = nat.process_cases(ctx, mode, blobs, step, rng, sample_size, smooth, bruteforce)
+    out, logs, _ = nat.process_cases(ctx, mode, blobs, step, rng, sample_size, smooth, bruteforce, postprocessing)
     L = labels
     lg = tuple(_logs(l) for l in logs)
     if mode == 4:
@@ -102,7 +99,7 @@ def from_file_full(input_path_ab, input_path_cd, labels=None, step_rotation_deg=
     """functions.rs:143-245 -> (pair_ab, pair_cd, pair_ac, pair_bd, (logs_a, logs_b, logs_c, logs_d))."""
     _unsupported(write_obj, postprocessing)
     blobs, names = _four_from_paths(input_path_ab, input_path_cd, labels, image_center, radius, n_points)
-    return _run(4, blobs, names, step_rotation_deg, range_rotation_deg, sample_size, smooth, bruteforce)
+    return _run(4, blobs, names, step_rotation_deg, range_rotation_deg, sample_size, smooth, bruteforce, postprocessing)
 
 
 def from_file_doublepair(input_path_ab, input_path_cd, labels=None, step_rotation_deg=0.5, range_rotation_deg=90.0,
@@ -113,7 +110,7 @@ def from_file_doublepair(input_path_ab, input_path_cd, labels=None, step_rotatio
     """functions.rs:332-413 -> (pair_ab, pair_cd, (logs x4))."""
     _unsupported(write_obj, postprocessing)
     blobs, names = _four_from_paths(input_path_ab, input_path_cd, labels, image_center, radius, n_points)
-    return _run(3, blobs, names, step_rotation_deg, range_rotation_deg, sample_size, smooth, bruteforce)
+    return _run(3, blobs, names, step_rotation_deg, range_rotation_deg, sample_size, smooth, bruteforce, postprocessing)
 
 
 def from_file_singlepair(input_path, labels=None, step_rotation_deg=0.5, range_rotation_deg=90.0, sample_size=500,
@@ -126,7 +123,7 @@ def from_file_singlepair(input_path, labels=None, step_rotation_deg=0.5, range_r
     names = [labels[i] if use else _basename(input_path) for i in range(2)]
     blobs = [nat.geometry_from_dir(input_path, names[i], dia, image_center, radius, n_points)
              for i, dia in enumerate((True, False))]
-    return _run(2, blobs, names, step_rotation_deg, range_rotation_deg, sample_size, smooth, bruteforce)
+    return _run(2, blobs, names, step_rotation_deg, range_rotation_deg, sample_size, smooth, bruteforce, postprocessing)
 
 
 def from_file_single(input_path, labels=None, diastole=True, step_rotation_deg=0.5, range_rotation_deg=90.0,
@@ -139,9 +136,10 @@ def from_file_single(input_path, labels=None, diastole=True, step_rotation_deg=0
     return _run(1, [blob], [name], step_rotation_deg, range_rotation_deg, sample_size, smooth, bruteforce)
 
 
-def _from_inputs(mode, inputs, step, rng, sample_size, image_center, radius, n_points, smooth, bruteforce):
+def _from_inputs(mode, inputs, step, rng, sample_size, image_center, radius, n_points, smooth, bruteforce,
+                 postprocessing=False):
     blobs = [_blob_from_input(i, image_center, radius, n_points) for i in inputs]
-    return _run(mode, blobs, [i.label for i in inputs], step, rng, sample_size, smooth, bruteforce)
+    return _run(mode, blobs, [i.label for i in inputs], step, rng, sample_size, smooth, bruteforce, postprocessing)
 
 
 def from_array_full(input_data_a, input_data_b, input_data_c, input_data_d, step_rotation_deg=0.5,
@@ -153,7 +151,8 @@ def from_array_full(input_data_a, input_data_b, input_data_c, input_data_d, step
     """functions.rs:801-1010."""
     _unsupported(write_obj, postprocessing)
     return _from_inputs(4, [input_data_a, input_data_b, input_data_c, input_data_d], step_rotation_deg,
-                        range_rotation_deg, sample_size, image_center, radius, n_points, smooth, bruteforce)
+                        range_rotation_deg, sample_size, image_center, radius, n_points, smooth, bruteforce,
+                        postprocessing)
 
 
 def from_array_doublepair(input_data_a, input_data_b, input_data_c, input_data_d, step_rotation_deg=0.5,
@@ -164,7 +163,8 @@ def from_array_doublepair(input_data_a, input_data_b, input_data_c, input_data_d
     """functions.rs:1012-1187."""
     _unsupported(write_obj, postprocessing)
     return _from_inputs(3, [input_data_a, input_data_b, input_data_c, input_data_d], step_rotation_deg,
-                        range_rotation_deg, sample_size, image_center, radius, n_points, smooth, bruteforce)
+                        range_rotation_deg, sample_size, image_center, radius, n_points, smooth, bruteforce,
+                        postprocessing)
 
 
 def from_array_singlepair(input_data_a, input_data_b, step_rotation_deg=0.5, range_rotation_deg=90.0,
@@ -174,7 +174,7 @@ def from_array_singlepair(input_data_a, input_data_b, step_rotation_deg=0.5, ran
     """functions.rs:1189-1332."""
     _unsupported(write_obj, postprocessing)
     return _from_inputs(2, [input_data_a, input_data_b], step_rotation_deg, range_rotation_deg, sample_size,
-                        image_center, radius, n_points, smooth, bruteforce)
+                        image_center, radius, n_points, smooth, bruteforce, postprocessing)
 
 
 def from_array_single(input_data, step_rotation_deg=0.5, range_rotation_deg=90.0, sample_size=500,

@@ -1056,6 +1056,244 @@ inline GeometryPair align_between_geometries(Geometry& a, Geometry& b, double ro
     return p;
 }
 
+// ---- processing/postprocessing.rs ---------------------------------------------------
+// :100-114
+inline double get_avg_z_diff(const Geometry& g) {
+    if (g.frames.size() < 2) return 0.0;
+    double sum = 0.0;
+    for (size_t i = 1; i < g.frames.size(); ++i) sum += g.frames[i].cz - g.frames[i - 1].cz;
+    return sum / (double)(g.frames.size() - 1);
+}
+// Frame::set_value(None, None, None, Some(z)), frame.rs:95-118
+inline void frame_set_z(Frame& f, double z) {
+    for (auto& p : f.lumen.points) p.z = z;
+    if (f.lumen.centroid) std::get<2>(*f.lumen.centroid) = z;
+    for (auto& kv : f.extras) {
+        for (auto& p : kv.second.points) p.z = z;
+        if (kv.second.centroid) std::get<2>(*kv.second.centroid) = z;
+    }
+    if (f.reference_point) f.reference_point->z = z;
+    f.cz = z;
+}
+// :116-140
+inline Geometry resample_by_diff(const Geometry& gin, double diff) {
+    Geometry g = gin;
+    if (!g.frames.empty()) {
+        size_t min_idx = 0;  // Iterator::min_by keeps the FIRST minimum
+        for (size_t i = 1; i < g.frames.size(); ++i)
+            if (g.frames[i].cz < g.frames[min_idx].cz) min_idx = i;
+        if (min_idx != 0) std::rotate(g.frames.begin(), g.frames.begin() + min_idx, g.frames.end());
+    }
+    if (g.frames.empty()) throw Error("index out of bounds: resample_by_diff on an empty geometry");
+    double start_z = g.frames[0].cz;
+    for (size_t i = 1; i < g.frames.size(); ++i) frame_set_z(g.frames[i], start_z + (double)i * diff);
+    return g;
+}
+// :142-195
+inline std::vector<double> predict_z_positions(double ref_z, double start_z, double stop_z, double z_diff) {
+    std::vector<double> z;
+    if (!std::isfinite(z_diff) || z_diff == 0.0) return z;
+    const double eps = 1e-9;
+    if (std::fabs(ref_z - start_z) > eps && std::fabs(ref_z - stop_z) > eps) {
+        double cur = ref_z;
+        while (cur >= start_z - eps) {
+            z.push_back(cur);
+            cur -= z_diff;
+            if (!std::isfinite(cur)) break;
+        }
+        std::stable_sort(z.begin(), z.end());
+        cur = ref_z + z_diff;
+        while (cur <= stop_z + eps) {
+            z.push_back(cur);
+            cur += z_diff;
+            if (!std::isfinite(cur)) break;
+        }
+    } else {
+        double cur = start_z;
+        if (stop_z >= start_z && z_diff > 0.0) {
+            while (cur <= stop_z + eps) {
+                z.push_back(cur);
+                cur += z_diff;
+                if (!std::isfinite(cur)) break;
+            }
+        } else if (stop_z <= start_z && z_diff < 0.0) {
+            while (cur >= stop_z - eps) {
+                z.push_back(cur);
+                cur += z_diff;
+                if (!std::isfinite(cur)) break;
+            }
+        }
+    }
+    return z;
+}
+// :302-340
+inline Contour blend_contour(const Contour& c1, const Contour& c2, double t) {
+    Contour o;
+    size_t n = std::min(c1.points.size(), c2.points.size());
+    for (size_t i = 0; i < n; ++i) {
+        ContourPoint p = c1.points[i];
+        p.x = c1.points[i].x + t * (c2.points[i].x - c1.points[i].x);
+        p.y = c1.points[i].y + t * (c2.points[i].y - c1.points[i].y);
+        o.points.push_back(p);
+    }
+    if (c1.centroid && c2.centroid) {
+        auto [ax, ay, az] = *c1.centroid;
+        auto [bx, by, bz] = *c2.centroid;
+        o.centroid = Vec3(ax + t * (bx - ax), ay + t * (by - ay), az + t * (bz - az));
+    }
+    if (c1.aortic_thickness && c2.aortic_thickness)
+        o.aortic_thickness = *c1.aortic_thickness + t * (*c2.aortic_thickness - *c1.aortic_thickness);
+    if (c1.pulmonary_thickness && c2.pulmonary_thickness)
+        o.pulmonary_thickness = *c1.pulmonary_thickness + t * (*c2.pulmonary_thickness - *c1.pulmonary_thickness);
+    o.id = c1.id;
+    o.original_frame = c1.original_frame;
+    o.kind = c1.kind;
+    return o;
+}
+// :197-300
+inline Geometry new_frames_by_sample_rate(const Geometry& g, std::vector<double> z_coords) {
+    std::vector<Frame> nf;
+    std::stable_sort(z_coords.begin(), z_coords.end());
+    if (g.frames.empty()) throw Error("index out of bounds: new_frames_by_sample_rate on an empty geometry");
+    double max_z = g.frames.back().cz;
+    for (double z : z_coords) {
+        if (z > max_z) break;
+        const Frame* exact = nullptr;
+        for (auto& f : g.frames)
+            if (std::fabs(f.cz - z) < 1e-9) {
+                exact = &f;
+                break;
+            }
+        if (exact) {
+            nf.push_back(*exact);
+            continue;
+        }
+        const Frame *lo = nullptr, *up = nullptr;
+        for (size_t i = 0; i + 1 < g.frames.size(); ++i)
+            if (g.frames[i].cz <= z && g.frames[i + 1].cz >= z) {
+                lo = &g.frames[i];
+                up = &g.frames[i + 1];
+                break;
+            }
+        if (!lo) throw Error("Cannot find frames to interpolate between");
+        double t = (z - lo->cz) / (up->cz - lo->cz);
+        Frame f;
+        f.lumen = blend_contour(lo->lumen, up->lumen, t);
+        for (ContourType k : {Eem, Calcification, Sidebranch, Catheter, Wall}) {
+            auto a = lo->extras.find(k), b = up->extras.find(k);
+            if (a != lo->extras.end() && b != up->extras.end()) f.extras[k] = blend_contour(a->second, b->second, t);
+        }
+        f.id = lo->id;
+        f.cx = lo->cx + t * (up->cx - lo->cx);
+        f.cy = lo->cy + t * (up->cy - lo->cy);
+        f.cz = z;
+        nf.push_back(std::move(f));
+    }
+    std::stable_sort(nf.begin(), nf.end(), [](const Frame& a, const Frame& b) { return a.cz < b.cz; });
+    for (size_t i = 0; i < nf.size(); ++i) {
+        Frame& f = nf[i];
+        f.id = (uint32_t)i;
+        f.lumen.id = (uint32_t)i;
+        for (auto& p : f.lumen.points) p.z = f.cz;
+        if (f.lumen.centroid) std::get<2>(*f.lumen.centroid) = f.cz;
+        for (auto& kv : f.extras) {
+            kv.second.id = (uint32_t)i;
+            for (auto& p : kv.second.points) p.z = f.cz;
+        }
+        if (f.reference_point) f.reference_point->z = f.cz;
+    }
+    Geometry o;
+    o.frames = std::move(nf);
+    o.label = g.label;
+    return o;
+}
+// :342-409
+inline GeometryPair trim_geom_pair(const GeometryPair& p) {
+    auto trim = [](const Geometry& g, size_t ref, size_t before, size_t after) {
+        size_t start = ref - before, end = ref + after;
+        std::vector<Frame> fr;
+        if (start < end && end <= g.frames.size())
+            fr.assign(g.frames.begin() + start, g.frames.begin() + end);
+        else
+            fr = g.frames;
+        for (size_t i = 0; i < fr.size(); ++i) {
+            fr[i].id = (uint32_t)i;
+            fr[i].lumen.id = (uint32_t)i;
+            for (auto& kv : fr[i].extras) kv.second.id = (uint32_t)i;
+        }
+        Geometry o;
+        o.frames = std::move(fr);
+        o.label = g.label;
+        return o;
+    };
+    size_t ra = find_ref_frame_idx(p.geom_a).value_or(0), rb = find_ref_frame_idx(p.geom_b).value_or(0);
+    if (ra > p.geom_a.frames.size() || rb > p.geom_b.frames.size()) throw Error("attempt to subtract with overflow (trim_geom_pair)");
+    size_t before = std::min(ra, rb);
+    size_t after = std::min(p.geom_a.frames.size() - ra, p.geom_b.frames.size() - rb);
+    GeometryPair o;
+    o.geom_a = trim(p.geom_a, ra, before, after);
+    o.geom_b = trim(p.geom_b, rb, before, after);
+    o.label = p.label;
+    return o;
+}
+// :411-470
+inline GeometryPair adjust_walls_anomalous_geom_pair(const GeometryPair& p) {
+    std::vector<Frame> fa, fb;
+    size_t n = std::min(p.geom_a.frames.size(), p.geom_b.frames.size());
+    for (size_t i = 0; i < n; ++i) {
+        Frame a = p.geom_a.frames[i], b = p.geom_b.frames[i];
+        auto ta = a.lumen.aortic_thickness, tb = b.lumen.aortic_thickness;
+        if (ta || tb) {
+            double adj = (ta && tb) ? (*ta + *tb) / 2.0 : (ta ? *ta : *tb);
+            a.lumen.aortic_thickness = adj;
+            b.lumen.aortic_thickness = adj;
+        }
+        fa.push_back(std::move(a));
+        fb.push_back(std::move(b));
+    }
+    GeometryPair o;
+    o.geom_a.frames = create_wall_frames(fa, true);
+    o.geom_a.label = p.geom_a.label;
+    o.geom_b.frames = create_wall_frames(fb, true);
+    o.geom_b.label = p.geom_b.label;
+    o.label = p.label;
+    return o;
+}
+// :12-87
+inline GeometryPair postprocess_geom_pair(const GeometryPair& p, double tol, bool anomalous) {
+    double da = get_avg_z_diff(p.geom_a), db = get_avg_z_diff(p.geom_b);
+    bool same = (da - db) < tol;  // sic: signed difference (:93)
+    auto ria = find_ref_frame_idx(p.geom_a), rib = find_ref_frame_idx(p.geom_b);
+    if (!ria || !rib) throw Error("No reference point found in any frame");
+    double ref_z_a = p.geom_a.frames[*ria].cz, ref_z_b = p.geom_b.frames[*rib].cz;
+    GeometryPair r;
+    r.label = p.label;
+    auto span = [](const Geometry& g) {
+        double z0 = g.frames.front().cz, zn = g.frames.back().cz;
+        return (z0 < zn) ? std::make_pair(z0, zn) : std::make_pair(zn, z0);
+    };
+    if (same) {
+        double mean = (da + db) / 2.0;
+        r.geom_a = resample_by_diff(p.geom_a, mean);
+        r.geom_b = resample_by_diff(p.geom_b, mean);
+    } else if (da < db) {
+        auto [start, stop] = span(p.geom_b);
+        r.geom_b = new_frames_by_sample_rate(p.geom_b, predict_z_positions(ref_z_b, start, stop, da));
+        r.geom_a = resample_by_diff(p.geom_a, da);
+    } else {
+        auto [start, stop] = span(p.geom_a);
+        r.geom_a = new_frames_by_sample_rate(p.geom_a, predict_z_positions(ref_z_a, start, stop, db));
+        r.geom_b = resample_by_diff(p.geom_b, db);
+    }
+    auto ra2 = find_ref_frame_idx(r.geom_a), rb2 = find_ref_frame_idx(r.geom_b);
+    if (!ra2 || !rb2) throw Error("No reference point found in any frame");
+    if (*ra2 >= p.geom_a.frames.size() || *rb2 >= p.geom_b.frames.size()) throw Error("index out of bounds: postprocess_geom_pair");
+    double translation = p.geom_a.frames[*ra2].cz - p.geom_b.frames[*rb2].cz;  // sic: indexes the ORIGINAL pair (:76-77)
+    translate_geometry(r.geom_a, 0.0, 0.0, translation);
+    GeometryPair t = trim_geom_pair(r);
+    return anomalous ? adjust_walls_anomalous_geom_pair(t) : t;
+}
+
 // ---- ingest: io/input.rs, io/build.rs, geometry.rs reorder/proximal ------------
 inline std::vector<std::string> split_line(const std::string& line, char delim) {
     std::vector<std::string> out;
@@ -1443,9 +1681,10 @@ inline Geometry build_geometry_from_inputdata(const InputData& in, const std::st
 struct ProcessParams {
     double step_deg = 0.5, range_deg = 90.0;
     size_t sample_size = 500;
-    bool smooth = true, bruteforce = false;
+    bool smooth = true, bruteforce = false, postprocessing = false;
     int threads = 1;
 };
+constexpr double TOLERANCE = 0.03;  // entry.rs:21
 struct FullResult {
     GeometryPair ab, cd, ac, bd;
     std::vector<AlignLog> logs[4];
@@ -1455,16 +1694,26 @@ inline FullResult full_processing(std::vector<Geometry> geoms, const ProcessPara
     if (geoms.size() != 4) throw Error("Full processing requires exactly 4 geometries, got " + std::to_string(geoms.size()));
     FullResult r;
     Geometry g[4];
+    bool anomalous = false;
     for (int i = 0; i < 4; ++i) {
         auto w = align_frames_in_geometry(geoms[i], p.step_deg, p.range_deg, p.smooth, p.bruteforce, p.sample_size, p.threads);
         g[i] = std::move(w.geometry);
         r.logs[i] = std::move(w.logs);
+        anomalous = anomalous || w.anomalous;
     }
     r.ab = align_between_geometries(g[0], g[1], p.range_deg, p.step_deg, p.sample_size, p.threads);
     r.cd = align_between_geometries(g[2], g[3], p.range_deg, p.step_deg, p.sample_size, p.threads);
     if (!double_pair) {
         r.ac = align_between_geometries(g[0], g[2], p.range_deg, p.step_deg, p.sample_size, p.threads);
         r.bd = align_between_geometries(g[1], g[3], p.range_deg, p.step_deg, p.sample_size, p.threads);
+    }
+    if (p.postprocessing) {  // maybe_postprocess, entry.rs:56-69, :279-289
+        r.ab = postprocess_geom_pair(r.ab, TOLERANCE, anomalous);
+        r.cd = postprocess_geom_pair(r.cd, TOLERANCE, anomalous);
+        if (!double_pair) {
+            r.ac = postprocess_geom_pair(r.ac, TOLERANCE, anomalous);
+            r.bd = postprocess_geom_pair(r.bd, TOLERANCE, anomalous);
+        }
     }
     return r;
 }
@@ -1477,12 +1726,15 @@ inline PairResult pair_processing(std::vector<Geometry> geoms, const ProcessPara
     if (geoms.size() != 2) throw Error("Single Pair processing requires exactly 2 geometries, got " + std::to_string(geoms.size()));
     PairResult r;
     Geometry g[2];
+    bool anomalous = false;
     for (int i = 0; i < 2; ++i) {
         auto w = align_frames_in_geometry(geoms[i], p.step_deg, p.range_deg, p.smooth, p.bruteforce, p.sample_size, p.threads);
         g[i] = std::move(w.geometry);
         r.logs[i] = std::move(w.logs);
+        anomalous = anomalous || w.anomalous;
     }
     r.pair = align_between_geometries(g[0], g[1], p.range_deg, p.step_deg, p.sample_size, p.threads);
+    if (p.postprocessing) r.pair = postprocess_geom_pair(r.pair, TOLERANCE, anomalous);  // entry.rs:668-671
     return r;
 }
 

@@ -223,10 +223,11 @@ int ora_align_between(const double* blob_a, long len_a, const double* blob_b, lo
 // (:363-570), 2 = single pair (:572-689), 1 = single (:691-780).
 // in: `n_geoms` blobs (1, 2 or 4). out: for mode 4 eight blobs (ab.a, ab.b,
 // cd.a, cd.b, ac.a, ac.b, bd.a, bd.b), mode 3 four, mode 2 two, mode 1 one;
-// logs: one (n,7) array per input geometry. postprocessing / OBJ export are out of scope.
+// logs: one (n,7) array per input geometry. postprocessing != 0 applies postprocess_geom_pair
+// (processing/postprocessing.rs:12-87) to every pair (modes 2-4). OBJ export is out of scope.
 int ora_process(int mode, const double* const* blobs, const long* lens, double step_deg, double range_deg, int smooth,
-                int bruteforce, long sample_size, int threads, double** out_blobs, long* out_lens, double** out_logs,
-                long* out_nlogs) {
+                int bruteforce, long sample_size, int threads, int postprocessing, double** out_blobs, long* out_lens,
+                double** out_logs, long* out_nlogs) {
     return guard([&] {
         ProcessParams p;
         p.step_deg = step_deg;
@@ -235,6 +236,7 @@ int ora_process(int mode, const double* const* blobs, const long* lens, double s
         p.bruteforce = bruteforce != 0;
         p.sample_size = (size_t)sample_size;
         p.threads = threads;
+        p.postprocessing = postprocessing != 0;
         int n_in = mode >= 3 ? 4 : mode;
         std::vector<Geometry> geoms;
         for (int i = 0; i < n_in; ++i) geoms.push_back(decode_geometry(blobs[i], (size_t)lens[i], "g" + std::to_string(i)));
@@ -267,6 +269,29 @@ int ora_process(int mode, const double* const* blobs, const long* lens, double s
             out_nlogs[i] = (long)logs[i].size();
         }
     });
+}
+
+// postprocess_geom_pair (processing/postprocessing.rs:12-87) on one pair.
+int ora_postprocess_pair(const double* blob_a, long len_a, const double* blob_b, long len_b, double tol, int anomalous,
+                         double** out_a, long* out_a_len, double** out_b, long* out_b_len) {
+    return guard([&] {
+        GeometryPair p;
+        p.geom_a = decode_geometry(blob_a, (size_t)len_a, "a");
+        p.geom_b = decode_geometry(blob_b, (size_t)len_b, "b");
+        p.label = "a - b";
+        GeometryPair r = postprocess_geom_pair(p, tol, anomalous != 0);
+        auto va = encode_geometry(r.geom_a), vb = encode_geometry(r.geom_b);
+        *out_a = dup_vec(va);
+        *out_a_len = (long)va.size();
+        *out_b = dup_vec(vb);
+        *out_b_len = (long)vb.size();
+    });
+}
+// predict_z_positions (:142-195); returns the count.
+long ora_predict_z_positions(double ref_z, double start_z, double stop_z, double z_diff, double* out, long cap) {
+    auto z = predict_z_positions(ref_z, start_z, stop_z, z_diff);
+    for (long i = 0; i < (long)z.size() && i < cap; ++i) out[i] = z[i];
+    return (long)z.size();
 }
 
 // CPU baseline kernel for bench.py: the reference's loop nest (threads over

@@ -263,7 +263,7 @@ def align_between(blob_a, blob_b, rot_deg, step_deg, sample_size, threads=1):
     return _take(ob, ol.value), ang.value
 
 
-def process(mode, blobs, step_deg, range_deg, smooth, bruteforce, sample_size, threads=1):
+def process(mode, blobs, step_deg, range_deg, smooth, bruteforce, sample_size, threads=1, postprocessing=False):
     """mode 4 full / 3 double pair / 2 single pair / 1 single. Returns (out_blobs, logs)."""
     n_in = 4 if mode >= 3 else mode
     n_out = {4: 8, 3: 4, 2: 2, 1: 1}[mode]
@@ -276,7 +276,25 @@ def process(mode, blobs, step_deg, range_deg, smooth, bruteforce, sample_size, t
     lg = (c_dp * n_in)()
     nl = (C.c_long * n_in)()
     _check(lib().ora_process(int(mode), ptrs, lens, C.c_double(step_deg), C.c_double(range_deg), int(smooth),
-                             int(bruteforce), C.c_long(sample_size), int(threads), ob, ol, lg, nl))
+                             int(bruteforce), C.c_long(sample_size), int(threads), int(postprocessing), ob, ol, lg, nl))
     outs = [_take(ob[i], ol[i]) for i in range(n_out)]
     logs = [_take(lg[i], nl[i] * 7).reshape(-1, 7) for i in range(n_in)]
     return outs, logs
+
+
+def postprocess_pair(blob_a, blob_b, tol=0.03, anomalous=False):
+    a = np.ascontiguousarray(blob_a, dtype=np.float64)
+    b = np.ascontiguousarray(blob_b, dtype=np.float64)
+    oa, la, ob, lb = c_dp(), C.c_long(), c_dp(), C.c_long()
+    _check(lib().ora_postprocess_pair(a.ctypes.data_as(c_dp), C.c_long(len(a)), b.ctypes.data_as(c_dp), C.c_long(len(b)),
+                                      C.c_double(tol), int(anomalous), C.byref(oa), C.byref(la), C.byref(ob),
+                                      C.byref(lb)))
+    return _take(oa, la.value), _take(ob, lb.value)
+
+
+def predict_z_positions(ref_z, start_z, stop_z, z_diff, cap=100000):
+    out = np.empty(cap, dtype=np.float64)
+    lib().ora_predict_z_positions.restype = C.c_long
+    n = lib().ora_predict_z_positions(C.c_double(ref_z), C.c_double(start_z), C.c_double(stop_z), C.c_double(z_diff),
+                                      out.ctypes.data_as(c_dp), C.c_long(cap))
+    return out[:n].copy()

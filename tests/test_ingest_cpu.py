@@ -65,7 +65,7 @@ def test_pyinputdata_round_trip_and_types():
 
 
 def test_unsupported_options_fail_loudly():
-    with pytest.raises(NotImplementedError, match="postprocessing"):
+    with pytest.raises(NotImplementedError, match="write_obj"):      # the reference default; OBJ export is out of scope
         mm.from_file_full("a", "b")
-    with pytest.raises(NotImplementedError, match="write_obj"):
-        mm.from_file_full("a", "b", postprocessing=False)
+    with pytest.raises(NotImplementedError, match="align_three_point"):
+        mm.align_three_point(None, None, None, None, None)

@@ -147,3 +147,28 @@ def test_reference_guards_surface_as_errors():
         nat.process_cases(ctx, 1, [blob], 0.5, 30.0, 0, False, False)
     with pytest.raises(nat.MmrsError, match="Geometry contains no frames"):  # :32-34
         nat.process_cases(ctx, 1, [np.array([0.0])], 0.5, 30.0, 6, False, False)
+
+
+@pytest.mark.parametrize("mode", [4, 2])
+def test_postprocessing_matches_oracle(mode):
+    """postprocessing=True (the reference default): postprocess_geom_pair (postprocessing.rs:12-87) on
+    every pair — resample to a common z spacing, align reference frames, trim — bit-identical."""
+    pack = gio.inputs()
+    names = FULL[:nat.N_IN[mode]]
+    blobs = oracle_blobs(pack, names)
+    want_out, want_logs = ora.process(mode, blobs, 0.5, 90.0, True, False, 500, threads=8, postprocessing=True)
+    ins = [gio.py_input(mm, pack, n, d, n) for n, d in names]
+    kw = dict(step_rotation_deg=0.5, range_rotation_deg=90.0, sample_size=500, write_obj=False, postprocessing=True)
+    if mode == 4:
+        ab, cd, ac, bd, logs = mm.from_array_full(*ins, **kw)
+        got = [ab.geom_a, ab.geom_b, cd.geom_a, cd.geom_b, ac.geom_a, ac.geom_b, bd.geom_a, bd.geom_b]
+    else:
+        pair, logs = mm.from_array_singlepair(*ins, **kw)
+        got = [pair.geom_a, pair.geom_b]
+    for g, w in zip(got, want_out):
+        assert np.array_equal(g.to_blob(), w)
+    # trimmed to the common span: both members of a pair have the same number of frames
+    for k in range(0, len(got), 2):
+        assert len(got[k].frames) == len(got[k + 1].frames)
+    plain, _ = ora.process(mode, blobs, 0.5, 90.0, True, False, 500, threads=8, postprocessing=False)
+    assert any(not np.array_equal(a, b) for a, b in zip(plain, want_out))   # the step does something

@@ -147,19 +147,39 @@ def test_zero_angle_shortcut_is_bitwise(ctx):
 
 def test_plateau_ties_resolve_to_lowest_index(ctx):
     """A circle against itself: every angle ties (up to rounding). The reference keeps the
-    leftmost minimum (process_utils.rs:69-74); shortlist overflow must fall back to the full
-    f64 recheck and still agree."""
+    leftmost minimum (process_utils.rs:69-74); all 181 candidates must be rechecked in f64."""
     n = 180
     phi = np.linspace(0, 2 * np.pi, n, endpoint=False)
     p = np.stack([2.0 * np.cos(phi), 2.0 * np.sin(phi)], axis=1)
     g = nat.make_grid(2.0, 180.0)   # 2-deg steps == the point spacing: every candidate maps the circle onto itself
     res = ctx.sweep_batched(p, [0, n], p, [0, n], [[0.0, 0.0]], [g], mode=0, shortlist_cap=8)
     o = ora.sweep(p, p, (0.0, 0.0), 0, 2.0, 180.0)
-    assert res["flags"][0] & nat.FLAG_FULL_F64
+    assert res["n_shortlist"][0] == g.n_cand          # one unit may take any share of the recheck pool
     assert res["best_idx"][0] == o["index"]
     assert res["best_dist"][0] == o["cost"]
     idx, d = ctx.shortlist(0)
-    assert len(idx) == g.n_cand and (d == o["costs"]).all()
+    order = np.argsort(idx)
+    assert (idx[order] == np.arange(g.n_cand)).all() and (d[order] == o["costs"]).all()
+
+
+def test_recheck_pool_overflow_falls_back_to_full_f64(ctx):
+    """72 000 tying candidates exceed the 65 536-item recheck pool: the unit is rechecked over ALL its
+    candidates in f64 (MMRS_FLAG_FULL_F64) and must still agree with the oracle bit for bit."""
+    n = 72
+    phi = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    p = np.stack([2.0 * np.cos(phi), 2.0 * np.sin(phi)], axis=1)
+    q = np.stack([2.0 * np.cos(phi + 0.01), 2.0 * np.sin(phi + 0.01)], axis=1)
+    g = nat.make_grid(0.005, 180.0)
+    assert g.n_cand == 72000
+    # a huge window makes every candidate a shortlist member
+    res = ctx.sweep_batched(np.concatenate([p, q]), [0, n, 2 * n], np.concatenate([p, p]), [0, n, 2 * n],
+                            np.zeros((2, 2)), [g], mode=0, shortlist_abs=10.0)
+    for u, t in enumerate((p, q)):
+        o = ora.sweep(t, p, (0.0, 0.0), 0, 0.005, 180.0, threads=8)
+        assert res["best_idx"][u] == o["index"] and res["best_dist"][u] == o["cost"]
+    assert (res["flags"] & nat.FLAG_FULL_F64).any()
+    idx, d = ctx.shortlist(int(np.argmax(res["flags"] & nat.FLAG_FULL_F64)))
+    assert len(idx) == g.n_cand
 
 
 def test_wrap_duplicates_pick_first(ctx):
