@@ -136,6 +136,12 @@ int mmrs_sweep_batched(mmrs_ctx* ctx, const mmrs_sweep_batch* batch, const mmrs_
  * upload (H2D + layout), run (all kernels; results stay on the device),
  * download (D2H of the n_units results).                                     */
 int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* batch, const mmrs_sweep_opts* opts);
+/* Keeps the uploaded points (and their device layout) and replaces only the candidate grids —
+ * what the 2nd..4th window of find_best_rotation needs (align_within.rs:208-246): same point
+ * sets, a new grid per unit centred on the previous window's result. A unit whose grid is
+ * degenerate is skipped. */
+int mmrs_sweep_regrid(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, const int32_t* grid_of_unit,
+                      double tie_margin);
 int mmrs_sweep_run(mmrs_ctx* ctx);
 int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out);
 

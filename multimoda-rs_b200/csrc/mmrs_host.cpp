@@ -721,26 +721,55 @@ struct Searcher {
     void check(int rc) {
         if (rc != MMRS_OK) throw std::runtime_error(mmrs_last_error(ctx));
     }
-    // One stage for a batch of units. `centres` empty => centre None for every unit
-    // (one shared grid); otherwise one grid per unit. Returns per-unit results.
-    std::vector<mmrs_unit_result> stage(const SweepUnits& u, int mode, double step_deg, double window_deg,
-                                        double limes_deg, const std::vector<double>& centres, double tie_margin) {
-        const size_t U = u.count();
-        std::vector<mmrs_unit_result> out(U);
-        if (U == 0) return out;
-        std::vector<mmrs_grid> grids;
-        std::vector<int32_t> which;
-        if (centres.empty()) {
+    // Grids of one stage: `centres` empty => centre None for every unit (one shared grid);
+    // otherwise one grid per unit. A unit with skip[i] != 0 gets a degenerate grid (not swept).
+    void make_grids(size_t U, double step_deg, double window_deg, double limes_deg, const std::vector<double>& centres,
+                    const std::vector<char>* skip, std::vector<mmrs_grid>& grids, std::vector<int32_t>& which) {
+        grids.clear();
+        which.clear();
+        if (centres.empty() && !skip) {
             grids.resize(1);
             check(mmrs_grid_from_reference_params(step_deg, window_deg, 0, 0.0, limes_deg, &grids[0]));
-        } else {
-            grids.resize(U);
-            which.resize(U);
-            for (size_t i = 0; i < U; ++i) {
-                check(mmrs_grid_from_reference_params(step_deg, window_deg, 1, centres[i], limes_deg, &grids[i]));
-                which[i] = (int32_t)i;
-            }
+            return;
         }
+        grids.resize(U);
+        which.resize(U);
+        for (size_t i = 0; i < U; ++i) {
+            which[i] = (int32_t)i;
+            if (skip && (*skip)[i]) {
+                grids[i] = mmrs_grid{};
+                grids[i].degenerate = 1;
+                continue;
+            }
+            if (centres.empty())
+                check(mmrs_grid_from_reference_params(step_deg, window_deg, 0, 0.0, limes_deg, &grids[i]));
+            else
+                check(mmrs_grid_from_reference_params(step_deg, window_deg, 1, centres[i], limes_deg, &grids[i]));
+        }
+    }
+    std::vector<mmrs_unit_result> finish(size_t U, const std::vector<mmrs_grid>& grids,
+                                         const std::vector<int32_t>& which) {
+        std::vector<mmrs_unit_result> out(U);
+        check(mmrs_sweep_run(ctx));
+        check(mmrs_sweep_download(ctx, out.data()));
+        for (size_t i = 0; i < U; ++i) {
+            const mmrs_grid& g = grids[which.empty() ? 0 : i];
+            if (g.degenerate) continue;
+            stats[0] += 1;
+            stats[1] += g.n_cand;
+            stats[2] += out[i].n_shortlist > 0 ? out[i].n_shortlist : 0;
+        }
+        stats[4] += ctx->launches + ctx->upload_launches;
+        return out;
+    }
+    // Uploads the point sets of `u` and runs the first stage of their search.
+    std::vector<mmrs_unit_result> first(const SweepUnits& u, int mode, double step_deg, double window_deg,
+                                        double limes_deg, const std::vector<double>& centres, double tie_margin) {
+        const size_t U = u.count();
+        if (U == 0) return {};
+        std::vector<mmrs_grid> grids;
+        std::vector<int32_t> which;
+        make_grids(U, step_deg, window_deg, limes_deg, centres, nullptr, grids, which);
         mmrs_sweep_batch b{};
         b.n_units = (int64_t)U;
         b.test_xy = u.test.data();
@@ -754,14 +783,19 @@ struct Searcher {
         b.mode = mode;
         mmrs_sweep_opts o{};
         o.tie_margin = tie_margin;
-        check(mmrs_sweep_batched(ctx, &b, &o, out.data()));
-        stats[0] += (int64_t)U;
-        for (size_t i = 0; i < U; ++i) {
-            stats[1] += grids[which.empty() ? 0 : i].degenerate ? 0 : grids[which.empty() ? 0 : i].n_cand;
-            stats[2] += out[i].n_shortlist > 0 ? out[i].n_shortlist : 0;
-        }
-        stats[4] += ctx->launches + ctx->upload_launches;
-        return out;
+        check(mmrs_sweep_upload(ctx, &b, &o));
+        return finish(U, grids, which);
+    }
+    // Next window of the same search: the points stay on the device, only the grids change.
+    std::vector<mmrs_unit_result> next(size_t U, double step_deg, double window_deg, double limes_deg,
+                                       const std::vector<double>& centres, const std::vector<char>* skip,
+                                       double tie_margin) {
+        if (U == 0) return {};
+        std::vector<mmrs_grid> grids;
+        std::vector<int32_t> which;
+        make_grids(U, step_deg, window_deg, limes_deg, centres, skip, grids, which);
+        check(mmrs_sweep_regrid(ctx, grids.data(), (int64_t)grids.size(), which.empty() ? nullptr : which.data(), tie_margin));
+        return finish(U, grids, which);
     }
 };
 
@@ -1111,36 +1145,22 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
     std::vector<double> angle(U, 0.0);
     std::vector<int> good_stages(U, 0);  // number of leading stages certified
     {
-        std::vector<size_t> live(U);
-        std::iota(live.begin(), live.end(), 0);
-        for (int s = 0; s < plan.n && !live.empty(); ++s) {
-            SweepUnits sub;
-            const SweepUnits* use = &units;
-            std::vector<double> centres;
-            if (live.size() != U) {  // compact the still-certified units
-                for (size_t u : live) {
-                    sub.test.insert(sub.test.end(), units.test.begin() + 2 * units.toff[u],
-                                    units.test.begin() + 2 * units.toff[u + 1]);
-                    sub.ref.insert(sub.ref.end(), units.ref.begin() + 2 * units.roff[u],
-                                   units.ref.begin() + 2 * units.roff[u + 1]);
-                    sub.close_unit(0.0, 0.0);
-                }
-                use = &sub;
-            }
-            if (s > 0)
-                for (size_t u : live) centres.push_back(angle[u]);
-            auto res = S.stage(*use, 0, plan.step[s], plan.window[s], P.range_deg, centres, kTieMargin);
-            std::vector<size_t> next;
-            for (size_t k = 0; k < live.size(); ++k) {
-                const size_t u = live[k];
-                const bool unique = (res[k].flags & MMRS_FLAG_DEGENERATE) || res[k].n_ties == 1;
+        std::vector<char> dropped(U, 0);
+        size_t live = U;
+        for (int s = 0; s < plan.n && live > 0; ++s) {
+            auto res = (s == 0) ? S.first(units, 0, plan.step[0], plan.window[0], P.range_deg, {}, kTieMargin)
+                                : S.next(U, plan.step[s], plan.window[s], P.range_deg, angle, &dropped, kTieMargin);
+            for (size_t u = 0; u < U; ++u) {
+                if (dropped[u]) continue;
+                const bool unique = (res[u].flags & MMRS_FLAG_DEGENERATE) || res[u].n_ties == 1;
                 if (unique) {
-                    angle[u] = res[k].best_angle;
+                    angle[u] = res[u].best_angle;
                     good_stages[u] = s + 1;
-                    next.push_back(u);
+                } else {
+                    dropped[u] = 1;  // resolved on the chain below
+                    --live;
                 }
             }
-            live.swap(next);
         }
     }
     // 3. replay the chain on the host; re-search uncertified frames on the chain's own points
@@ -1160,10 +1180,14 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
                 gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.test);
                 gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.ref);
                 one.close_unit(cur.c[0], cur.c[1]);
+                bool uploaded = false;
                 for (int s = good_stages[u]; s < plan.n; ++s) {
                     std::vector<double> centres;
                     if (s > 0) centres.push_back(best);
-                    best = S.stage(one, 0, plan.step[s], plan.window[s], P.range_deg, centres, 0.0)[0].best_angle;
+                    auto r = uploaded ? S.next(1, plan.step[s], plan.window[s], P.range_deg, centres, nullptr, 0.0)
+                                      : S.first(one, 0, plan.step[s], plan.window[s], P.range_deg, centres, 0.0);
+                    uploaded = true;
+                    best = r[0].best_angle;
                 }
                 S.stats[3] += 1;
             }
@@ -1238,9 +1262,8 @@ void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>
     const Plan plan = make_plan(P.step_deg, P.range_deg, false);
     std::vector<double> angle(N, 0.0);
     for (int s = 0; s < plan.n; ++s) {
-        std::vector<double> centres;
-        if (s > 0) centres = angle;
-        auto res = S.stage(units, 1, plan.step[s], plan.window[s], P.range_deg, centres, 0.0);
+        auto res = (s == 0) ? S.first(units, 1, plan.step[0], plan.window[0], P.range_deg, {}, 0.0)
+                            : S.next(N, plan.step[s], plan.window[s], P.range_deg, angle, nullptr, 0.0);
         for (size_t k = 0; k < N; ++k) angle[k] = res[k].best_angle;
     }
     for (size_t k = 0; k < N; ++k) {

@@ -248,54 +248,10 @@ static int choose_ta(const std::vector<int>& ns) {
 }
 
 // ---- upload ----------------------------------------------------------------------------
-extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const mmrs_sweep_opts* o) {
-    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_sweep_upload: ctx is NULL");
-    if (!b || b->n_units < 0 || (b->n_units > 0 && (!b->test_off || !b->ref_off || !b->centre_xy || !b->grids)) ||
-        b->n_grids < 1 && b->n_units > 0)
-        return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: bad batch");
-    if (b->mode != 0 && b->mode != 1) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: mode must be 0 or 1");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    ctx->ready = false;
+// Points part of an upload: validates the offsets, chooses the register tile, lays every unit out in the
+// staging image (k_prep) and keeps the f64 points on the device. Grid-independent.
+static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
     const int64_t U = b->n_units;
-    ctx->n_units = U;
-    ctx->mode = b->mode;
-    ctx->opt_rel = (o && o->shortlist_rel > 0) ? o->shortlist_rel : 2e-6;
-    ctx->opt_abs = (o && o->shortlist_abs > 0) ? o->shortlist_abs : 2e-6;
-    ctx->cap = (o && o->shortlist_cap > 0) ? o->shortlist_cap : 64;
-    ctx->tie_margin = (o && o->tie_margin > 0) ? o->tie_margin : 0.0;
-    ctx->grids.assign(b->grids, b->grids + (U > 0 ? b->n_grids : 0));
-    ctx->grid_of_unit.resize(U);
-    for (int64_t u = 0; u < U; ++u) {
-        int g = b->grid_of_unit ? b->grid_of_unit[u] : 0;
-        if (g < 0 || g >= b->n_grids) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: grid_of_unit out of range");
-        ctx->grid_of_unit[u] = g;
-    }
-    if (U == 0) {
-        ctx->ready = true;
-        ctx->total_cands = 0;
-        return MMRS_OK;
-    }
-    // cos/sin tables: HOST glibc (bit-identical to Rust's f64::sin/cos), one per grid.
-    std::vector<long long> grid_off(b->n_grids + 1, 0);
-    for (int64_t g = 0; g < b->n_grids; ++g) {
-        const mmrs_grid& gr = b->grids[g];
-        if (gr.n_cand < 0 || gr.n_cand > (1ll << 31) - 2) return set_err(ctx, MMRS_ERR_ARG, "grid: bad n_cand");
-        grid_off[g + 1] = grid_off[g] + (gr.degenerate ? 0 : gr.n_cand);
-    }
-    const long long n_cs = grid_off[b->n_grids];
-    ctx->h_cs.resize(2 * (size_t)n_cs);
-    ctx->h_zero.resize((size_t)n_cs);
-    for (int64_t g = 0; g < b->n_grids; ++g) {
-        const mmrs_grid& gr = b->grids[g];
-        if (gr.degenerate) continue;
-        for (int64_t i = 0; i < gr.n_cand; ++i) {
-            const double a = mmrs_grid_angle(&gr, i);
-            ctx->h_cs[2 * (grid_off[g] + i)] = std::cos(a);
-            ctx->h_cs[2 * (grid_off[g] + i) + 1] = std::sin(a);
-            ctx->h_zero[grid_off[g] + i] = (b->mode == 0 && a == 0.0) ? 1 : 0;
-        }
-    }
-    // unit descriptors
     std::vector<int> ns(U);
     int max_n = 1, max_m = 1;
     for (int64_t u = 0; u < U; ++u) {
@@ -310,7 +266,7 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
     ctx->max_pts = std::max(max_n, max_m);
     std::vector<UnitDesc>& units = ctx->h_units;
     units.assign(U, UnitDesc{});
-    long long lay_off = 0, dist_off = 0;
+    long long lay_off = 0;
     bool multi = false;
     size_t smem_max = 0;
     for (int64_t u = 0; u < U; ++u) {
@@ -321,14 +277,6 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
         d.m = (int)(b->ref_off[u + 1] - b->ref_off[u]);
         d.cx = b->centre_xy[2 * u];
         d.cy = b->centre_xy[2 * u + 1];
-        const mmrs_grid& gr = b->grids[ctx->grid_of_unit[u]];
-        d.cand_off = grid_off[ctx->grid_of_unit[u]];
-        d.n_cand = gr.degenerate ? 0 : (int)gr.n_cand;
-        d.flags = 0;
-        if (gr.degenerate) d.flags |= MMRS_FLAG_DEGENERATE;
-        if (d.n == 0 || d.m == 0) d.flags |= MMRS_FLAG_EMPTY;
-        d.dist_off = dist_off;
-        dist_off += d.n_cand;
         d.lay_off = lay_off;
         if (d.n > 0 && d.m > 0) {
             d.n_chunks = (d.n + 32 * TA - 1) / (32 * TA);
@@ -351,44 +299,16 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
         return set_err(ctx, MMRS_ERR_ARG,
                        "unit too large for the shared-memory staging of the sweep kernel (" +
                            std::to_string(ctx->smem_sweep) + " B > 227 KB)");
-    ctx->total_cands = dist_off;
-    // work list: one CTA = one unit x one tile of candidates (8 warps, one candidate per warp per pass)
-    {
-        long long live = 0;
-        for (auto& d : units)
-            if (!(d.flags & (MMRS_FLAG_EMPTY | MMRS_FLAG_DEGENERATE))) live += d.n_cand;
-        const long long slots = (long long)ctx->n_sm * 2 * 4;  // CTAs for ~4 waves at 2 CTAs/SM
-        long long per_warp = (live + slots * kWarpsPerCta - 1) / (slots * kWarpsPerCta);
-        per_warp = std::max<long long>(1, std::min<long long>(per_warp, 8));
-        const int tile = (int)per_warp * kWarpsPerCta;
-        ctx->h_work.clear();
-        for (int64_t u = 0; u < U; ++u) {
-            const UnitDesc& d = units[u];
-            if (d.flags & (MMRS_FLAG_EMPTY | MMRS_FLAG_DEGENERATE)) continue;
-            for (int c0 = 0; c0 < d.n_cand; c0 += tile)
-                ctx->h_work.push_back(WorkItem{(int)u, c0, std::min(tile, d.n_cand - c0), 0});
-        }
-    }
     const size_t n_test = (size_t)b->test_off[U], n_ref = (size_t)b->ref_off[U];
     if ((n_test && !b->test_xy) || (n_ref && !b->ref_xy)) return set_err(ctx, MMRS_ERR_ARG, "point arrays are NULL");
     ENSURE(ctx->d_test, n_test * 16);
     ENSURE(ctx->d_ref, n_ref * 16);
     ENSURE(ctx->d_units, U * sizeof(UnitDesc));
-    ENSURE(ctx->d_work, ctx->h_work.size() * sizeof(WorkItem));
     ENSURE(ctx->d_lay, (size_t)lay_off * 16);
-    ENSURE(ctx->d_cs64, (size_t)n_cs * 16);
-    ENSURE(ctx->d_cs32, (size_t)n_cs * 8);
-    ENSURE(ctx->d_zero, (size_t)n_cs);
-    ENSURE(ctx->d_dist32, (size_t)dist_off * 4);
     ENSURE(ctx->d_key, U * 8);
     ENSURE(ctx->d_rmax, U * 4);
-    // item pool shared by all units: `cap` per unit on average, never less than 64 Ki items
-    ctx->pool_cap = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((unsigned long long)U * ctx->cap, 1ull << 16),
-                                                           0x7fffffffull);
     ENSURE(ctx->d_sl_base, U * 4);
-    ENSURE(ctx->d_sl_dist, (size_t)ctx->pool_cap * 8);
     ENSURE(ctx->d_sl_count, U * 4);
-    ENSURE(ctx->d_items, (size_t)ctx->pool_cap * 8);
     ENSURE(ctx->d_nitems, 16);
     ENSURE(ctx->d_res, U * sizeof(UnitResultDev));
     if ((size_t)U > ctx->h_res_cap) {
@@ -401,6 +321,86 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
     if (n_test) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_test.p, b->test_xy, n_test * 16, cudaMemcpyHostToDevice, s));
     if (n_ref) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ref.p, b->ref_xy, n_ref * 16, cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), U * sizeof(UnitDesc), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_rmax.p, 0, U * 4, s));
+    k_prep<<<(unsigned)U, 256, 0, s>>>((const UnitDesc*)ctx->d_units.p, (const double*)ctx->d_test.p,
+                                       (const double*)ctx->d_ref.p, (float4*)ctx->d_lay.p, (unsigned*)ctx->d_rmax.p,
+                                       TA);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->upload_launches = 1;
+    return MMRS_OK;
+}
+
+// Grid part: candidate tables (host glibc cos/sin), per-unit candidate ranges, the CTA work list.
+static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, const int32_t* grid_of_unit) {
+    const int64_t U = ctx->n_units;
+    ctx->grids.assign(grids, grids + n_grids);
+    ctx->grid_of_unit.resize(U);
+    for (int64_t u = 0; u < U; ++u) {
+        const int g = grid_of_unit ? grid_of_unit[u] : 0;
+        if (g < 0 || g >= n_grids) return set_err(ctx, MMRS_ERR_ARG, "grid_of_unit out of range");
+        ctx->grid_of_unit[u] = g;
+    }
+    // cos/sin tables: HOST glibc (bit-identical to Rust's f64::sin/cos), one per grid.
+    std::vector<long long> grid_off(n_grids + 1, 0);
+    for (int64_t g = 0; g < n_grids; ++g) {
+        const mmrs_grid& gr = grids[g];
+        if (gr.n_cand < 0 || gr.n_cand > (1ll << 31) - 2) return set_err(ctx, MMRS_ERR_ARG, "grid: bad n_cand");
+        grid_off[g + 1] = grid_off[g] + (gr.degenerate ? 0 : gr.n_cand);
+    }
+    const long long n_cs = grid_off[n_grids];
+    ctx->h_cs.resize(2 * (size_t)n_cs);
+    ctx->h_zero.resize((size_t)n_cs);
+    for (int64_t g = 0; g < n_grids; ++g) {
+        const mmrs_grid& gr = grids[g];
+        if (gr.degenerate) continue;
+        for (int64_t i = 0; i < gr.n_cand; ++i) {
+            const double a = mmrs_grid_angle(&gr, i);
+            ctx->h_cs[2 * (grid_off[g] + i)] = std::cos(a);
+            ctx->h_cs[2 * (grid_off[g] + i) + 1] = std::sin(a);
+            ctx->h_zero[grid_off[g] + i] = (ctx->mode == 0 && a == 0.0) ? 1 : 0;
+        }
+    }
+    std::vector<UnitDesc>& units = ctx->h_units;
+    long long dist_off = 0, live = 0;
+    for (int64_t u = 0; u < U; ++u) {
+        UnitDesc& d = units[u];
+        const mmrs_grid& gr = grids[ctx->grid_of_unit[u]];
+        d.cand_off = grid_off[ctx->grid_of_unit[u]];
+        d.n_cand = gr.degenerate ? 0 : (int)gr.n_cand;
+        d.flags = 0;
+        if (gr.degenerate) d.flags |= MMRS_FLAG_DEGENERATE;
+        if (d.n == 0 || d.m == 0) d.flags |= MMRS_FLAG_EMPTY;
+        d.dist_off = dist_off;
+        dist_off += d.n_cand;
+        if (!d.flags) live += d.n_cand;
+    }
+    ctx->total_cands = dist_off;
+    // work list: one CTA = one unit x one tile of candidates (8 warps, one candidate per warp per pass)
+    {
+        const long long slots = (long long)ctx->n_sm * 2 * 4;  // CTAs for ~4 waves at 2 CTAs/SM
+        long long per_warp = (live + slots * kWarpsPerCta - 1) / (slots * kWarpsPerCta);
+        per_warp = std::max<long long>(1, std::min<long long>(per_warp, 8));
+        const int tile = (int)per_warp * kWarpsPerCta;
+        ctx->h_work.clear();
+        for (int64_t u = 0; u < U; ++u) {
+            const UnitDesc& d = units[u];
+            if (d.flags) continue;
+            for (int c0 = 0; c0 < d.n_cand; c0 += tile)
+                ctx->h_work.push_back(WorkItem{(int)u, c0, std::min(tile, d.n_cand - c0), 0});
+        }
+    }
+    ENSURE(ctx->d_work, ctx->h_work.size() * sizeof(WorkItem));
+    ENSURE(ctx->d_cs64, (size_t)n_cs * 16);
+    ENSURE(ctx->d_cs32, (size_t)n_cs * 8);
+    ENSURE(ctx->d_zero, (size_t)n_cs);
+    ENSURE(ctx->d_dist32, (size_t)dist_off * 4);
+    // item pool shared by all units: `cap` per unit on average, never less than 64 Ki items
+    ctx->pool_cap = (unsigned)std::min<unsigned long long>(
+        std::max<unsigned long long>((unsigned long long)U * ctx->cap, 1ull << 16), 0x7fffffffull);
+    ENSURE(ctx->d_sl_dist, (size_t)ctx->pool_cap * 8);
+    ENSURE(ctx->d_items, (size_t)ctx->pool_cap * 8);
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), U * sizeof(UnitDesc), cudaMemcpyHostToDevice, s));
     if (!ctx->h_work.empty())
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work.p, ctx->h_work.data(), ctx->h_work.size() * sizeof(WorkItem),
                                       cudaMemcpyHostToDevice, s));
@@ -409,17 +409,61 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zero.p, ctx->h_zero.data(), (size_t)n_cs, cudaMemcpyHostToDevice, s));
         k_cs32<<<(unsigned)((n_cs + 255) / 256), 256, 0, s>>>((const double2*)ctx->d_cs64.p, (float2*)ctx->d_cs32.p,
                                                               n_cs);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->upload_launches += 1;
     }
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_rmax.p, 0, U * 4, s));
-    k_prep<<<(unsigned)U, 256, 0, s>>>((const UnitDesc*)ctx->d_units.p, (const double*)ctx->d_test.p,
-                                       (const double*)ctx->d_ref.p, (float4*)ctx->d_lay.p, (unsigned*)ctx->d_rmax.p,
-                                       TA);
-    CUDA_TRY(ctx, cudaGetLastError());
-    // The host arrays (and our own staging vectors) must outlive the async copies.
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    ctx->upload_launches = (n_cs ? 1 : 0) + 1;
-    ctx->ready = true;
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const mmrs_sweep_opts* o) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_sweep_upload: ctx is NULL");
+    if (!b || b->n_units < 0 || (b->n_units > 0 && (!b->test_off || !b->ref_off || !b->centre_xy || !b->grids)) ||
+        (b->n_grids < 1 && b->n_units > 0))
+        return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: bad batch");
+    if (b->mode != 0 && b->mode != 1) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: mode must be 0 or 1");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->ready = false;
     ctx->ran = false;
+    ctx->n_units = b->n_units;
+    ctx->mode = b->mode;
+    ctx->opt_rel = (o && o->shortlist_rel > 0) ? o->shortlist_rel : 2e-6;
+    ctx->opt_abs = (o && o->shortlist_abs > 0) ? o->shortlist_abs : 2e-6;
+    ctx->cap = (o && o->shortlist_cap > 0) ? o->shortlist_cap : 64;
+    ctx->tie_margin = (o && o->tie_margin > 0) ? o->tie_margin : 0.0;
+    if (b->n_units == 0) {
+        ctx->grids.clear();
+        ctx->grid_of_unit.clear();
+        ctx->h_units.clear();
+        ctx->h_work.clear();
+        ctx->total_cands = 0;
+        ctx->ready = true;
+        return MMRS_OK;
+    }
+    int rc = upload_points(ctx, b);
+    if (rc != MMRS_OK) return rc;
+    rc = apply_grids(ctx, b->grids, b->n_grids, b->grid_of_unit);
+    if (rc != MMRS_OK) return rc;
+    // The host arrays (and our own staging vectors) must outlive the async copies.
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ready = true;
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_sweep_regrid(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, const int32_t* grid_of_unit,
+                                 double tie_margin) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_sweep_regrid: ctx is NULL");
+    if (!ctx->ready) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_regrid: no batch uploaded");
+    if (ctx->n_units == 0) return MMRS_OK;
+    if (!grids || n_grids < 1) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_regrid: bad grids");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->ready = false;
+    ctx->ran = false;
+    ctx->tie_margin = tie_margin > 0 ? tie_margin : 0.0;
+    ctx->upload_launches = 0;
+    int rc = apply_grids(ctx, grids, n_grids, grid_of_unit);
+    if (rc != MMRS_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ready = true;
     return MMRS_OK;
 }
 

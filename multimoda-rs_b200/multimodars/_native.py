@@ -60,7 +60,7 @@ FLAG_DEGENERATE, FLAG_FULL_F64, FLAG_EMPTY = 1, 2, 4
 # every symbol include/mmrs_b200.h declares
 EXPORTS = [
     "mmrs_ctx_create", "mmrs_ctx_destroy", "mmrs_last_error", "mmrs_version", "mmrs_grid_from_reference_params",
-    "mmrs_grid_angle", "mmrs_stage_plan", "mmrs_sweep_batched", "mmrs_sweep_upload", "mmrs_sweep_run",
+    "mmrs_grid_angle", "mmrs_stage_plan", "mmrs_sweep_batched", "mmrs_sweep_upload", "mmrs_sweep_regrid", "mmrs_sweep_run",
     "mmrs_sweep_download", "mmrs_sweep_plan", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
     "mmrs_process_cases", "mmrs_process_stats",
@@ -90,6 +90,7 @@ def lib():
         L.mmrs_stage_plan.argtypes = [C.c_double, C.c_double, c_dp, c_dp]
         L.mmrs_sweep_batched.argtypes = [C.c_void_p, C.POINTER(SweepBatch), C.POINTER(SweepOpts), C.c_void_p]
         L.mmrs_sweep_upload.argtypes = [C.c_void_p, C.POINTER(SweepBatch), C.POINTER(SweepOpts)]
+        L.mmrs_sweep_regrid.argtypes = [C.c_void_p, C.POINTER(Grid), C.c_int64, c_i32p, C.c_double]
         L.mmrs_sweep_run.argtypes = [C.c_void_p]
         L.mmrs_sweep_download.argtypes = [C.c_void_p, C.c_void_p]
         L.mmrs_sweep_plan.argtypes = [C.c_void_p, c_i64p]
@@ -193,6 +194,12 @@ class Context:
         o = self._opts(**opts)
         self._check(lib().mmrs_sweep_upload(self._p, C.byref(b), C.byref(o)))
         self._n_units = U
+
+    def sweep_regrid(self, grids, grid_of_unit=None, tie_margin=0.0):
+        garr = (Grid * max(len(grids), 1))(*grids)
+        gou = None if grid_of_unit is None else np.ascontiguousarray(grid_of_unit, dtype=np.int32)
+        self._check(lib().mmrs_sweep_regrid(self._p, garr, len(grids), None if gou is None else gou.ctypes.data_as(c_i32p),
+                                            float(tie_margin)))
 
     def sweep_run(self):
         self._check(lib().mmrs_sweep_run(self._p))

@@ -223,6 +223,27 @@ def test_three_step_api_and_timings(ctx):
     check_against_oracle(ctx, tests, refs, cents, a, 0.1, 30.0, 0, check_dist32=False)
 
 
+def test_regrid_keeps_points_resident(ctx):
+    """mmrs_sweep_regrid: second window of find_best_rotation on the SAME uploaded points must equal a
+    fresh upload with those grids; skipped (degenerate-grid) units are reported as such."""
+    rng = np.random.default_rng(31)
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, [(300, 280), (520, 520), (128, 128)])
+    ctx.sweep_upload(txy, toff, rxy, roff, cents, [nat.make_grid(1.0, 60.0)], mode=0)
+    ctx.sweep_run()
+    coarse = ctx.sweep_download()
+    grids = [nat.make_grid(0.1, 5.0, center=float(c), limes_deg=60.0) for c in coarse["best_angle"]]
+    grids[2] = nat.make_grid(0.0, 5.0, center=0.125)          # degenerate: this unit is skipped
+    ctx.sweep_regrid(grids, grid_of_unit=[0, 1, 2])
+    ctx.sweep_run()
+    fine = ctx.sweep_download()
+    fresh = ctx.sweep_batched(txy, toff, rxy, roff, cents, grids, grid_of_unit=[0, 1, 2], mode=0)
+    assert (fine == fresh).all()
+    assert fine["flags"][2] & nat.FLAG_DEGENERATE and fine["best_angle"][2] == 0.125
+    for u in range(2):
+        o = ora.sweep(tests[u], refs[u], cents[u], 0, 0.1, 5.0, center=float(coarse["best_angle"][u]), limes_deg=60.0)
+        assert fine["best_idx"][u] == o["index"] and fine["best_dist"][u] == o["cost"]
+
+
 def test_rotation_linearity_property_full_size(ctx):
     """Size-independent property at BASELINE sizes: rotating the test contour by a grid angle
     shifts the arg-min by exactly that many candidates (no oracle needed)."""
@@ -240,6 +261,27 @@ def test_rotation_linearity_property_full_size(ctx):
     mid = (g.n_cand - 1) // 2
     assert abs(int(res["best_idx"][0]) - (mid + k)) <= 1
     assert res["best_dist"][0] < 1e-3
+
+
+def test_fp32_error_stays_inside_half_the_shortlist_window(ctx):
+    """Soundness of the FP32 filter: the f64 arg-min is guaranteed to be rechecked iff
+    |d32 - d64| <= window/2 for every candidate, window = 2e-6 * d_min + 2e-6 * Rmax."""
+    rng = np.random.default_rng(77)
+    sizes = [(520, 520), (505, 505), (2020, 2020), (64, 300), (600, 600)]
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, sizes)
+    g = nat.make_grid(0.25, 180.0)
+    res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=0, keep_dist32=True)
+    worst = 0.0
+    for u, (t, r, c) in enumerate(zip(tests, refs, cents)):
+        o = ora.sweep(t, r, c, 0, 0.25, 180.0, threads=8)
+        d32 = ctx.dist32(u, g.n_cand).astype(np.float64)
+        rmax = max(np.abs(t - c).max(), np.abs(r - c).max())
+        half_window = 0.5 * (2e-6 * o["costs"].min() + 2e-6 * rmax)
+        err = np.abs(d32 - o["costs"]).max()
+        worst = max(worst, err / half_window)
+        assert err <= half_window, (u, err, half_window)
+        assert res["best_idx"][u] == o["index"]
+    assert worst < 1.0
 
 
 def test_fp32_probe_reports_plausible_peak(ctx):
