@@ -107,8 +107,10 @@ typedef struct mmrs_sweep_opts {
                               items, a single unit may take any share of it. A unit
                               that does not fit is rechecked over ALL its candidates
                               in f64 (MMRS_FLAG_FULL_F64).                        */
-    /* n_ties = number of rechecked candidates whose f64 distance is
-     * <= best + tie_margin * max(1, Rmax). 0 = exact ties only.               */
+    /* n_ties = 1 + number of OTHER rechecked candidates whose f64 distance is
+     * <= best + tie_margin * max(1, Rmax) and whose wrapped angle differs from
+     * the winner's (same-angle duplicates, e.g. -pi / +pi, are not ambiguous).
+     * 0 = exact ties only.                                                    */
     double tie_margin;
     int32_t keep_dist32; /* != 0: keep the FP32 distance of every candidate for
                             mmrs_sweep_get_dist32 (tests, diagnostics).        */
@@ -124,7 +126,7 @@ typedef struct mmrs_unit_result {
     double best_dist;     /* f64 Hausdorff distance at best_idx, reference arithmetic        */
     float best_dist_f32;  /* FP32 sweep minimum (before the recheck)                         */
     int32_t n_shortlist;  /* candidates rechecked in f64                                     */
-    int32_t n_ties;       /* rechecked candidates within tie_margin of best (>= 1)           */
+    int32_t n_ties;       /* 1 + distinct-angle candidates within tie_margin of best         */
     int32_t flags;
 } mmrs_unit_result;
 

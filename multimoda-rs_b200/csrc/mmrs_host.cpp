@@ -25,6 +25,12 @@
 // =============================================================================
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <exception>
+#include <mutex>
+#include <thread>
+#include <chrono>
+#include <cstdio>
 #include <cerrno>
 #include <cmath>
 #include <cstdlib>
@@ -51,6 +57,50 @@ constexpr double kTieMargin = 1e-9;
 struct InputErr : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+
+// MMRS_TRACE=1: phase timings of mmrs_process_cases on stderr.
+struct Trace {
+    bool on = std::getenv("MMRS_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mmrs] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
+// Host-side parallelism over independent geometries (the reference runs its 4 pullbacks in a
+// crossbeam scope, binding/entry.rs:140-203). The first exception wins and is rethrown.
+template <class F>
+void parallel_for(size_t n, F&& f) {
+    const size_t nt = std::min<size_t>(n, std::max(1u, std::thread::hardware_concurrency()));
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex mu;
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nt; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n) return;
+                try {
+                    f(i);
+                } catch (...) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!err) err = std::current_exception();
+                    next.store(n);
+                    return;
+                }
+            }
+        });
+    for (auto& th : pool) th.join();
+    if (err) std::rethrow_exception(err);
+}
 
 inline double rad2deg(double r) { return r * (180.0 / kPi); }
 inline double rem_euclid(double a, double b) {
@@ -305,30 +355,51 @@ Geometry decode(const double* data, int64_t len) {
     }
     return g;
 }
-void write_contour(std::vector<double>& o, const Contour& c) {
+size_t contour_doubles(const Contour& c) { return 12 + 6 * c.size(); }
+size_t geometry_doubles(const Geometry& g) {
+    size_t n = 1;
+    for (auto& f : g.frames) {
+        n += 12 + contour_doubles(f.lumen);
+        for (auto& kv : f.extras) n += contour_doubles(kv.second);
+    }
+    return n;
+}
+double* write_contour(double* w, const Contour& c) {
     const double h[12] = {(double)c.kind, (double)c.id,        (double)c.original_frame, c.has_c ? 1.0 : 0.0,
                           c.has_c ? c.c[0] : 0.0, c.has_c ? c.c[1] : 0.0, c.has_c ? c.c[2] : 0.0, c.has_at ? 1.0 : 0.0,
                           c.has_at ? c.at : 0.0, c.has_pt ? 1.0 : 0.0, c.has_pt ? c.pt : 0.0, (double)c.size()};
-    o.insert(o.end(), h, h + 12);
-    for (size_t i = 0; i < c.size(); ++i) {
-        const double p[6] = {(double)c.fi[i], (double)c.pi[i], c.x[i], c.y[i], c.z[i], c.ao[i] ? 1.0 : 0.0};
-        o.insert(o.end(), p, p + 6);
+    std::memcpy(w, h, sizeof h);
+    w += 12;
+    const size_t n = c.size();
+    for (size_t i = 0; i < n; ++i, w += 6) {
+        w[0] = (double)c.fi[i];
+        w[1] = (double)c.pi[i];
+        w[2] = c.x[i];
+        w[3] = c.y[i];
+        w[4] = c.z[i];
+        w[5] = c.ao[i] ? 1.0 : 0.0;
     }
+    return w;
 }
-std::vector<double> encode(const Geometry& g) {
-    std::vector<double> o;
-    o.push_back((double)g.frames.size());
+// Encodes straight into a malloc'ed buffer (what the C ABI hands out; release with mmrs_free).
+double* encode_malloc(const Geometry& g, int64_t* len_out) {
+    const size_t n = geometry_doubles(g);
+    double* base = (double*)std::malloc(n * sizeof(double));
+    if (!base) throw std::bad_alloc();
+    double* w = base;
+    *w++ = (double)g.frames.size();
     for (auto& f : g.frames) {
-        const double h[11] = {(double)f.id, f.c[0], f.c[1], f.c[2], f.has_ref ? 1.0 : 0.0,
+        const double h[12] = {(double)f.id, f.c[0], f.c[1], f.c[2], f.has_ref ? 1.0 : 0.0,
                               f.has_ref ? (double)f.ref.fi : 0.0, f.has_ref ? (double)f.ref.pi : 0.0,
                               f.has_ref ? f.ref.x : 0.0, f.has_ref ? f.ref.y : 0.0, f.has_ref ? f.ref.z : 0.0,
-                              (f.has_ref && f.ref.ao) ? 1.0 : 0.0};
-        o.insert(o.end(), h, h + 11);
-        o.push_back((double)(1 + f.extras.size()));
-        write_contour(o, f.lumen);
-        for (auto& kv : f.extras) write_contour(o, kv.second);
+                              (f.has_ref && f.ref.ao) ? 1.0 : 0.0, (double)(1 + f.extras.size())};
+        std::memcpy(w, h, sizeof h);
+        w += 12;
+        w = write_contour(w, f.lumen);
+        for (auto& kv : f.extras) w = write_contour(w, kv.second);
     }
-    return o;
+    *len_out = (int64_t)n;
+    return base;
 }
 double* to_malloc(const std::vector<double>& v) {
     double* p = (double*)std::malloc(std::max<size_t>(v.size(), 1) * sizeof(double));
@@ -718,6 +789,7 @@ struct SweepUnits {
 struct Searcher {
     mmrs_ctx* ctx;
     int64_t* stats;
+    std::mutex gpu;  // one context = one stream: sweeps issued from the chain-replay threads are serialised
     void check(int rc) {
         if (rc != MMRS_OK) throw std::runtime_error(mmrs_last_error(ctx));
     }
@@ -1104,6 +1176,7 @@ struct WithinOut {
 
 void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_align_params& P,
                        std::vector<WithinOut>& outs) {
+    Trace tr;
     const size_t G = geoms.size();
     outs.assign(G, WithinOut{});
     struct Meta {
@@ -1126,19 +1199,41 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
             meta[g].n_cath = as_usize(std::ceil((double)c->size() * ratio));
         }
     }
-    // 1. decoupled units from the ORIGINAL frames, each centred on its own frame centroid
-    SweepUnits units;
-    for (size_t g = 0; g < G; ++g) {
-        Geometry& geo = *geoms[g];
-        meta[g].first_unit = units.count();
+    // 1. decoupled units from the ORIGINAL frames, each centred on its own frame centroid (built per pullback
+    //    in parallel, then concatenated in pullback order)
+    std::vector<SweepUnits> part(G);
+    parallel_for(G, [&](size_t g) {
+        const Geometry& geo = *geoms[g];
+        SweepUnits& u = part[g];
         for (size_t i = 1; i < geo.frames.size(); ++i) {
             const Frame &cur = geo.frames[i], &prev = geo.frames[i - 1];
-            gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, cur.c[0], cur.c[1], units.test);
-            gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, prev.c[0], prev.c[1], units.ref);
-            units.close_unit(0.0, 0.0);
+            gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, cur.c[0], cur.c[1], u.test);
+            gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, prev.c[0], prev.c[1], u.ref);
+            u.close_unit(0.0, 0.0);
+        }
+    });
+    SweepUnits units;
+    {
+        size_t nt = 0, nr = 0, nu = 0;
+        for (auto& p : part) nt += p.test.size(), nr += p.ref.size(), nu += p.count();
+        units.test.reserve(nt);
+        units.ref.reserve(nr);
+        units.centre.reserve(2 * nu);
+        for (size_t g = 0; g < G; ++g) {
+            meta[g].first_unit = units.count();
+            const int64_t t0 = (int64_t)units.test.size() / 2, r0 = (int64_t)units.ref.size() / 2;
+            units.test.insert(units.test.end(), part[g].test.begin(), part[g].test.end());
+            units.ref.insert(units.ref.end(), part[g].ref.begin(), part[g].ref.end());
+            units.centre.insert(units.centre.end(), part[g].centre.begin(), part[g].centre.end());
+            for (size_t k = 1; k < part[g].toff.size(); ++k) {
+                units.toff.push_back(t0 + part[g].toff[k]);
+                units.roff.push_back(r0 + part[g].roff[k]);
+            }
+            part[g] = SweepUnits{};
         }
     }
     const size_t U = units.count();
+    tr.lap("within: build units");
     const Plan plan = make_plan(P.step_deg, P.range_deg, P.bruteforce != 0);
     // 2. stage-by-stage batched search; a unit stays "certified" while every stage has a unique
     //    winner by more than kTieMargin
@@ -1163,8 +1258,9 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
             }
         }
     }
-    // 3. replay the chain on the host; re-search uncertified frames on the chain's own points
-    for (size_t g = 0; g < G; ++g) {
+    tr.lap("within: batched sweeps");
+    // 3. replay the chain on the host (one thread per pullback); re-search uncertified frames on the chain's own points
+    parallel_for(G, [&](size_t g) {
         Geometry& geo = *geoms[g];
         double cumulative = 0.0;
         for (size_t i = 1; i < geo.frames.size(); ++i) {
@@ -1180,6 +1276,7 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
                 gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.test);
                 gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.ref);
                 one.close_unit(cur.c[0], cur.c[1]);
+                std::lock_guard<std::mutex> lk(S.gpu);
                 bool uploaded = false;
                 for (int s = good_stages[u]; s < plan.n; ++s) {
                     std::vector<double> centres;
@@ -1215,7 +1312,8 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
         add_walls(geo, anomalous);
         if (P.smooth) smooth(geo);
         outs[g].anomalous = anomalous;
-    }
+    });
+    tr.lap("within: chain + post steps");
 }
 
 // =============================================================================
@@ -1266,7 +1364,7 @@ void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>
                             : S.next(N, plan.step[s], plan.window[s], P.range_deg, angle, nullptr, 0.0);
         for (size_t k = 0; k < N; ++k) angle[k] = res[k].best_angle;
     }
-    for (size_t k = 0; k < N; ++k) {
+    parallel_for(N, [&](size_t k) {
         Geometry &a = *pairs[k].first, &b = *pairs[k].second;
         // rotate_geometry_around_point, :95-145 (contour centroids rotate too, unlike Frame::rotate)
         const double ca = std::cos(angle[k]), sa = std::sin(angle[k]), cx = pivot[k][0], cy = pivot[k][1];
@@ -1287,7 +1385,7 @@ void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>
         }
         const Frame &fa = a.frames.at(a.ref_or_proximal()), &fb = b.frames.at(b.ref_or_proximal());
         b.shift_all(fa.c[0] - fb.c[0], fa.c[1] - fb.c[1], fa.c[2] - fb.c[2]);
-    }
+    });
 }
 
 // =============================================================================
@@ -1504,9 +1602,7 @@ extern "C" int mmrs_geometry_from_dir(mmrs_ctx* ctx, const char* path, const cha
     if (!path || !label || !blob_out || !len_out) return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_geometry_from_dir: NULL argument");
     return guarded(ctx, [&] {
         const Input in = read_directory(path, diastole != 0);
-        const auto v = encode(build_geometry(in, label, diastole != 0, icx, icy, radius, n_points));
-        *blob_out = to_malloc(v);
-        *len_out = (int64_t)v.size();
+        *blob_out = encode_malloc(build_geometry(in, label, diastole != 0, icx, icy, radius, n_points), len_out);
     });
 }
 
@@ -1543,9 +1639,7 @@ extern "C" int mmrs_geometry_from_arrays(mmrs_ctx* ctx, const double* lumen, int
             }
         }
         in.ref = conv(ref_point, 1)[0];
-        const auto v = encode(build_geometry(in, label, diastole != 0, icx, icy, radius, n_points));
-        *blob_out = to_malloc(v);
-        *len_out = (int64_t)v.size();
+        *blob_out = encode_malloc(build_geometry(in, label, diastole != 0, icx, icy, radius, n_points), len_out);
     });
 }
 
@@ -1560,40 +1654,48 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
     for (int i = 0; i < 5; ++i) ctx->stats[i] = 0;
     return guarded(ctx, [&] {
         Searcher S{ctx, ctx->stats};
+        Trace tr;
         std::vector<Geometry> geo((size_t)n_cases * n_in);
-        for (size_t k = 0; k < geo.size(); ++k) geo[k] = decode(blobs[k], blob_lens[k]);
+        parallel_for(geo.size(), [&](size_t k) { geo[k] = decode(blobs[k], blob_lens[k]); });
+        tr.lap("decode blobs");
         // intrapullback: every pullback of every case in one batch per stage (entry.rs:140-203)
         std::vector<Geometry*> all;
         for (auto& g : geo) all.push_back(&g);
         std::vector<WithinOut> w;
         align_within_many(S, all, *params, w);
+        tr.lap("align_within_many (total)");
         for (size_t k = 0; k < geo.size(); ++k) {
             out_logs[k] = to_malloc(w[k].logs);
             out_nlogs[k] = (int64_t)w[k].logs.size() / 7;
             if (out_anomalous) out_anomalous[k] = w[k].anomalous ? 1 : 0;
         }
-        auto emit = [&](int64_t c, int slot, const Geometry& g) {
-            const auto v = encode(g);
-            out_blobs[c * n_out + slot] = to_malloc(v);
-            out_lens[c * n_out + slot] = (int64_t)v.size();
+        // Outputs are clones taken at the moment the reference takes them (align_between.rs:91); they are
+        // post-processed (maybe_postprocess, entry.rs:56-69, with the case-wide anomalous flag, :279-289) and
+        // encoded in parallel at the end of each dependency level.
+        struct Out {
+            int64_t slot;
+            Geometry a, b;
+            bool pair, anomalous;
         };
-        // a pair leaves as clones; maybe_postprocess (entry.rs:56-69) works on those clones with the
-        // case-wide anomalous flag (entry.rs:279-289)
+        std::vector<Out> pending;
+        auto emit = [&](int64_t c, int slot, const Geometry& g) { pending.push_back(Out{c * n_out + slot, g, Geometry{}, false, false}); };
         auto emit_pair = [&](int64_t c, int slot, const Geometry& a, const Geometry& b) {
-            if (!params->postprocessing) {
-                emit(c, slot, a);
-                emit(c, slot + 1, b);
-                return;
-            }
             bool anomalous = false;
             for (int k = 0; k < n_in; ++k) anomalous = anomalous || w[c * n_in + k].anomalous;
-            Geometry ca = a, cb = b;
-            postprocess_pair(ca, cb, 0.03, anomalous);
-            emit(c, slot, ca);
-            emit(c, slot + 1, cb);
+            pending.push_back(Out{c * n_out + slot, a, b, true, anomalous});
+        };
+        auto flush = [&] {
+            parallel_for(pending.size(), [&](size_t i) {
+                Out& o = pending[i];
+                if (o.pair && params->postprocessing) postprocess_pair(o.a, o.b, 0.03, o.anomalous);
+                out_blobs[o.slot] = encode_malloc(o.a, &out_lens[o.slot]);
+                if (o.pair) out_blobs[o.slot + 1] = encode_malloc(o.b, &out_lens[o.slot + 1]);
+            });
+            pending.clear();
         };
         if (mode == 1) {
             for (int64_t c = 0; c < n_cases; ++c) emit(c, 0, geo[c]);
+            flush();
             return;
         }
         // inter-pullback level 1: A<-B (and C<-D), every case at once (entry.rs:206-240, :617-666)
@@ -1604,11 +1706,14 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
             if (mode >= 3) level.push_back({g + 2, g + 3});
         }
         align_between_many(S, level, *params);
+        tr.lap("align_between_many level 1");
         for (int64_t c = 0; c < n_cases; ++c) {
             Geometry* g = &geo[c * n_in];
             emit_pair(c, 0, g[0], g[1]);
             if (mode >= 3) emit_pair(c, 2, g[2], g[3]);  // pair CD holds C and D as they were BEFORE level 2 moves them
         }
+        flush();
+        tr.lap("postprocess + encode level 1");
         if (mode != 4) return;
         // level 2: A<-C and B<-D on the already moved B and D (entry.rs:243-277)
         level.clear();
@@ -1623,6 +1728,8 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
             emit_pair(c, 4, g[0], g[2]);
             emit_pair(c, 6, g[1], g[3]);
         }
+        flush();
+        tr.lap("level 2 + encode");
     });
 }
 

@@ -491,8 +491,10 @@ static int full_f64_unit(mmrs_ctx* ctx, int64_t u, UnitResultDev& r) {
     for (int c = 1; c < d.n_cand; ++c)
         if (h[c] < h[best]) best = c;
     const double lim = h[best] + ctx->tie_margin * std::fmax(1.0, (double)ctx->h_rmax[u]);
-    int ties = 0;
-    for (int c = 0; c < d.n_cand; ++c) ties += (h[c] <= lim) ? 1 : 0;
+    int ties = 1;
+    const double* cs = ctx->h_cs.data() + 2 * d.cand_off;
+    for (int c = 0; c < d.n_cand; ++c)
+        if (c != best && h[c] <= lim && (cs[2 * c] != cs[2 * best] || cs[2 * c + 1] != cs[2 * best + 1])) ++ties;
     r.best_idx = best;
     r.best_dist = h[best];
     r.n_shortlist = d.n_cand;
@@ -541,7 +543,8 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
                                         (const int2*)ctx->d_items.p, (const unsigned*)ctx->d_nitems.p, ctx->pool_cap,
                                         (double*)ctx->d_sl_dist.p, ctx->max_pts);
         CUDA_TRY(ctx, cudaGetLastError());
-        k_select<<<(unsigned)((U + 7) / 8), 256, 0, s>>>(units, (int)U, (const int2*)ctx->d_items.p,
+        k_select<<<(unsigned)((U + 7) / 8), 256, 0, s>>>(units, (int)U, (const double2*)ctx->d_cs64.p,
+                                                         (const int2*)ctx->d_items.p,
                                                          (const double*)ctx->d_sl_dist.p, (const int*)ctx->d_sl_count.p,
                                                          (const unsigned*)ctx->d_sl_base.p,
                                                          (const unsigned long long*)ctx->d_key.p,

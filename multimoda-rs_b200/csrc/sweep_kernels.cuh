@@ -468,8 +468,9 @@ __global__ void __launch_bounds__(256)
 // ties -> lowest candidate index: process_utils.rs:69-74) and the tie count.
 // One warp per unit.
 // =============================================================================
-__global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const int2* __restrict__ items,
-                         const double* __restrict__ sl_dist, const int* __restrict__ sl_count,
+__global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const double2* __restrict__ cs64,
+                         const int2* __restrict__ items, const double* __restrict__ sl_dist,
+                         const int* __restrict__ sl_count,
                          const unsigned* __restrict__ sl_base, const unsigned long long* __restrict__ key,
                          const unsigned* __restrict__ rmax_bits, double tie_margin, UnitResultDev* __restrict__ res) {
     const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -503,13 +504,23 @@ __global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const 
                 bi = oi;
             }
         }
+        // Tie count: rechecked candidates within the margin whose ANGLE differs from the winner's. A candidate
+        // with the winner's own angle (the -pi / +pi wrap duplicates of a +-180 deg grid) has the winner's cost
+        // in any arithmetic, so the lowest index wins there regardless and it is not an ambiguity.
         const double lim = bd + tie_margin * fmax(1.0, (double)__uint_as_float(rmax_bits[u]));
+        const long long co = units[u].cand_off;
+        const double2 wcs = cs64[co + bi];
         int ties = 0;
-        for (int k = lane; k < n; k += 32) ties += (sl_dist[base + k] <= lim) ? 1 : 0;
+        for (int k = lane; k < n; k += 32) {
+            const int i = items[base + k].y;
+            if (i == bi || sl_dist[base + k] > lim) continue;
+            const double2 c = cs64[co + i];
+            ties += (c.x != wcs.x || c.y != wcs.y) ? 1 : 0;
+        }
         for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
         r.best_idx = bi;
         r.best_dist = bd;
-        r.n_ties = ties;
+        r.n_ties = ties + 1;
     }
     if (lane == 0) res[u] = r;
 }

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -255,9 +256,14 @@ class Context:
 
 # ---- geometry-level entry points ---------------------------------------------------
 def _take_blob(ptr, n):
-    arr = np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].copy()
-    lib().mmrs_free(ptr)
-    return arr
+    """Wraps a malloc'ed f64 buffer handed out by the library as a numpy array WITHOUT copying; the buffer is
+    released with mmrs_free when the last view of it dies."""
+    if n <= 0:
+        lib().mmrs_free(ptr)
+        return np.zeros(0, dtype=np.float64)
+    buf = (C.c_double * n).from_address(C.addressof(ptr.contents))
+    weakref.finalize(buf, lib().mmrs_free, C.cast(ptr, C.c_void_p))
+    return np.frombuffer(buf, dtype=np.float64)
 
 
 def geometry_from_dir(path, label, diastole, image_center=(4.5, 4.5), radius=0.5, n_points=20, ctx: Context | None = None):

@@ -72,7 +72,7 @@ class PyContourPoint:
 
 def _rows_from_points(points):
     if isinstance(points, np.ndarray):
-        a = np.ascontiguousarray(points, dtype=np.float64)
+        a = points if (points.dtype == np.float64 and points.flags.c_contiguous) else np.ascontiguousarray(points, dtype=np.float64)
         if a.ndim != 2 or a.shape[1] != 6:
             raise ValueError("point array must be (n, 6): frame_index, point_index, x, y, z, aortic")
         return a
@@ -218,7 +218,7 @@ class PyGeometry:
             for k in range(nc):
                 h = b[pos:pos + 12]
                 n = int(h[11])
-                rows = b[pos + 12:pos + 12 + 6 * n].reshape(n, 6).copy()
+                rows = b[pos + 12:pos + 12 + 6 * n].reshape(n, 6)   # a view: the blob stays alive through it
                 pos += 12 + 6 * n
                 c = PyContour(int(h[1]), int(h[2]), rows, tuple(h[4:7]) if h[3] else None,
                               float(h[8]) if h[7] else None, float(h[10]) if h[9] else None, KIND_NAMES[int(h[0])])
@@ -316,14 +316,18 @@ def numpy_to_inputdata(lumen_arr, ref_point, diastole, record=None, eem_arr=None
             return None
         out = []
         frames = a[:, 0].astype(np.int64)
-        for fid in np.unique(frames):
-            sel = a[frames == fid]
+        order = np.argsort(frames, kind="stable")          # one pass: group rows by frame id, keeping row order
+        sf = frames[order]
+        cuts = np.flatnonzero(np.diff(sf)) + 1
+        for idx in np.split(order, cuts):
+            sel = a[idx]
+            fid = int(sel[0, 0])
             rows = np.zeros((len(sel), 6))
             rows[:, 0] = sel[:, 0]
             rows[:, 1] = np.arange(len(sel))
             rows[:, 2:5] = sel[:, 1:4]
-            out.append(PyContour(int(fid), int(fid), rows, (float(np.mean(sel[:, 1])), float(np.mean(sel[:, 2])),
-                                                           float(np.mean(sel[:, 3]))), None, None, kind))
+            out.append(PyContour(fid, fid, rows, (float(np.mean(sel[:, 1])), float(np.mean(sel[:, 2])),
+                                                  float(np.mean(sel[:, 3]))), None, None, kind))
         return out
 
     lumen_arr = num(lumen_arr)
