@@ -229,6 +229,17 @@ int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, const doubl
                        const int64_t* blob_lens, const mmrs_align_params* params, double** out_blobs,
                        int64_t* out_lens, double** out_logs, int64_t* out_nlogs, int32_t* out_anomalous);
 
+/* ---- multi-GPU: sharding the units of every batched sweep across ranks -------------------------
+ * One process per GPU. Every rank calls mmrs_process_cases with IDENTICAL inputs; inside, each batched
+ * sweep stage evaluates only this rank's contiguous block of units on its GPU and the per-unit results
+ * (40 B each) are combined with `exchange`, an in-place all-reduce(SUM) over int64 words across ranks
+ * (non-owned entries are zero, so the sum is an exact merge; the host binds it to ncclAllReduce /
+ * torch.distributed.all_reduce). The frame chain, post steps and inter-pullback bookkeeping are then
+ * replayed identically on every rank (cheap, O(points)). There is no other collective.
+ * world <= 1 or fn == NULL switches sharding off.                                                */
+typedef int (*mmrs_exchange_fn)(void* user, int64_t* buf, int64_t n_words);
+int mmrs_ctx_set_shard(mmrs_ctx* ctx, int32_t rank, int32_t world, mmrs_exchange_fn fn, void* user);
+
 /* Counters of the last mmrs_process_cases call: [0] units swept, [1] candidate
  * evaluations (FP32), [2] f64 rechecks, [3] units resolved on the sequential
  * chain (tie sets), [4] kernel launches.                                      */

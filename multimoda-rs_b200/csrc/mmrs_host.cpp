@@ -819,6 +819,21 @@ struct Searcher {
                 check(mmrs_grid_from_reference_params(step_deg, window_deg, 1, centres[i], limes_deg, &grids[i]));
         }
     }
+    // Unit sharding (mmrs_ctx_set_shard): rank r owns the r-th contiguous balanced block of the U units.
+    bool sharded(size_t U) const { return ctx->shard_world > 1 && ctx->exchange && U > 1; }
+    bool owns(size_t U, size_t u) const {
+        const size_t w = (size_t)ctx->shard_world, r = (size_t)ctx->shard_rank;
+        const size_t base = U / w, extra = U % w;
+        const size_t lo = r * base + std::min(r, extra), hi = lo + base + (r < extra ? 1 : 0);
+        return u >= lo && u < hi;
+    }
+    // Merges `skip` (may be null) with the units other ranks own.
+    const std::vector<char>* shard_skip(size_t U, const std::vector<char>* skip, std::vector<char>& store) const {
+        if (!sharded(U)) return skip;
+        store.assign(U, 0);
+        for (size_t u = 0; u < U; ++u) store[u] = ((skip && (*skip)[u]) || !owns(U, u)) ? 1 : 0;
+        return &store;
+    }
     std::vector<mmrs_unit_result> finish(size_t U, const std::vector<mmrs_grid>& grids,
                                          const std::vector<int32_t>& which) {
         std::vector<mmrs_unit_result> out(U);
@@ -832,6 +847,13 @@ struct Searcher {
             stats[2] += out[i].n_shortlist > 0 ? out[i].n_shortlist : 0;
         }
         stats[4] += ctx->launches + ctx->upload_launches;
+        if (sharded(U)) {  // keep only what this rank evaluated, then sum across ranks (zeros elsewhere)
+            static_assert(sizeof(mmrs_unit_result) == 40, "exchange works on 5 int64 words per unit");
+            for (size_t u = 0; u < U; ++u)
+                if (!owns(U, u)) std::memset(&out[u], 0, sizeof(mmrs_unit_result));
+            if (ctx->exchange(ctx->exchange_user, reinterpret_cast<int64_t*>(out.data()), (int64_t)U * 5) != 0)
+                throw std::runtime_error("mmrs: the exchange callback (all-reduce of per-unit results) failed");
+        }
         return out;
     }
     // Uploads the point sets of `u` and runs the first stage of their search.
@@ -841,7 +863,8 @@ struct Searcher {
         if (U == 0) return {};
         std::vector<mmrs_grid> grids;
         std::vector<int32_t> which;
-        make_grids(U, step_deg, window_deg, limes_deg, centres, nullptr, grids, which);
+        std::vector<char> store;
+        make_grids(U, step_deg, window_deg, limes_deg, centres, shard_skip(U, nullptr, store), grids, which);
         mmrs_sweep_batch b{};
         b.n_units = (int64_t)U;
         b.test_xy = u.test.data();
@@ -865,7 +888,8 @@ struct Searcher {
         if (U == 0) return {};
         std::vector<mmrs_grid> grids;
         std::vector<int32_t> which;
-        make_grids(U, step_deg, window_deg, limes_deg, centres, skip, grids, which);
+        std::vector<char> store;
+        make_grids(U, step_deg, window_deg, limes_deg, centres, shard_skip(U, skip, store), grids, which);
         check(mmrs_sweep_regrid(ctx, grids.data(), (int64_t)grids.size(), which.empty() ? nullptr : which.data(), tie_margin));
         return finish(U, grids, which);
     }
@@ -1731,6 +1755,16 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
         flush();
         tr.lap("level 2 + encode");
     });
+}
+
+extern "C" int mmrs_ctx_set_shard(mmrs_ctx* ctx, int32_t rank, int32_t world, mmrs_exchange_fn fn, void* user) {
+    if (!ctx) return mmrs::set_err(nullptr, MMRS_ERR_ARG, "mmrs_ctx_set_shard: ctx is NULL");
+    if (world > 1 && fn && (rank < 0 || rank >= world)) return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_ctx_set_shard: bad rank");
+    ctx->shard_rank = (world > 1 && fn) ? rank : 0;
+    ctx->shard_world = (world > 1 && fn) ? world : 1;
+    ctx->exchange = (world > 1) ? fn : nullptr;
+    ctx->exchange_user = user;
+    return MMRS_OK;
 }
 
 extern "C" int mmrs_process_stats(mmrs_ctx* ctx, int64_t s[5]) {

@@ -83,6 +83,11 @@ struct mmrs_ctx {
     mmrs::DevBuf d_test, d_ref, d_units, d_work, d_lay, d_cs64, d_cs32, d_zero, d_dist32, d_key, d_rmax, d_sl_base,
         d_sl_dist, d_sl_count, d_items, d_nitems, d_res, d_tmp;
 
+    // unit sharding across ranks (mmrs_ctx_set_shard)
+    int shard_rank = 0, shard_world = 1;
+    mmrs_exchange_fn exchange = nullptr;
+    void* exchange_user = nullptr;
+
     // counters of the last mmrs_process_cases call
     int64_t stats[5] = {0, 0, 0, 0, 0};
 

@@ -58,13 +58,15 @@ assert RESULT_DTYPE.itemsize == C.sizeof(UnitResult)
 
 FLAG_DEGENERATE, FLAG_FULL_F64, FLAG_EMPTY = 1, 2, 4
 
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_i64p, C.c_int64)
+
 # every symbol include/mmrs_b200.h declares
 EXPORTS = [
     "mmrs_ctx_create", "mmrs_ctx_destroy", "mmrs_last_error", "mmrs_version", "mmrs_grid_from_reference_params",
     "mmrs_grid_angle", "mmrs_stage_plan", "mmrs_sweep_batched", "mmrs_sweep_upload", "mmrs_sweep_regrid", "mmrs_sweep_run",
     "mmrs_sweep_download", "mmrs_sweep_plan", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
-    "mmrs_process_cases", "mmrs_process_stats",
+    "mmrs_process_cases", "mmrs_process_stats", "mmrs_ctx_set_shard",
 ]
 
 _lib = None
@@ -102,6 +104,7 @@ def lib():
                                       C.c_int32, c_dp, C.c_int64, c_dp]
         L.mmrs_fp32_probe.argtypes = [C.c_void_p, C.c_int32, c_dp]
         L.mmrs_process_stats.argtypes = [C.c_void_p, c_i64p]
+        L.mmrs_ctx_set_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int32, EXCHANGE_FN, C.c_void_p]
         _lib = L
     return _lib
 
@@ -247,6 +250,27 @@ class Context:
         t = C.c_double()
         self._check(lib().mmrs_fp32_probe(self._p, iters, C.byref(t)))
         return t.value
+
+    def set_shard(self, rank: int, world: int, allreduce_sum_int64):
+        """mmrs_ctx_set_shard. `allreduce_sum_int64(np.ndarray[int64]) -> None` sums the array in place across
+        ranks (see multimodars._dist.make_exchange). world <= 1 switches sharding off."""
+        if world <= 1 or allreduce_sum_int64 is None:
+            self._exchange_cb = None
+            self._check(lib().mmrs_ctx_set_shard(self._p, 0, 1, C.cast(None, EXCHANGE_FN), None))
+            return
+
+        def _cb(_user, buf, n):
+            try:
+                allreduce_sum_int64(np.ctypeslib.as_array(buf, shape=(n,)))
+                return 0
+            except Exception:  # surfaced as an MmrsError by the C side
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        self._exchange_cb = EXCHANGE_FN(_cb)   # keep the trampoline alive
+        self._check(lib().mmrs_ctx_set_shard(self._p, int(rank), int(world), self._exchange_cb, None))
 
     def process_stats(self):
         s = (C.c_int64 * 5)()

@@ -172,3 +172,21 @@ def test_postprocessing_matches_oracle(mode):
         assert len(got[k].frames) == len(got[k + 1].frames)
     plain, _ = ora.process(mode, blobs, 0.5, 90.0, True, False, 500, threads=8, postprocessing=False)
     assert any(not np.array_equal(a, b) for a, b in zip(plain, want_out))   # the step does something
+
+
+def test_unit_sharding_across_two_gpus():
+    """mmrs_ctx_set_shard under torchrun with 2 ranks: every rank reproduces the golden config-1 result and
+    all ranks agree on config 2 (scripts/sharded_check.py). Needs 2 GPUs; skipped on a 1-GPU box."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = gio.GOLD.parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", str(root / "scripts" / "sharded_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"config1_matches_golden": true' in r.stdout and '"config2_all_ranks_identical": true' in r.stdout
