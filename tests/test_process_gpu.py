@@ -190,3 +190,54 @@ def test_unit_sharding_across_two_gpus():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"config1_matches_golden": true' in r.stdout and '"config2_all_ranks_identical": true' in r.stdout
+
+
+# ---- edge cases the reference handles on this path ---------------------------------------------------------
+def _cmp_single(blob, step, rng, sample, smooth, brute):
+    ctx = mm.get_context()
+    want_out, want_logs, want_an = ora.align_within(blob, step, rng, smooth, brute, sample)
+    out, logs, an = nat.process_cases(ctx, 1, [blob], step, rng, sample, smooth, brute)
+    assert np.array_equal(logs[0], want_logs)
+    assert np.array_equal(out[0], want_out)
+    assert an[0] == want_an
+
+
+def test_no_catheter_and_downsampling():
+    """n_points = 0 (no synthetic catheter, align_within.rs:44-59 -> None) and sample_size < contour length
+    (strided down-sampling, contour.rs:47-58)."""
+    pack = gio.inputs()
+    a = gio.phase_arrays(pack, "rest", True)
+    blob = nat.geometry_from_arrays(a["lumen"], a["ref_point"], records=a["records"], diastole=True, n_points=0)
+    assert np.array_equal(blob, ora.build_geometry_from_arrays(a["lumen"], a["ref_point"], records=a["records"],
+                                                                diastole=True, n_points=0))
+    _cmp_single(blob, 0.5, 45.0, 200, False, False)
+    _cmp_single(blob, 1.0, 30.0, 37, True, True)
+
+
+def test_ragged_frames_and_tiny_geometries():
+    """Frames with different point counts (possible through the blob boundary: only ingest enforces equal counts,
+    integrity_check.rs:121-166), a two-frame pullback and a single-frame pullback (no frame pair at all)."""
+    rng = np.random.default_rng(5)
+    frames = []
+    for i, n in enumerate((40, 64, 33, 57, 40)):
+        phi = np.linspace(0, 2 * np.pi, n, endpoint=False)
+        r = 2.0 + 0.3 * np.cos(2 * phi + 0.2 * i) + rng.normal(0, 0.01, n)
+        x, y = 4.5 + r * np.cos(phi + 0.1 * i), 4.5 + r * np.sin(phi + 0.1 * i)
+        pts = np.stack([np.full(n, i), np.arange(n), x, y, np.full(n, float(i)), np.zeros(n)], 1)
+        c = (float(x.mean()), float(y.mean()), float(i))
+        frames.append(dict(id=i, centroid=c, reference_point=np.array([i, 0, 8.0, 4.5, float(i), 0]) if i == 0 else None,
+                           contours={0: dict(kind=0, id=i, original_frame=10 - i, centroid=c, aortic_thickness=None,
+                                             pulmonary_thickness=None, points=pts)}))
+    # smoothing indexes neighbours by the current frame's point count (geometry.rs:165-239) -> keep it off for ragged input
+    _cmp_single(ora.encode_geometry(frames), 0.5, 60.0, 500, False, False)
+    _cmp_single(ora.encode_geometry(frames[:2]), 0.1, 20.0, 16, False, False)
+    _cmp_single(ora.encode_geometry(frames[:1]), 0.5, 20.0, 16, False, False)
+
+
+def test_step_regimes_of_find_best_rotation():
+    """All four arms of the coarse-to-fine driver (align_within.rs:208-246): >= 1, [0.1, 1), [0.01, 0.1), < 0.01,
+    plus a range smaller than the 5-degree medium window."""
+    lumen, rp = fx.synthetic_pullback(6, 160, seed=42)
+    blob = nat.geometry_from_arrays(lumen, rp, diastole=True)
+    for step, rng_deg in ((2.0, 40.0), (0.3, 40.0), (0.03, 40.0), (0.004, 40.0), (0.03, 3.0), (0.004, 0.05)):
+        _cmp_single(blob, step, rng_deg, 120, False, False)
