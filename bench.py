@@ -197,6 +197,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout: ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = max(args.warmup, 3)
     K = args.steps
