@@ -140,6 +140,138 @@ class PyContour:
     def points_as_tuples(self):
         return [(float(r[2]), float(r[3]), float(r[4])) for r in self._sync()]
 
+    def _clone(self, rows=None, **kw):
+        c = PyContour(self.id, self.original_frame, (self._sync() if rows is None else rows).copy(), self.centroid,
+                      self.aortic_thickness, self.pulmonary_thickness, self.kind)
+        c._has_centroid = getattr(self, "_has_centroid", True)
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def _point(self, i):
+        return PyContourPoint(*self._sync()[i])
+
+    def find_farthest_points(self):
+        """contour.rs:227-243 — first pair with the largest 3-D distance."""
+        r = self._sync()
+        if len(r) == 0:
+            raise ValueError("contour has no points")
+        d = np.sqrt(((r[:, None, 2:5] - r[None, :, 2:5]) ** 2).sum(axis=2))
+        iu = np.triu_indices(len(r), 1)
+        if len(iu[0]) == 0:
+            return (self._point(0), self._point(0)), 0.0
+        k = int(np.argmax(d[iu]))  # first maximum in (i, j>i) row-major order == the Rust loop order
+        return (self._point(int(iu[0][k])), self._point(int(iu[1][k]))), float(d[iu][k])
+
+    def find_closest_opposite(self):
+        """contour.rs:247-309 — the pair closest to opposite (by angle about the centroid) with the shortest chord."""
+        r = self._sync()
+        n = len(r)
+        if n <= 2:
+            raise ValueError("Need at least 3 points")
+        cx, cy = self.centroid[0], self.centroid[1]
+        th = np.arctan2(r[:, 3] - cy, r[:, 2] - cx)
+        th = np.where(th < 0, th + 2 * math.pi, th)
+        best, best_d = (0, 1), float("inf")
+        for i in range(n):
+            delta = np.abs(th - th[i])
+            delta = np.where(delta > math.pi, 2 * math.pi - delta, delta)
+            diff = np.abs(delta - math.pi)
+            diff[i] = np.inf
+            j = int(np.argmin(diff))
+            dist = math.hypot(r[i, 2] - r[j, 2], r[i, 3] - r[j, 3])
+            if dist < best_d:
+                best_d, best = dist, (i, j)
+        return (self._point(best[0]), self._point(best[1])), best_d
+
+    def get_elliptic_ratio(self):
+        """contour.rs:313-343."""
+        r = self._sync()
+        n = len(r)
+        if n <= 2:
+            raise ValueError("Need at least 3 points")
+        major = self.find_farthest_points()[1]
+        j = (np.arange(n) + n // 2) % n
+        minor = float(np.sqrt(((r[:, 2:5] - r[j, 2:5]) ** 2).sum(axis=1)).min())
+        return minor / major if major < minor else major / minor
+
+    def get_area(self):
+        """contour.rs:345-363 — half the norm of the summed cross products."""
+        r = self._sync()
+        n = len(r)
+        if n < 3:
+            return 0.0
+        p1, p2 = r[:, 2:5], np.roll(r[:, 2:5], -1, axis=0)
+        cx = cy = cz = 0.0
+        for a, b in zip(p1, p2):
+            cx += a[1] * b[2] - a[2] * b[1]
+            cy += a[2] * b[0] - a[0] * b[2]
+            cz += a[0] * b[1] - a[1] * b[0]
+        return 0.5 * math.sqrt(cx * cx + cy * cy + cz * cz)
+
+    def rotate(self, angle_deg):
+        """py_contour.rs:215-224 — about the contour's own (recomputed) centroid."""
+        c = self._clone()
+        c.compute_centroid()
+        c._has_centroid = True
+        _rotate_rows(c._rows, angle_deg * (math.pi / 180.0), c.centroid[0], c.centroid[1])
+        return c
+
+    def translate(self, dx, dy, dz):
+        """py_contour.rs:245-249."""
+        c = self._clone()
+        c._rows[:, 2] = c._rows[:, 2] + dx
+        c._rows[:, 3] = c._rows[:, 3] + dy
+        c._rows[:, 4] = c._rows[:, 4] + dz
+        return c
+
+    def sort_contour_points(self):
+        """contour.rs:368-405."""
+        c = self._clone()
+        c._rows = _sort_rows(c._rows)
+        return c
+
+
+def _rotate_rows(rows, angle, cx, cy):
+    """ContourPoint::rotate on an (n, 6) row block, in place (contour_point.rs:38-52)."""
+    if angle == 0.0 or len(rows) == 0:
+        return
+    ca, sa = math.cos(angle), math.sin(angle)
+    x, y = rows[:, 2] - cx, rows[:, 3] - cy
+    rows[:, 2], rows[:, 3] = x * ca - y * sa + cx, x * sa + y * ca + cy
+
+
+def _sort_rows(rows):
+    """Contour::sort_contour_points (contour.rs:368-405): stable ascending atan2 about the mean, the LAST
+    highest-y point first, point_index = position."""
+    n = len(rows)
+    if n == 0:
+        return rows
+    sx = sy = 0.0
+    for r in rows:
+        sx += r[2]
+        sy += r[3]
+    cx, cy = sx / n, sy / n
+    key = np.array([math.atan2(r[3] - cy, r[2] - cx) for r in rows])
+    rows = rows[np.argsort(key, kind="stable")]
+    start = 0
+    for i in range(1, n):
+        if not (rows[i, 3] < rows[start, 3]):
+            start = i
+    rows = np.roll(rows, -start, axis=0)
+    rows[:, 1] = np.arange(n)
+    return rows
+
+
+def _centroid_rows(rows):
+    sx = sy = sz = 0.0
+    for r in rows:
+        sx += r[2]
+        sy += r[3]
+        sz += r[4]
+    n = float(len(rows))
+    return (sx / n, sy / n, sz / n)
+
 
 class PyFrame:
     """src/types/binding/py_frame.rs:32-130."""
@@ -155,6 +287,50 @@ class PyFrame:
         return (f"Frame(id={self.id}, centroid=({self.centroid[0]:.2f}, {self.centroid[1]:.2f}, "
                 f"{self.centroid[2]:.2f}), lumen_points={len(self.lumen)}, extras={sorted(self.extras)}, "
                 f"has_reference_point={self.reference_point is not None})")
+
+    def _clone(self):
+        rp = self.reference_point
+        return PyFrame(self.id, self.centroid, self.lumen._clone(), {k: c._clone() for k, c in self.extras.items()},
+                       None if rp is None else PyContourPoint(*rp._row()))
+
+    def rotate(self, angle_deg):
+        """Frame::rotate about the frame centroid (py_frame.rs:89-95, frame.rs:40-63)."""
+        f = self._clone()
+        a = angle_deg * (math.pi / 180.0)
+        if a == 0.0:
+            return f
+        cx, cy = f.centroid[0], f.centroid[1]
+        for c in [f.lumen, *f.extras.values()]:
+            _rotate_rows(c._rows, a, cx, cy)
+        if f.reference_point is not None:
+            row = np.array([f.reference_point._row()])
+            _rotate_rows(row, a, cx, cy)
+            f.reference_point = PyContourPoint(*row[0])
+        x, y = f.centroid[0] - cx, f.centroid[1] - cy
+        f.centroid = (x * math.cos(a) - y * math.sin(a) + cx, x * math.sin(a) + y * math.cos(a) + cy, f.centroid[2])
+        return f
+
+    def translate(self, dx, dy, dz):
+        """Frame::translate (frame.rs:18-38): contour centroids are recomputed, the frame centroid shifted."""
+        f = self._clone()
+        for c in [f.lumen, *f.extras.values()]:
+            c._rows[:, 2] = c._rows[:, 2] + dx
+            c._rows[:, 3] = c._rows[:, 3] + dy
+            c._rows[:, 4] = c._rows[:, 4] + dz
+            if len(c._rows):
+                c.centroid = _centroid_rows(c._rows)
+                c._has_centroid = True
+        if f.reference_point is not None:
+            r = f.reference_point
+            f.reference_point = PyContourPoint(r.frame_index, r.point_index, r.x + dx, r.y + dy, r.z + dz, r.aortic)
+        f.centroid = (f.centroid[0] + dx, f.centroid[1] + dy, f.centroid[2] + dz)
+        return f
+
+    def sort_frame_points(self):
+        f = self._clone()
+        for c in [f.lumen, *f.extras.values()]:
+            c._rows = _sort_rows(c._rows)
+        return f
 
 
 class PyGeometry:
@@ -180,6 +356,101 @@ class PyGeometry:
 
     def get_lumen_contours(self):
         return [f.lumen for f in self.frames]
+
+    def rotate(self, angle_deg):
+        """Geometry::rotate_geometry (geometry.rs:241-250): every frame about its own centroid, then re-sorted."""
+        if angle_deg * (math.pi / 180.0) == 0.0:
+            return PyGeometry([f._clone() for f in self.frames], self.label)
+        return PyGeometry([f.rotate(angle_deg).sort_frame_points() for f in self.frames], self.label)
+
+    def translate(self, dx, dy, dz):
+        return PyGeometry([f.translate(dx, dy, dz) for f in self.frames], self.label)
+
+    def smooth_frames(self):
+        """Geometry::smooth_frames (geometry.rs:165-239): 3-frame moving average of x, y for lumen, Eem, Wall."""
+        out = []
+        n = len(self.frames)
+        for i, f in enumerate(self.frames):
+            prev, nxt = self.frames[max(i - 1, 0)], self.frames[min(i + 1, n - 1)]
+            g = f._clone()
+            cnt = len(f.lumen)
+
+            def avg(cur, p, q):
+                a, b, c = cur._sync()[:cnt], p._sync()[:cnt], q._sync()[:cnt]
+                if min(len(a), len(b), len(c)) < cnt:
+                    raise IndexError("index out of bounds (smooth_frames)")
+                rows = a.copy()
+                rows[:, 2] = (b[:, 2] + a[:, 2] + c[:, 2]) / 3.0
+                rows[:, 3] = (b[:, 3] + a[:, 3] + c[:, 3]) / 3.0
+                o = cur._clone(rows)
+                o.centroid = _centroid_rows(rows) if len(rows) else (0.0, 0.0, 0.0)
+                o._has_centroid = len(rows) > 0
+                return o
+
+            g.lumen = avg(f.lumen, prev.lumen, nxt.lumen)
+            for k in ("Eem", "Wall"):
+                if k in f.extras and k in prev.extras and k in nxt.extras:
+                    g.extras[k] = avg(f.extras[k], prev.extras[k], nxt.extras[k])
+            out.append(g)
+        return PyGeometry(out, self.label)
+
+    def get_summary(self):
+        """(mla, max_stenosis, stenosis_length_mm) — py_geometry.rs:190-254."""
+        if not self.frames:
+            return (0.0, 0.0, 0.0)
+        areas = [f.lumen.get_area() for f in self.frames]
+        biggest, mla = max(areas), min(areas)
+        max_sten = 1.0 - (mla / biggest) if biggest > 0.0 else 0.0
+        thr = (0.70 if all(f.lumen.get_elliptic_ratio() < 1.3 for f in self.frames) else 0.50) * biggest
+        cen = [f.centroid for f in self.frames]
+        longest, i = 0.0, 0
+        while i < len(areas):
+            if areas[i] < thr:
+                end = i
+                while end + 1 < len(areas) and areas[end + 1] < thr:
+                    end += 1
+                run = 0.0
+                for k in range(i, end):
+                    run += math.sqrt(sum((cen[k][d] - cen[k + 1][d]) ** 2 for d in range(3)))
+                longest = max(longest, run)
+                i = end + 1
+            else:
+                i += 1
+        return (mla, max_sten, longest)
+
+    def get_frame_at_z(self, z):
+        if not self.frames:
+            raise ValueError("geometry contains no frames")
+        return min(self.frames, key=lambda f: abs(f.centroid[2] - z))
+
+    def get_frame_at_index(self, index):
+        if not 0 <= index < len(self.frames):
+            raise IndexError(f"index {index} out of range for geometry with {len(self.frames)} frames")
+        return self.frames[index]
+
+    def replace_frame(self, index, frame):
+        if not 0 <= index < len(self.frames):
+            raise IndexError(f"index {index} is out of range for geometry with {len(self.frames)} frames")
+        fr = list(self.frames)
+        fr[index] = frame
+        return PyGeometry(fr, self.label)
+
+    def downsample(self, n_points):
+        """py_geometry.rs:394-434: strided down-sampling (contour.rs:47-58) of every contour but the catheter."""
+        def ds(c):
+            rows = c._sync()
+            if len(rows) <= n_points:
+                return c._clone()
+            step = len(rows) / n_points
+            return c._clone(rows[[int(i * step) for i in range(n_points)]])
+
+        out = []
+        for f in self.frames:
+            g = f._clone()
+            g.lumen = ds(f.lumen)
+            g.extras = {k: (c._clone() if k == "Catheter" else ds(c)) for k, c in f.extras.items()}
+            out.append(g)
+        return PyGeometry(out, self.label)
 
     # ---- blob codec ------------------------------------------------------------
     def to_blob(self) -> np.ndarray:
