@@ -29,18 +29,8 @@ namespace mmrs {
 #ifndef MMRS_J_UNROLL
 #define MMRS_J_UNROLL 0  // 0 = default per kernel flavour
 #endif
-#ifndef MMRS_B_UNIFORM
-#define MMRS_B_UNIFORM 0
-#endif
-#ifndef MMRS_B_CONST_EXPERIMENT
-#define MMRS_B_CONST_EXPERIMENT 0
-#endif
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-
-#if MMRS_B_CONST_EXPERIMENT
-__constant__ float4 c_expB[2048];
-#endif
 
 // ---- packed FP32 helpers (Blackwell-only PTX: *.f32x2, 3-input min.f32) --------
 __device__ __forceinline__ uint64_t pk(float lo, float hi) {
@@ -194,9 +184,6 @@ __global__ void __launch_bounds__(kThreads, 2)
     __syncthreads();
     mbar_wait(bar, 0);
 
-#if MMRS_B_UNIFORM
-    const int zl = lane & w.pad;  // == 0 at run time (WorkItem::pad is always 0)
-#endif
     unsigned long long best = ~0ull;
     unsigned* my_col = s_col + wid * b_pts;
     const float INF = __int_as_float(0x7f800000);
@@ -228,21 +215,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
 #pragma unroll JU
             for (int j = 0; j < ud.m_pairs; ++j) {
-#if MMRS_B_UNIFORM
-                // The reference point is the same for every lane. Passing it through a warp-wide OR
-                // (CREDUX -> uniform register) lets FADD2 take it as a UNIFORM-register operand, which
-                // costs no vector register-file read: the sweep is RF-bandwidth bound.
-                // `zl` is a run-time zero that keeps ptxas from folding the reduction away.
-                float4 B = sB[j + zl];  // (bx0, by0, bx1, by1)
-                B.x = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(B.x)));
-                B.y = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(B.y)));
-                B.z = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(B.z)));
-                B.w = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(B.w)));
-#elif MMRS_B_CONST_EXPERIMENT
-                const float4 B = c_expB[j];  // TIMING EXPERIMENT ONLY (wrong results)
-#else
                 const float4 B = sB[j];  // (bx0, by0, bx1, by1)
-#endif
                 const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y);
                 const uint64_t bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
                 float c0 = INF, c1 = INF;
