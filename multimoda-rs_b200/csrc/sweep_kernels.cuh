@@ -27,7 +27,7 @@
 namespace mmrs {
 
 #ifndef MMRS_J_UNROLL
-#define MMRS_J_UNROLL 0  // 0 = default per kernel flavour
+#define MMRS_J_UNROLL 0  // 0 = default (2)
 #endif
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     constexpr int H = TA / 2;          // packed pairs of test points per lane
     constexpr bool TAIL = (TA & 1);    // plus one unpaired point when TA is odd
     constexpr int S = H + (TAIL ? 1 : 0);
-    constexpr int JU = (MMRS_J_UNROLL > 0) ? MMRS_J_UNROLL : (MULTI ? 1 : 2);  // measured: +2% single-chunk, -3% multi
+    constexpr int JU = (MMRS_J_UNROLL > 0) ? MMRS_J_UNROLL : 2;  // measured on B200: +2-3 % over 1, 4 is no better
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw + 8);
@@ -219,11 +219,19 @@ __global__ void __launch_bounds__(kThreads, 2)
                 const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y);
                 const uint64_t bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
                 float c0 = INF, c1 = INF;
-                if (TAIL) {  // scalar FP32 ops for the unpaired point; its distances seed the column minima
+                if (MULTI && ch > 0 && lane == 0) {
+                    // Column minima of the previous chunks enter lane 0's accumulators up front: the load is
+                    // issued a whole iteration before its use and the warp REDUX below does the merge for free.
+                    const uint2 prev = *reinterpret_cast<const uint2*>(&my_col[2 * j]);
+                    c0 = __uint_as_float(prev.x);
+                    c1 = __uint_as_float(prev.y);
+                }
+                if (TAIL) {  // scalar FP32 ops for the unpaired point
                     const float ex0 = tx - B.x, ey0 = ty - B.y, ex1 = tx - B.z, ey1 = ty - B.w;
-                    c0 = fmaf(ex0, ex0, ey0 * ey0);
-                    c1 = fmaf(ex1, ex1, ey1 * ey1);
-                    row[TA - 1] = min3(row[TA - 1], c0, c1);
+                    const float t0 = fmaf(ex0, ex0, ey0 * ey0), t1 = fmaf(ex1, ex1, ey1 * ey1);
+                    row[TA - 1] = min3(row[TA - 1], t0, t1);
+                    c0 = MULTI ? fminf(c0, t0) : t0;  // single-chunk: the tail's distances seed the column minima
+                    c1 = MULTI ? fminf(c1, t1) : t1;
                 }
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
@@ -241,15 +249,10 @@ __global__ void __launch_bounds__(kThreads, 2)
                 }
                 unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
                 unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
-                if (!MULTI) {
-                    colmax = max(colmax, max(r0, r1));
+                if (!MULTI || ch == ud.n_chunks - 1) {
+                    colmax = max(colmax, max(r0, r1));  // all test points seen: these are the column minima
                 } else if (lane == 0) {
-                    if (ch > 0) {
-                        r0 = min(r0, my_col[2 * j]);
-                        r1 = min(r1, my_col[2 * j + 1]);
-                    }
-                    my_col[2 * j] = r0;
-                    my_col[2 * j + 1] = r1;
+                    *reinterpret_cast<uint2*>(&my_col[2 * j]) = make_uint2(r0, r1);
                 }
             }
             float rm = row[0];
@@ -257,11 +260,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             for (int k = 1; k < TA; ++k) rm = fmaxf(rm, row[k]);
             rowmax = max(rowmax, __float_as_uint(rm));
         }
-        if (MULTI) {
-            __syncwarp();
-            for (int j = lane; j < b_pts; j += 32) colmax = max(colmax, my_col[j]);
-            __syncwarp();
-        }
+        if (MULTI) __syncwarp();  // the next candidate reuses my_col
         const unsigned h2 = __reduce_max_sync(0xffffffffu, max(rowmax, colmax));
         const float d = sqrtf(__uint_as_float(h2));
         if (lane == 0) {

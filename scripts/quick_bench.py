@@ -35,5 +35,6 @@ if __name__ == "__main__":
     run(ctx, 398, 520, 0.01, 180.0)
     run(ctx, 40, 510, 0.01, 180.0)
     run(ctx, 8, 2020, 0.05, 180.0)
+    run(ctx, 74, 2020, 0.05, 180.0)
     run(ctx, 1596, 510, 1.0, 180.0)
     print("fp32 probe TFLOP/s:", ctx.fp32_probe(4096), flush=True)
