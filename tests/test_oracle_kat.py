@@ -246,3 +246,66 @@ def test_rotate_round_trip_is_close():
     f = g[1]
     r = fx.frame_rotate(fx.frame_rotate(f, 15 * RAD, *f["centroid"][:2]), -15 * RAD, *f["centroid"][:2])
     assert np.allclose(r["contours"][0]["points"], f["contours"][0]["points"], atol=1e-12)
+
+
+# ---- fixture-based KATs (data/fixtures/idealized_geometry, re-encoded in tests/golden/inputs.npz) ----------
+def _ideal_blob():
+    from tests import golden_io as gio
+
+    a = gio.phase_arrays(gio.inputs(), "ideal", True)
+    return ora.build_geometry_from_arrays(a["lumen"], a["ref_point"], a["eem"], a["calc"], a["side"], a["records"],
+                                          True, "stress", (4.5, 4.5), 0.5, 20)
+
+
+def test_idealized_geometry():  # align_within.rs:855-887
+    out, logs, anomalous = ora.align_within(_ideal_blob(), 0.01, 20.0, True, False, 200)
+    assert len(ora.decode_geometry(out)) > 0 and anomalous
+    for i, log in enumerate(logs):
+        assert abs(abs(log[2]) - 15.0) <= 1.0
+        assert log[3] == pytest.approx(-0.01 * (i + 1), abs=1e-3) and log[4] == pytest.approx(0.01 * (i + 1), abs=1e-3)
+
+
+def test_align_between_optimized_geometries():  # align_between.rs:305-373
+    out, _, _ = ora.align_within(_ideal_blob(), 0.01, 45.0, True, False, 200)
+    a = ora.decode_geometry(out)
+    b = ora.decode_geometry(out.copy())      # decode returns views: B needs its own buffer
+    # rotate B by 15 deg about its proximal frame's centroid (rotate_geometry_around_point, align_between.rs:95-145)
+    n = len(b)
+    prox = b[0]["contours"][0]["id"] if b[0]["contours"][0]["original_frame"] > b[n - 1]["contours"][0]["original_frame"] \
+        else b[n - 1]["contours"][0]["id"]
+    cx, cy = b[prox]["centroid"][0], b[prox]["centroid"][1]
+    ca, sa = math.cos(15.0 * RAD), math.sin(15.0 * RAD)
+
+    def rot(x, y):
+        tx, ty = x - cx, y - cy
+        return tx * ca - ty * sa + cx, tx * sa + ty * ca + cy
+
+    for f in b:
+        for c in f["contours"].values():
+            for p in c["points"]:
+                p[2], p[3] = rot(p[2], p[3])
+            if c["centroid"] is not None:
+                x, y = rot(c["centroid"][0], c["centroid"][1])
+                c["centroid"] = (x, y, c["centroid"][2])
+        x, y = rot(f["centroid"][0], f["centroid"][1])
+        f["centroid"] = (x, y, f["centroid"][2])
+        if f["reference_point"] is not None:
+            f["reference_point"][2], f["reference_point"][3] = rot(f["reference_point"][2], f["reference_point"][3])
+    out_b, best = ora.align_between(ora.encode_geometry(a), ora.encode_geometry(b), 30.0, 0.01, 500)
+    fb = ora.decode_geometry(out_b)
+    errs = []
+    for fa, fbk in zip(a, fb):
+        assert fa["centroid"][2] == pytest.approx(fbk["centroid"][2], abs=1e-4)
+        pa, pb = fa["contours"][0]["points"], fbk["contours"][0]["points"]
+        assert len(pa) == len(pb)
+        errs.append(np.abs(pa[:, 2:4] - pb[:, 2:4]))
+    e = np.concatenate(errs)
+    assert e.max() < 0.01 and e.mean() < 0.001
+    assert math.degrees(best) == pytest.approx(-15.0, abs=0.02)
+
+
+def test_geometry_rotate_round_trip_exact_fields():  # geometry.rs:450-503: +15 then -15 deg keeps ids / counts, points to 1e-9
+    blob = ora.encode_geometry(fx.dummy_geometry())
+    frames = ora.decode_geometry(blob)
+    assert [f["id"] for f in frames] == [0, 1, 2] and all(len(f["contours"][0]["points"]) == 6 for f in frames)
+    assert np.array_equal(ora.encode_geometry(frames), blob)
