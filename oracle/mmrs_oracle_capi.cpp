@@ -204,6 +204,34 @@ int ora_align_within(const double* blob, long len, double step_deg, double range
     });
 }
 
+// The frame chain of align_within.rs:72-134 with a tap: for frame pair `pair` (0-based) returns the chain-state
+// sample points the reference's cost closure sees (testing_points, reference_points), the rotation centre
+// (current.centroid after the translation) and the chosen angle. Used to measure how far the "decoupled" costs
+// the product sweeps are from the chain's own.
+int ora_within_chain_tap(const double* blob, long len, double step_deg, double range_deg, int bruteforce,
+                         long sample_size, int threads, long pair, double** test_xy, long* n_test, double** ref_xy,
+                         long* n_ref, double centre[2], double* best) {
+    return guard([&] {
+        Geometry g = decode_geometry(blob, (size_t)len, "geom");
+        ChainTap tap;
+        align_frames_in_geometry(g, step_deg, range_deg, false, bruteforce != 0, (size_t)sample_size, threads, &tap, false);
+        if (pair < 0 || pair >= (long)tap.test.size()) throw Error("pair index out of range");
+        auto flat = [](const std::vector<ContourPoint>& v) {
+            std::vector<double> o;
+            for (auto& p : v) o.insert(o.end(), {p.x, p.y});
+            return o;
+        };
+        auto t = flat(tap.test[pair]), r = flat(tap.ref[pair]);
+        *test_xy = dup_vec(t);
+        *n_test = (long)tap.test[pair].size();
+        *ref_xy = dup_vec(r);
+        *n_ref = (long)tap.ref[pair].size();
+        centre[0] = tap.centre[pair].first;
+        centre[1] = tap.centre[pair].second;
+        *best = tap.best[pair];
+    });
+}
+
 // align_between.rs:11-92. Returns the (unchanged) A and the moved B, plus the chosen rotation.
 int ora_align_between(const double* blob_a, long len_a, const double* blob_b, long len_b, double rot_deg,
                       double step_deg, long sample_size, int threads, double** out_b, long* out_b_len,

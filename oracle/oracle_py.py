@@ -298,3 +298,14 @@ def predict_z_positions(ref_z, start_z, stop_z, z_diff, cap=100000):
     n = lib().ora_predict_z_positions(C.c_double(ref_z), C.c_double(start_z), C.c_double(stop_z), C.c_double(z_diff),
                                       out.ctypes.data_as(c_dp), C.c_long(cap))
     return out[:n].copy()
+
+
+def within_chain_tap(blob, step_deg, range_deg, bruteforce, sample_size, pair, threads=1):
+    """Chain-state (test_xy, ref_xy, centre, best_angle) of frame pair `pair` as the reference's closure sees them."""
+    b = np.ascontiguousarray(blob, dtype=np.float64)
+    t, nt, r, nr, best = c_dp(), C.c_long(), c_dp(), C.c_long(), C.c_double()
+    cen = (C.c_double * 2)()
+    _check(lib().ora_within_chain_tap(b.ctypes.data_as(c_dp), C.c_long(len(b)), C.c_double(step_deg), C.c_double(range_deg),
+                                      int(bruteforce), C.c_long(sample_size), int(threads), C.c_long(pair), C.byref(t),
+                                      C.byref(nt), C.byref(r), C.byref(nr), cen, C.byref(best)))
+    return (_take(t, 2 * nt.value).reshape(-1, 2), _take(r, 2 * nr.value).reshape(-1, 2), (cen[0], cen[1]), best.value)
