@@ -71,6 +71,60 @@ __global__ void __launch_bounds__(256, 2) kern(float* out, int m_pairs, int reps
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// b-packed variant: one packed instruction = one test point against TWO reference points; the reference pair
+// (bx0,bx1)/(by0,by1) is the same operand for every test point of the lane (operand-reuse friendly).
+template <int TA, int JU>
+__global__ void __launch_bounds__(256, 2) kern_bp(float* out, int m_pairs, int reps, float s) {
+    __shared__ float4 sB[1024];
+    for (int i = threadIdx.x; i < 1024; i += 256) sB[i] = make_float4(s * i, s * i + 1, s * i + 2, s * i + 3);
+    __syncthreads();
+    float ax[TA], ay[TA], row[TA];
+    for (int k = 0; k < TA; ++k) { ax[k] = threadIdx.x * 0.01f + k; ay[k] = threadIdx.x * 0.03f + k; row[k] = 1e30f; }
+    unsigned colmax = 0;
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll JU
+        for (int j = 0; j < m_pairs; ++j) {
+            const float4 B = sB[j];  // (bx0, bx1, by0, by1)
+            const uint64_t BX = pk(B.x, B.y), BY = pk(B.z, B.w);
+            float c0 = 1e30f, c1 = 1e30f;
+#pragma unroll
+            for (int k = 0; k < TA; k += 2) {
+                const uint64_t dxa = sub2(pk(ax[k], ax[k]), BX), dya = sub2(pk(ay[k], ay[k]), BY);
+                const uint64_t dxb = sub2(pk(ax[k + 1], ax[k + 1]), BX), dyb = sub2(pk(ay[k + 1], ay[k + 1]), BY);
+                const uint64_t da = fma2(dxa, dxa, mul2(dya, dya));  // (|a-b0|^2, |a-b1|^2)
+                const uint64_t db = fma2(dxb, dxb, mul2(dyb, dyb));
+                float a0, a1, b0, b1;
+                upk(da, a0, a1); upk(db, b0, b1);
+                row[k] = min3(row[k], a0, a1);
+                row[k + 1] = min3(row[k + 1], b0, b1);
+                c0 = min3(c0, a0, b0);
+                c1 = min3(c1, a1, b1);
+            }
+            unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
+            unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
+            colmax = max(colmax, max(r0, r1));
+        }
+    }
+    float acc = __uint_as_float(colmax);
+    for (int k = 0; k < TA; ++k) acc += row[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+template <int TA, int JU>
+void run_bp(const char* name) {
+    float* out; cudaMalloc(&out, 148 * 2 * 256 * 4);
+    const int m_pairs = 256, reps = 200;
+    kern_bp<TA, JU><<<148 * 2, 256>>>(out, m_pairs, 2, 1.0f);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    kern_bp<TA, JU><<<148 * 2, 256>>>(out, m_pairs, reps, 1.0f);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    double kiters = (double)reps * m_pairs * (TA / 2) * 4;
+    double cyc = ms * 1e-3 * 1.965e9 / kiters;
+    printf("TA=%d %-42s JU=%d %8.3f ms  %6.2f SMSP-cycles per 2x2 pair block\n", TA, name, JU, ms, cyc);
+    cudaFree(out);
+}
+
 template <int H, int MODE, int JU>
 void run(const char* name) {
     float* out; cudaMalloc(&out, 148 * 2 * 256 * 4);
@@ -89,6 +143,14 @@ void run(const char* name) {
 }
 
 int main() {
+    run_bp<16, 1>("b-packed full");
+    run_bp<16, 2>("b-packed full");
+    run_bp<18, 2>("b-packed full");
+    run<8, 0, 2>("a-packed full (shipped form)");
+    run<9, 0, 2>("a-packed full (shipped form)");
+    return 0;
+}
+int main_old() {
     run<8, 1, 1>("FMA-pipe only");
     run<8, 2, 1>("FMA + row mins (2 FMNMX3)");
     run<8, 3, 1>("FMA + col mins (2 FMNMX3) + REDUX");
