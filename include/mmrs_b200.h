@@ -229,6 +229,56 @@ int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, const doubl
                        const int64_t* blob_lens, const mmrs_align_params* params, double** out_blobs,
                        int64_t* out_lens, double** out_logs, int64_t* out_nlogs, int32_t* out_anomalous);
 
+/* ---- OBJ / MTL / texture export ---------------------------------------------------------------
+ * Replaces to_object::process_case (src/intravascular/to_object/process.rs:9-61: interpolation
+ * between the two geometries, to_object/interpolation.rs:9-157; one texture PNG + MTL per mesh,
+ * to_object/write_mtl.rs:15-273 and to_object/texture.rs:6-95; one OBJ per mesh,
+ * io/output.rs:10-181, :245-307) for one geometry pair. File names, OBJ/MTL text and texture
+ * pixels follow the reference; the PNG files use stored (uncompressed) deflate blocks.
+ * kinds: contour kinds to write, in order (0 Lumen ... 5 Wall). label_a names the interpolated
+ * geometries ("{label_a}_inter_{k}"). ctx may be NULL (no GPU work).                          */
+int mmrs_export_pair(mmrs_ctx* ctx, const double* blob_a, int64_t len_a, const double* blob_b, int64_t len_b,
+                     const char* label_a, const char* case_name, const char* output_dir, int64_t interpolation_steps,
+                     int32_t watertight, const int32_t* kinds, int32_t n_kinds);
+/* One geometry, no UV coordinates. naming 0: the export of single_processing_rs
+ * (binding/entry.rs:741-818, files "{type}_{name}.obj/.mtl"); naming 1:
+ * to_object::write_single_geometry (process.rs:63-121, files "{name}_{type}.obj/.mtl").      */
+int mmrs_export_single(mmrs_ctx* ctx, const double* blob, int64_t len, const char* name, const char* output_dir,
+                       int32_t watertight, const int32_t* kinds, int32_t n_kinds, int32_t naming);
+
+/* ---- centerline alignment ----------------------------------------------------------------------
+ * Replaces align_three_point_rs / align_manual_rs / align_combined_rs
+ * (src/intravascular/centerline_align/align.rs:61-121, :123-164, :166-283; PyO3 wrappers in
+ * src/intravascular/binding/align.rs:65-155, :199-284, :334-463) without the `write` step (call
+ * mmrs_export_pair / mmrs_export_single with naming 1 afterwards).
+ *   method 0: three-point search (align_algorithms.rs:264-337) — 3-point squared error, not
+ *             Hausdorff-scored, host f64;
+ *   method 1: manual rotation (`manual_rotation_deg`, reference point in main_ref_pt);
+ *   method 2: three-point search + refine_alignment_hausdorff (align_algorithms.rs:339-451):
+ *             every (centerline index, angle) candidate is scored by the symmetric Hausdorff
+ *             distance on the GPU as one batch of sweep units (needs ctx; no CPU fallback).
+ * centerline: n_cl rows of 8 doubles (x, y, z, tangent_x, tangent_y, tangent_z, branch_id, radius)
+ * (CenterlinePoint, src/types/native/centerline_point.rs:4-11). n_geoms: 1 (Geometry) or 2
+ * (GeometryPair: the first blob is the primary geometry). Outputs: n_geoms malloc'ed blobs,
+ * the resampling spacing in mm, the total rotation in radians, and refine_out[2] =
+ * (best Hausdorff distance, candidates scored) for method 2 (-1, 0 otherwise).                */
+typedef struct mmrs_centerline_params {
+    double main_ref_pt[3];
+    double ccw_ref_pt[3];
+    double cw_ref_pt[3];
+    double angle_step_rad;
+    double manual_rotation_deg;
+    const double* points; /* method 2: CCTA point cloud, n_points x (x, y, z) */
+    int64_t n_points;
+    double angle_range_rad;
+    int64_t index_range;
+    int32_t align_wall_anomalous;
+} mmrs_centerline_params;
+int mmrs_align_centerline(mmrs_ctx* ctx, int32_t method, const double* centerline, int64_t n_cl, int32_t n_geoms,
+                          const double* const* blobs, const int64_t* blob_lens, const mmrs_centerline_params* params,
+                          double** out_blobs, int64_t* out_lens, double* spacing_out, double* rotation_rad_out,
+                          double* refine_out);
+
 /* ---- multi-GPU: sharding the units of every batched sweep across ranks -------------------------
  * One process per GPU. Every rank calls mmrs_process_cases with IDENTICAL inputs; inside, each batched
  * sweep stage evaluates only this rank's contiguous block of units on its GPU and the per-unit results

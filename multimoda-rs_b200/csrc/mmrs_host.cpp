@@ -26,6 +26,8 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <cctype>
+#include <charconv>
 #include <exception>
 #include <mutex>
 #include <thread>
@@ -43,6 +45,9 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include <sys/stat.h>
+#include <sys/types.h>
 
 #include "mmrs_internal.hpp"
 
@@ -1601,6 +1606,8 @@ void postprocess_pair(Geometry& ga, Geometry& gb, double tol, bool anomalous) { 
     gb = std::move(nb);
 }
 
+#include "mmrs_export_align.inc"
+
 template <class F>
 int guarded(mmrs_ctx* ctx, F&& f) {
     try {
@@ -1771,4 +1778,75 @@ extern "C" int mmrs_process_stats(mmrs_ctx* ctx, int64_t s[5]) {
     if (!ctx || !s) return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_process_stats: NULL argument");
     for (int i = 0; i < 5; ++i) s[i] = ctx->stats[i];
     return MMRS_OK;
+}
+
+// ---- OBJ / MTL / PNG export ---------------------------------------------------------------
+static std::vector<int> kinds_vec(const int32_t* kinds, int32_t n) {
+    std::vector<int> v;
+    for (int32_t i = 0; i < n; ++i) {
+        if (kinds[i] < 0 || kinds[i] > 5) throw InputErr("contour kind out of range");
+        v.push_back(kinds[i]);
+    }
+    return v;
+}
+
+extern "C" int mmrs_export_pair(mmrs_ctx* ctx, const double* blob_a, int64_t len_a, const double* blob_b, int64_t len_b,
+                                const char* label_a, const char* case_name, const char* output_dir,
+                                int64_t interpolation_steps, int32_t watertight, const int32_t* kinds, int32_t n_kinds) {
+    if (!blob_a || !blob_b || !case_name || !output_dir || (n_kinds > 0 && !kinds) || interpolation_steps < 0)
+        return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_export_pair: bad arguments");
+    return guarded(ctx, [&] {
+        Geometry a = decode(blob_a, len_a), b = decode(blob_b, len_b);
+        a.label = label_a ? label_a : "";
+        export_pair(a, b, case_name, output_dir, (size_t)interpolation_steps, watertight != 0, kinds_vec(kinds, n_kinds));
+    });
+}
+
+extern "C" int mmrs_export_single(mmrs_ctx* ctx, const double* blob, int64_t len, const char* name,
+                                  const char* output_dir, int32_t watertight, const int32_t* kinds, int32_t n_kinds,
+                                  int32_t naming) {
+    if (!blob || !name || !output_dir || (n_kinds > 0 && !kinds) || (naming != 0 && naming != 1))
+        return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_export_single: bad arguments");
+    return guarded(ctx, [&] {
+        export_single(decode(blob, len), name, output_dir, watertight != 0, kinds_vec(kinds, n_kinds), naming);
+    });
+}
+
+// ---- centerline alignment ----------------------------------------------------------------------
+extern "C" int mmrs_align_centerline(mmrs_ctx* ctx, int32_t method, const double* centerline, int64_t n_cl,
+                                     int32_t n_geoms, const double* const* blobs, const int64_t* blob_lens,
+                                     const mmrs_centerline_params* params, double** out_blobs, int64_t* out_lens,
+                                     double* spacing_out, double* rotation_rad_out, double* refine_out) {
+    if (method < 0 || method > 2 || n_cl < 0 || (n_cl > 0 && !centerline) || (n_geoms != 1 && n_geoms != 2) || !blobs ||
+        !blob_lens || !params || !out_blobs || !out_lens || (params->n_points > 0 && !params->points))
+        return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_align_centerline: bad arguments");
+    if (method == 2 && !ctx)
+        return mmrs::set_err(nullptr, MMRS_ERR_ARG,
+                             "mmrs_align_centerline: align_combined needs a CUDA context (no CPU fallback for the "
+                             "Hausdorff refinement)");
+    return guarded(ctx, [&] {
+        Centerline cl((size_t)n_cl);
+        for (int64_t i = 0; i < n_cl; ++i) {
+            const double* r = centerline + 8 * i;
+            cl[i].fi = cl[i].pi = (uint32_t)i;
+            cl[i].p = {r[0], r[1], r[2]};
+            cl[i].t = {r[3], r[4], r[5]};
+            cl[i].branch = (uint32_t)r[6];
+            cl[i].radius = r[7];
+        }
+        std::vector<Geometry> target;
+        for (int32_t g = 0; g < n_geoms; ++g) target.push_back(decode(blobs[g], blob_lens[g]));
+        CenterlineAlignOut o;
+        if (ctx) {
+            for (int i = 0; i < 5; ++i) ctx->stats[i] = 0;
+            Searcher S{ctx, ctx->stats};
+            o = align_to_centerline(&S, method, cl, target, *params);
+        } else {
+            o = align_to_centerline(nullptr, method, cl, target, *params);
+        }
+        for (int32_t g = 0; g < n_geoms; ++g) out_blobs[g] = encode_malloc(target[g], &out_lens[g]);
+        if (spacing_out) *spacing_out = o.spacing;
+        if (rotation_rad_out) *rotation_rad_out = o.rotation;
+        if (refine_out) refine_out[0] = o.refine_hausdorff, refine_out[1] = (double)o.refine_candidates;
+    });
 }

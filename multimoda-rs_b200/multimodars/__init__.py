@@ -1,8 +1,8 @@
 """Drop-in subset of the `multimodars` Python surface (multimodars/__init__.py:6-84) for the
 Hausdorff rotation-sweep path, running on B200 through libmmrs_b200.so."""
-from ._types import (PyContour, PyContourPoint, PyContourType, PyFrame, PyGeometry, PyGeometryPair, PyInputData,
+from ._types import (PyCenterline, PyCenterlinePoint, PyContour, PyContourPoint, PyContourType, PyFrame, PyGeometry, PyGeometryPair, PyInputData,
                      PyRecord, numpy_to_inputdata)
-from ._processing import (align_three_point, from_array_doublepair, from_array_full, from_array_single,
+from ._processing import (align_combined, align_manual, align_three_point, from_array_doublepair, from_array_full, from_array_single,
                           from_array_singlepair, from_file_doublepair, from_file_full, from_file_single,
                           from_file_singlepair, get_context)
 from ._native import MmrsError

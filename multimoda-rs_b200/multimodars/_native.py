@@ -52,6 +52,13 @@ class AlignParams(C.Structure):
                 ("smooth", C.c_int32), ("bruteforce", C.c_int32), ("postprocessing", C.c_int32)]
 
 
+class CenterlineParams(C.Structure):
+    _fields_ = [("main_ref_pt", C.c_double * 3), ("ccw_ref_pt", C.c_double * 3), ("cw_ref_pt", C.c_double * 3),
+                ("angle_step_rad", C.c_double), ("manual_rotation_deg", C.c_double), ("points", c_dp),
+                ("n_points", C.c_int64), ("angle_range_rad", C.c_double), ("index_range", C.c_int64),
+                ("align_wall_anomalous", C.c_int32)]
+
+
 RESULT_DTYPE = np.dtype([("best_idx", "<i8"), ("best_angle", "<f8"), ("best_dist", "<f8"), ("best_dist_f32", "<f4"),
                          ("n_shortlist", "<i4"), ("n_ties", "<i4"), ("flags", "<i4")], align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(UnitResult)
@@ -66,7 +73,8 @@ EXPORTS = [
     "mmrs_grid_angle", "mmrs_stage_plan", "mmrs_sweep_batched", "mmrs_sweep_upload", "mmrs_sweep_regrid", "mmrs_sweep_run",
     "mmrs_sweep_download", "mmrs_sweep_plan", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
-    "mmrs_process_cases", "mmrs_process_stats", "mmrs_ctx_set_shard",
+    "mmrs_process_cases", "mmrs_process_stats", "mmrs_ctx_set_shard", "mmrs_export_pair", "mmrs_export_single",
+    "mmrs_align_centerline",
 ]
 
 _lib = None
@@ -360,3 +368,78 @@ def process_cases(ctx: Context, mode, blobs, step_deg, range_deg, sample_size, s
     outs = [_take_blob(ob[i], ol[i]) for i in range(n_cases * n_out)]
     logs = [_take_blob(lg[i], nl[i] * 7).reshape(-1, 7) for i in range(len(arrs))]
     return outs, logs, [bool(an[i]) for i in range(len(arrs))]
+
+
+# ---- export + centerline alignment --------------------------------------------------
+def _kinds(kinds):
+    k = np.ascontiguousarray([int(x) for x in kinds], dtype=np.int32)
+    return k, k.ctypes.data_as(c_i32p), len(k)
+
+
+def export_pair(blob_a, blob_b, label_a, case_name, output_dir, interpolation_steps, watertight, kinds,
+                ctx: Context | None = None):
+    """mmrs_export_pair (to_object::process_case, to_object/process.rs:9-61)."""
+    L = lib()
+    L.mmrs_export_pair.argtypes = [C.c_void_p, c_dp, C.c_int64, c_dp, C.c_int64, C.c_char_p, C.c_char_p, C.c_char_p,
+                                   C.c_int64, C.c_int32, c_i32p, C.c_int32]
+    a, b = _f64(blob_a), _f64(blob_b)
+    keep, kp, kn = _kinds(kinds)
+    p = ctx._p if ctx is not None else None
+    rc = L.mmrs_export_pair(p, a.ctypes.data_as(c_dp), len(a), b.ctypes.data_as(c_dp), len(b), str(label_a).encode(),
+                            str(case_name).encode(), os.fsencode(str(output_dir)), int(interpolation_steps),
+                            int(bool(watertight)), kp, kn)
+    if rc:
+        raise MmrsError(_err(p))
+
+
+def export_single(blob, name, output_dir, watertight, kinds, naming, ctx: Context | None = None):
+    """mmrs_export_single (entry.rs:741-818 for naming 0, to_object/process.rs:63-121 for naming 1)."""
+    L = lib()
+    L.mmrs_export_single.argtypes = [C.c_void_p, c_dp, C.c_int64, C.c_char_p, C.c_char_p, C.c_int32, c_i32p,
+                                     C.c_int32, C.c_int32]
+    a = _f64(blob)
+    keep, kp, kn = _kinds(kinds)
+    p = ctx._p if ctx is not None else None
+    rc = L.mmrs_export_single(p, a.ctypes.data_as(c_dp), len(a), str(name).encode(), os.fsencode(str(output_dir)),
+                              int(bool(watertight)), kp, kn, int(naming))
+    if rc:
+        raise MmrsError(_err(p))
+
+
+def align_centerline(ctx: Context | None, method, centerline_rows, blobs, main_ref_pt=(0, 0, 0), ccw_ref_pt=(0, 0, 0),
+                     cw_ref_pt=(0, 0, 0), angle_step_rad=0.0, manual_rotation_deg=0.0, points=None,
+                     angle_range_rad=0.0, index_range=0, align_wall_anomalous=False):
+    """mmrs_align_centerline. centerline_rows: (n, 8) [x, y, z, tx, ty, tz, branch_id, radius].
+    Returns (out_blobs, spacing_mm, rotation_rad, (refine_hausdorff, refine_candidates))."""
+    L = lib()
+    L.mmrs_align_centerline.argtypes = [C.c_void_p, C.c_int32, c_dp, C.c_int64, C.c_int32, C.POINTER(c_dp), c_i64p,
+                                        C.POINTER(CenterlineParams), C.POINTER(c_dp), c_i64p, c_dp, c_dp, c_dp]
+    cl = np.ascontiguousarray(np.asarray(centerline_rows, dtype=np.float64).reshape(-1, 8))
+    arrs = [_f64(b) for b in blobs]
+    ptrs = (c_dp * len(arrs))(*[a.ctypes.data_as(c_dp) for a in arrs])
+    lens = (C.c_int64 * len(arrs))(*[len(a) for a in arrs])
+    prm = CenterlineParams()
+    prm.main_ref_pt[:] = [float(v) for v in main_ref_pt]
+    prm.ccw_ref_pt[:] = [float(v) for v in ccw_ref_pt]
+    prm.cw_ref_pt[:] = [float(v) for v in cw_ref_pt]
+    prm.angle_step_rad = float(angle_step_rad)
+    prm.manual_rotation_deg = float(manual_rotation_deg)
+    pts = None
+    if points is not None and len(points):
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 3))
+        prm.points = pts.ctypes.data_as(c_dp)
+        prm.n_points = len(pts)
+    prm.angle_range_rad = float(angle_range_rad)
+    prm.index_range = int(index_range)
+    prm.align_wall_anomalous = int(bool(align_wall_anomalous))
+    ob = (c_dp * len(arrs))()
+    ol = (C.c_int64 * len(arrs))()
+    spacing, rot = C.c_double(), C.c_double()
+    refine = (C.c_double * 2)()
+    p = ctx._p if ctx is not None else None
+    rc = L.mmrs_align_centerline(p, int(method), cl.ctypes.data_as(c_dp), len(cl), len(arrs), ptrs, lens,
+                                 C.byref(prm), ob, ol, C.byref(spacing), C.byref(rot), refine)
+    if rc:
+        raise MmrsError(_err(p))
+    outs = [_take_blob(ob[i], ol[i]) for i in range(len(arrs))]
+    return outs, spacing.value, rot.value, (refine[0], int(refine[1]))

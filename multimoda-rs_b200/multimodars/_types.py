@@ -513,6 +513,69 @@ class PyGeometryPair:
         return f"GeometryPair(label='{self.label}', geom_a={self.geom_a!r}, geom_b={self.geom_b!r})"
 
 
+class PyCenterlinePoint:
+    """src/types/binding/py_centerline_point.rs:8-48."""
+
+    def __init__(self, contour_point, tangent, branch_id=0):
+        self.contour_point = contour_point
+        self.tangent = (float(tangent[0]), float(tangent[1]), float(tangent[2]))
+        self.branch_id = int(branch_id)
+        self.radius = 0.0
+
+    def __repr__(self):
+        t = self.tangent
+        return (f"CenterlinePoint(point={self.contour_point!r}, tangent=({t[0]:.3f}, {t[1]:.3f}, {t[2]:.3f}), "
+                f"branch={self.branch_id}, radius={self.radius:.3f})")
+
+    __str__ = __repr__
+
+
+class PyCenterline:
+    """src/types/binding/py_centerline.rs:8-60 (constructor, from_contour_points, __len__, points_as_tuples).
+    The branch editing helpers (calculate_branches, split/merge, resample, smooth, ...) belong to the CCTA
+    preprocessing side of the reference and are not part of this build."""
+
+    def __init__(self, points):
+        self.points = list(points)
+        self.branch_start_indices = [0] if self.points else []
+
+    @staticmethod
+    def from_contour_points(contour_points):
+        # Centerline::from_contour_points, src/types/native/centerline.rs:14-43: tangent = normalised
+        # forward difference, the last point repeats its predecessor's tangent
+        pts = list(contour_points)
+        out = []
+        for i, cur in enumerate(pts):
+            if i < len(pts) - 1:
+                nx = pts[i + 1]
+                dx, dy, dz = nx.x - cur.x, nx.y - cur.y, nx.z - cur.z
+                n = math.sqrt(dx * dx + dy * dy + dz * dz)
+                t = (dx / n, dy / n, dz / n) if n != 0.0 else (math.nan, math.nan, math.nan)
+            elif out:
+                t = out[i - 1].tangent
+            else:
+                raise IndexError("index out of bounds: the len is 0 but the index is 18446744073709551615")
+            out.append(PyCenterlinePoint(cur, t, 0))
+        return PyCenterline(out)
+
+    def __len__(self):
+        return len(self.points)
+
+    def __repr__(self):
+        n_br = len(self.branch_start_indices)
+        return f"Centerline(len={len(self.points)}, branches={n_br}, spacing=N/A)"
+
+    __str__ = __repr__
+
+    def points_as_tuples(self):
+        return [(p.contour_point.x, p.contour_point.y, p.contour_point.z) for p in self.points]
+
+    def _rows(self):
+        """(n, 8) [x, y, z, tx, ty, tz, branch_id, radius] — the row layout of mmrs_align_centerline."""
+        return np.array([[p.contour_point.x, p.contour_point.y, p.contour_point.z, *p.tangent, float(p.branch_id),
+                          float(p.radius)] for p in self.points], dtype=np.float64).reshape(-1, 8)
+
+
 class PyRecord:
     """src/types/binding/py_record.rs:30-40."""
 
