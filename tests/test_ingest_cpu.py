@@ -64,8 +64,8 @@ def test_pyinputdata_round_trip_and_types():
     assert set(g.frames[0].extras) == {"Catheter"} and len(g.frames[0].extras["Catheter"]) == 20
 
 
-def test_unsupported_options_fail_loudly():
-    with pytest.raises(NotImplementedError, match="write_obj"):      # the reference default; OBJ export is out of scope
-        mm.from_file_full("a", "b")
-    with pytest.raises(NotImplementedError, match="align_three_point"):
+def test_argument_errors_follow_the_reference():
+    with pytest.raises(nat.MmrsError):      # missing input directory: anyhow error -> RuntimeError (functions.rs:228)
+        mm.from_file_full("does/not/exist/a", "does/not/exist/b")
+    with pytest.raises(TypeError):          # binding/align.rs:151
         mm.align_three_point(None, None, None, None, None)

@@ -241,3 +241,29 @@ def test_step_regimes_of_find_best_rotation():
     blob = nat.geometry_from_arrays(lumen, rp, diastole=True)
     for step, rng_deg in ((2.0, 40.0), (0.3, 40.0), (0.03, 40.0), (0.004, 40.0), (0.03, 3.0), (0.004, 0.05)):
         _cmp_single(blob, step, rng_deg, 120, False, False)
+
+
+def test_reference_defaults_write_obj(tmp_path):
+    """from_file_full with the reference's defaults (write_obj=True, postprocessing=True, interpolation_steps=0):
+    four output directories, per pair 2 meshes x 3 contour types x (obj, mtl, png) (to_object/process.rs:9-61)."""
+    import os
+    pack = gio.inputs()
+    rest, stress = gio.write_dir(pack, "rest", tmp_path / "ivus_rest"), gio.write_dir(pack, "stress", tmp_path / "ivus_stress")
+    outs = [str(tmp_path / "out" / n) for n in ("rest", "stress", "diastole", "systole")]
+    ab, cd, ac, bd, logs = mm.from_file_full(str(rest), str(stress), output_path_ab=outs[0], output_path_cd=outs[1],
+                                             output_path_ac=outs[2], output_path_bd=outs[3])
+    for d, pair in zip(outs, (ab, cd, ac, bd)):
+        names = sorted(os.listdir(d))
+        want = sorted(f"{t}_{i:03d}_{pair.label}.{e}" for t in ("lumen", "catheter", "wall") for i in (0, 1)
+                      for e in ("obj", "mtl", "png"))
+        assert names == want, d
+        obj = open(os.path.join(d, f"lumen_000_{pair.label}.obj")).read().splitlines()
+        n_pts = sum(len(f.lumen) for f in pair.geom_a.frames)
+        assert sum(l.startswith("v ") for l in obj) == n_pts + 2          # + the two cap centroids (watertight)
+        assert sum(l.startswith("vt ") for l in obj) == n_pts + 2 and obj[n_pts] == f"mtllib lumen_000_{pair.label}.mtl"
+        p0 = pair.geom_a.frames[0].lumen.points[0]
+        assert obj[0] == f"v {p0.x!r} {p0.y!r} {p0.z!r}".replace(".0 ", " ").removesuffix(".0")
+    # the single-geometry export of single_processing_rs (entry.rs:741-775)
+    g, _ = mm.from_file_single(str(rest), write_obj=True, output_path=str(tmp_path / "single"))
+    assert sorted(os.listdir(tmp_path / "single")) == sorted(
+        f"{t}_ivus_rest.{e}" for t in ("lumen", "catheter", "wall") for e in ("obj", "mtl"))
