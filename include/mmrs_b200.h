@@ -112,8 +112,20 @@ typedef struct mmrs_sweep_opts {
      * the winner's (same-angle duplicates, e.g. -pi / +pi, are not ambiguous).
      * 0 = exact ties only.                                                    */
     double tie_margin;
-    int32_t keep_dist32; /* != 0: keep the FP32 distance of every candidate for
-                            mmrs_sweep_get_dist32 (tests, diagnostics).        */
+    int32_t keep_dist32; /* != 0: the caller wants the exact FP32 distance of EVERY candidate from
+                            mmrs_sweep_get_dist32 (tests, diagnostics): with prefilter == 0
+                            (auto) this selects the dense FP32 sweep.                     */
+    /* Tensor-core prefilter tier (tcgen05, bf16x3 split operands, FP32 accumulation in TMEM): every
+     * candidate is first scored on the tensor cores with FP32-level (not bf16-level) error; only the
+     * candidates with d_tc^2 <= d_tc_min^2 + prefilter_abs * Rmax^2 are re-scored by the exact FP32
+     * kernel, and from there the FP32 window / f64 recheck / arg-min are unchanged, so the selected
+     * candidate and its f64 distance are identical to the dense path. With the prefilter,
+     * mmrs_sweep_get_dist32 returns prefilter-quality values (|error| <~ 1e-6 * Rmax^2 / d on d) for
+     * candidates outside that window and exact FP32 values inside it.
+     * 0 = auto (on when every unit has 64..2048 points per set and the batch averages >= 32
+     * candidates per unit), 1 = off (dense FP32 sweep of every candidate), 2 = required.        */
+    int32_t prefilter;
+    double prefilter_abs; /* <= 0 selects 4e-6 (about 7x the largest error measured) */
 } mmrs_sweep_opts;
 
 #define MMRS_FLAG_DEGENERATE 1 /* grid degenerate: best_angle = fallback, nothing evaluated */
@@ -161,6 +173,11 @@ int mmrs_sweep_get_shortlist(mmrs_ctx* ctx, int64_t unit, int64_t* idx_out, doub
 /* Device time of the last run in ms: [0] FP32 sweep kernel, [1] shortlist,
  * [2] f64 recheck + select, [3] whole run. Kernel launches of the last run.   */
 int mmrs_last_timings(mmrs_ctx* ctx, float ms_out[4], int32_t* launches_out);
+
+/* Tensor-core prefilter of the last run: [0] 1 if it ran, [1] K1t device time in ms, [2] tier-1 window +
+ * tier-2 exact FP32 re-scoring time in ms, [3] candidates re-scored in FP32 (all units), [4] largest observed
+ * |d_tc^2 - d_fp32^2| / Rmax^2 over them, [5] the window prefilter_abs in force.                              */
+int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]);
 
 /* Reference-arithmetic f64 cost of an explicit list of angles for one unit
  * (the cost closure itself; used by the host to resolve tie sets on the

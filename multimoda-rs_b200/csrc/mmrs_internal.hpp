@@ -53,6 +53,7 @@ struct mmrs_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_tc[3] = {nullptr, nullptr, nullptr};  // tensor-core prefilter: start, after K1t, after tier-2 FP32
     std::string err;
 
     // batch state
@@ -82,6 +83,17 @@ struct mmrs_ctx {
 
     mmrs::DevBuf d_test, d_ref, d_units, d_work, d_lay, d_cs64, d_cs32, d_zero, d_dist32, d_key, d_rmax, d_sl_base,
         d_sl_dist, d_sl_count, d_items, d_nitems, d_res, d_tmp;
+
+    // tensor-core prefilter tier (tc_kernels.cuh)
+    int opt_prefilter = 0;      // mmrs_sweep_opts.prefilter: 0 auto, 1 off, 2 required
+    bool tc_shape_ok = false;   // every live unit has kTcMinPts <= n, m <= kTcMaxPts (decided at upload)
+    bool use_tc = false;        // decided per grid set (apply_grids)
+    bool tc_ran = false;
+    double tc_abs = 4e-6;       // tier-1 window: d^2 <= dmin^2 + tc_abs * Rmax^2
+    unsigned l1_cap = 0;
+    size_t smem_tc = 0;
+    std::vector<mmrs::WorkItem> h_work_tc, h_work_list;
+    mmrs::DevBuf d_work_tc, d_work_list, d_key_tc, d_l1_items, d_l1_count, d_l1_base, d_l1_n;
 
     // unit sharding across ranks (mmrs_ctx_set_shard)
     int shard_rank = 0, shard_world = 1;

@@ -5,6 +5,7 @@
 // =============================================================================
 #include "mmrs_internal.hpp"
 #include "sweep_kernels.cuh"
+#include "tc_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -152,6 +153,7 @@ extern "C" int mmrs_ctx_create(int device, void* stream, mmrs_ctx** out) {
         ctx->own_stream = true;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->ev_tc) cudaEventCreate(&ev);
     *out = ctx;
     return MMRS_OK;
 }
@@ -162,13 +164,15 @@ extern "C" void mmrs_ctx_destroy(mmrs_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->free_all();
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_tc) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 void mmrs_ctx::free_all() {
     for (DevBuf* b : {&d_test, &d_ref, &d_units, &d_work, &d_lay, &d_cs64, &d_cs32, &d_zero, &d_dist32, &d_key,
-                      &d_rmax, &d_sl_base, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp}) {
+                      &d_rmax, &d_sl_base, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp, &d_work_tc,
+                      &d_work_list, &d_key_tc, &d_l1_items, &d_l1_count, &d_l1_base, &d_l1_n}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr;
         b->cap = 0;
@@ -198,25 +202,40 @@ static int ensure(mmrs_ctx* ctx, DevBuf& b, size_t bytes) {
     } while (0)
 
 // ---- kernel dispatch over TA ----------------------------------------------------------
+struct ListArgs {  // tier-2 (LIST) arguments of k_sweep; all null for the dense sweep
+    const int2* items = nullptr;
+    const int* count = nullptr;
+    const unsigned* base = nullptr;
+    const unsigned* rmax = nullptr;
+    unsigned* diag = nullptr;
+};
+template <int TA, bool MULTI, bool LIST>
+static void launch_sweep_k(int grid, size_t smem, cudaStream_t s, const UnitDesc* units, const WorkItem* work,
+                           const float4* lay, const float2* cs32, float* dist32, unsigned long long* key,
+                           const ListArgs& l) {
+    cudaFuncSetAttribute(k_sweep<TA, MULTI, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sweep<TA, MULTI, LIST><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key, l.items, l.count, l.base,
+                                                          l.rmax, l.diag);
+}
 template <int TA>
 static void launch_sweep_ta(bool multi, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
                             const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
-                            unsigned long long* key) {
-    if (multi) {
-        cudaFuncSetAttribute(k_sweep<TA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_sweep<TA, true><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key);
+                            unsigned long long* key, const ListArgs* l) {
+    if (l) {
+        if (multi) launch_sweep_k<TA, true, true>(grid, smem, s, units, work, lay, cs32, dist32, key, *l);
+        else launch_sweep_k<TA, false, true>(grid, smem, s, units, work, lay, cs32, dist32, key, *l);
     } else {
-        cudaFuncSetAttribute(k_sweep<TA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_sweep<TA, false><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key);
+        if (multi) launch_sweep_k<TA, true, false>(grid, smem, s, units, work, lay, cs32, dist32, key, ListArgs{});
+        else launch_sweep_k<TA, false, false>(grid, smem, s, units, work, lay, cs32, dist32, key, ListArgs{});
     }
 }
 static bool launch_sweep(int TA, bool multi, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
                          const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
-                         unsigned long long* key) {
+                         unsigned long long* key, const ListArgs* l = nullptr) {
     switch (TA) {
-#define CASE(T)                                                                     \
-    case T:                                                                         \
-        launch_sweep_ta<T>(multi, grid, smem, s, units, work, lay, cs32, dist32, key); \
+#define CASE(T)                                                                        \
+    case T:                                                                            \
+        launch_sweep_ta<T>(multi, grid, smem, s, units, work, lay, cs32, dist32, key, l); \
         return true;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
             CASE(15) CASE(16) CASE(17) CASE(18)
@@ -288,6 +307,21 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
         }
     }
     ctx->multi = multi;
+    {   // tensor-core prefilter: every non-empty unit must fit its operand layout
+        bool ok = true;
+        size_t smem_tc = 0;
+        for (auto& d : units) {
+            if (d.n <= 0 || d.m <= 0) continue;
+            if (d.n < kTcMinPts || d.m < kTcMinPts || d.n > kTcMaxPts || d.m > kTcMaxPts) {
+                ok = false;
+                break;
+            }
+            const int ra = (d.n + 127) / 128 * 128;
+            smem_tc = std::max(smem_tc, tc_smem_bytes(d.n, d.m, ra <= 1024 ? 2 : 1));
+        }
+        ctx->tc_shape_ok = ok && smem_tc > 0 && smem_tc <= 227 * 1024;
+        ctx->smem_tc = smem_tc;
+    }
     size_t col_bytes = 0;
     if (multi) {
         int max_pairs = 0;
@@ -389,6 +423,45 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
                 ctx->h_work.push_back(WorkItem{(int)u, c0, std::min(tile, d.n_cand - c0), 0});
         }
     }
+    // Tensor-core prefilter: worth it when the units carry enough candidates to amortise the per-CTA operand set-up.
+    {
+        long long live_units = 0;
+        for (auto& d : units)
+            if (!d.flags) ++live_units;
+        const char* env = std::getenv("MMRS_PREFILTER");  // experiments: 0 = off, 1 = on where the shapes allow
+        int mode = ctx->opt_prefilter;
+        if (env && *env) mode = (*env == '0') ? 1 : 2;
+        ctx->use_tc = mode != 1 && ctx->tc_shape_ok && live_units > 0 && (mode == 2 || live >= 32 * live_units);
+        if (mode == 2 && !ctx->use_tc && ctx->opt_prefilter == 2)
+            return set_err(ctx, MMRS_ERR_ARG,
+                           "prefilter required but the batch does not fit the tensor-core operand layout (64 <= points "
+                           "per set <= 2048)");
+        ctx->h_work_tc.clear();
+        ctx->h_work_list.clear();
+        if (ctx->use_tc) {
+            long long tile = (live + (long long)ctx->n_sm * 6 - 1) / ((long long)ctx->n_sm * 6);
+            tile = std::max<long long>(64, std::min<long long>(tile, 512));
+            for (int64_t u = 0; u < U; ++u) {
+                const UnitDesc& d = units[u];
+                if (d.flags) continue;
+                const int parts = (int)((d.n_cand + tile - 1) / tile);
+                const int per = (d.n_cand + parts - 1) / parts;
+                for (int c0 = 0; c0 < d.n_cand; c0 += per)
+                    ctx->h_work_tc.push_back(WorkItem{(int)u, c0, std::min(per, d.n_cand - c0), 0});
+                const int G = 4;
+                for (int g = 0; g < G; ++g) ctx->h_work_list.push_back(WorkItem{(int)u, g, G, 0});
+            }
+            ctx->l1_cap = (unsigned)std::min<unsigned long long>(
+                std::max<unsigned long long>((unsigned long long)U * 256, 1ull << 20), 0x7fffffffull);
+            ENSURE(ctx->d_work_tc, ctx->h_work_tc.size() * sizeof(WorkItem));
+            ENSURE(ctx->d_work_list, ctx->h_work_list.size() * sizeof(WorkItem));
+            ENSURE(ctx->d_key_tc, U * 8);
+            ENSURE(ctx->d_l1_items, (size_t)ctx->l1_cap * 8);
+            ENSURE(ctx->d_l1_count, U * 4);
+            ENSURE(ctx->d_l1_base, U * 4);
+            ENSURE(ctx->d_l1_n, 16);
+        }
+    }
     ENSURE(ctx->d_work, ctx->h_work.size() * sizeof(WorkItem));
     ENSURE(ctx->d_cs64, (size_t)n_cs * 16);
     ENSURE(ctx->d_cs32, (size_t)n_cs * 8);
@@ -404,6 +477,12 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
     if (!ctx->h_work.empty())
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work.p, ctx->h_work.data(), ctx->h_work.size() * sizeof(WorkItem),
                                       cudaMemcpyHostToDevice, s));
+    if (ctx->use_tc && !ctx->h_work_tc.empty()) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_tc.p, ctx->h_work_tc.data(), ctx->h_work_tc.size() * sizeof(WorkItem),
+                                      cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_list.p, ctx->h_work_list.data(),
+                                      ctx->h_work_list.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, s));
+    }
     if (n_cs) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cs64.p, ctx->h_cs.data(), (size_t)n_cs * 16, cudaMemcpyHostToDevice, s));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zero.p, ctx->h_zero.data(), (size_t)n_cs, cudaMemcpyHostToDevice, s));
@@ -430,6 +509,11 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
     ctx->opt_abs = (o && o->shortlist_abs > 0) ? o->shortlist_abs : 2e-6;
     ctx->cap = (o && o->shortlist_cap > 0) ? o->shortlist_cap : 64;
     ctx->tie_margin = (o && o->tie_margin > 0) ? o->tie_margin : 0.0;
+    ctx->opt_prefilter = o ? o->prefilter : 0;
+    if (o && o->keep_dist32 && ctx->opt_prefilter == 0) ctx->opt_prefilter = 1;  // exact FP32 for EVERY candidate
+    ctx->tc_abs = (o && o->prefilter_abs > 0) ? o->prefilter_abs : 4e-6;
+    if (ctx->opt_prefilter < 0 || ctx->opt_prefilter > 2)
+        return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: prefilter must be 0 (auto), 1 (off) or 2 (required)");
     if (b->n_units == 0) {
         ctx->grids.clear();
         ctx->grid_of_unit.clear();
@@ -518,7 +602,41 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_key.p, 0xff, U * 8, s));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_nitems.p, 0, 16, s));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
-    if (!ctx->h_work.empty()) {
+    const bool tc = ctx->use_tc && !ctx->h_work_tc.empty();
+    ctx->tc_ran = tc;
+    if (tc) {
+        // tier 0: every candidate on the tensor cores (bf16x3, FP32 accumulate) -> approximate dist32 + per-unit minimum
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_key_tc.p, 0xff, U * 8, s));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_tc));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[0], s));
+        k_tc_sweep<<<(unsigned)ctx->h_work_tc.size(), kTcThreads, ctx->smem_tc, s>>>(
+            units, (const WorkItem*)ctx->d_work_tc.p, (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
+            (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key_tc.p);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[1], s));
+        // tier 1: candidates inside the prefilter's error window of the unit's minimum ...
+        k_shortlist<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p,
+                                                (const unsigned long long*)ctx->d_key_tc.p,
+                                                (const unsigned*)ctx->d_rmax.p, 1e-6f, (float)ctx->tc_abs, ctx->l1_cap,
+                                                (int*)ctx->d_l1_count.p, (unsigned*)ctx->d_l1_base.p,
+                                                (int2*)ctx->d_l1_items.p, (unsigned*)ctx->d_l1_n.p, 1, nullptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        // ... are re-scored with the exact FP32 arithmetic of the dense sweep (tier 2)
+        ListArgs la;
+        la.items = (const int2*)ctx->d_l1_items.p;
+        la.count = (const int*)ctx->d_l1_count.p;
+        la.base = (const unsigned*)ctx->d_l1_base.p;
+        la.rmax = (const unsigned*)ctx->d_rmax.p;
+        la.diag = (unsigned*)ctx->d_l1_n.p + 1;
+        if (!launch_sweep(ctx->TA, ctx->multi, (int)ctx->h_work_list.size(), ctx->smem_sweep, s, units,
+                          (const WorkItem*)ctx->d_work_list.p, (const float4*)ctx->d_lay.p,
+                          (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p, &la))
+            return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[2], s));
+        ctx->launches += 3;
+    } else if (!ctx->h_work.empty()) {
         if (!launch_sweep(ctx->TA, ctx->multi, (int)ctx->h_work.size(), ctx->smem_sweep, s, units,
                           (const WorkItem*)ctx->d_work.p, (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p,
                           (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p))
@@ -531,7 +649,7 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
                                             (const unsigned long long*)ctx->d_key.p, (const unsigned*)ctx->d_rmax.p,
                                             (float)ctx->opt_rel, (float)ctx->opt_abs, ctx->pool_cap,
                                             (int*)ctx->d_sl_count.p, (unsigned*)ctx->d_sl_base.p, (int2*)ctx->d_items.p,
-                                            (unsigned*)ctx->d_nitems.p);
+                                            (unsigned*)ctx->d_nitems.p, 0, tc ? (const int*)ctx->d_l1_count.p : nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     {
@@ -759,5 +877,29 @@ extern "C" int mmrs_fp32_probe(mmrs_ctx* ctx, int32_t iters, double* tflops_out)
     cudaEventDestroy(b);
     const double flops = (double)blocks * 256 * (double)iters * 16 * 8 * 2;
     *tflops_out = flops / (ms * 1e-3) / 1e12;
+    return MMRS_OK;
+}
+
+// ---- tensor-core prefilter diagnostics -----------------------------------------------------------
+extern "C" int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]) {
+    if (!ctx || !out) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_prefilter_info: NULL argument");
+    if (!ctx->ran) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_prefilter_info: nothing has been run");
+    for (int i = 0; i < 6; ++i) out[i] = 0.0;
+    out[5] = ctx->tc_abs;
+    if (!ctx->tc_ran || ctx->n_units == 0) return MMRS_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
+    float a = 0.f, b = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&a, ctx->ev_tc[0], ctx->ev_tc[1]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&b, ctx->ev_tc[1], ctx->ev_tc[2]));
+    unsigned h[2] = {0u, 0u};
+    CUDA_TRY(ctx, cudaMemcpy(h, ctx->d_l1_n.p, 8, cudaMemcpyDeviceToHost));
+    float err;
+    std::memcpy(&err, &h[1], 4);
+    out[0] = 1.0;
+    out[1] = a;
+    out[2] = b;
+    out[3] = (double)h[0];
+    out[4] = (double)err;
     return MMRS_OK;
 }

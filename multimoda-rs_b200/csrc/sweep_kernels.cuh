@@ -151,10 +151,17 @@ __global__ void k_cs32(const double2* __restrict__ cs64, float2* __restrict__ cs
 // =============================================================================
 // K1: the FP32 sweep.
 // =============================================================================
-template <int TA, bool MULTI>
+// LIST = false: the dense sweep, work item = (unit, first candidate, candidates in this tile).
+// LIST = true : tier 2 of the tensor-core prefilter (tc_kernels.cuh): work item = (unit, g, G); the CTA scores the
+//               positions g*8 + warp, stepping G*8, of the unit's tier-1 candidate list with the same arithmetic,
+//               overwrites the prefilter's approximate dist32 entries and records the largest observed
+//               |d_tc^2 - d_fp32^2| / Rmax^2 (the prefilter's error, checked against its window by the host).
+template <int TA, bool MULTI, bool LIST>
 __global__ void __launch_bounds__(kThreads, 2)
     k_sweep(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
-            const float2* __restrict__ cs32, float* __restrict__ dist32, unsigned long long* __restrict__ key) {
+            const float2* __restrict__ cs32, float* __restrict__ dist32, unsigned long long* __restrict__ key,
+            const int2* __restrict__ l_items, const int* __restrict__ l_count, const unsigned* __restrict__ l_base,
+            const unsigned* __restrict__ rmax_bits, unsigned* __restrict__ diag) {
     static_assert(TA >= 2 && TA <= 18, "register tile out of range");
     constexpr int H = TA / 2;          // packed pairs of test points per lane
     constexpr bool TAIL = (TA & 1);    // plus one unpaired point when TA is odd
@@ -166,6 +173,15 @@ __global__ void __launch_bounds__(kThreads, 2)
     float4* sA = reinterpret_cast<float4*>(smem_raw + 16);
 
     const WorkItem w = work[blockIdx.x];
+    int total = w.count, first = 0, step = kWarpsPerCta;
+    const int2* my_items = nullptr;
+    if (LIST) {
+        total = l_count[w.unit];
+        first = w.begin * kWarpsPerCta;
+        step = w.count * kWarpsPerCta;
+        if (total <= first) return;  // nothing for this CTA (uniform: before any barrier)
+        my_items = l_items + l_base[w.unit];
+    }
     const UnitDesc ud = units[w.unit];
     const int a_elems = ud.n_chunks * S * 32;
     const int b_elems = ud.m_pairs;          // float4 per PAIR of reference points
@@ -188,8 +204,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     unsigned* my_col = s_col + wid * b_pts;
     const float INF = __int_as_float(0x7f800000);
 
-    for (int ci = wid; ci < w.count; ci += kWarpsPerCta) {
-        const int c = w.begin + ci;
+    float worst = 0.f;
+    for (int ci = first + wid; ci < total; ci += step) {
+        const int c = LIST ? my_items[ci].y : w.begin + ci;
         const float2 cs = __ldg(&cs32[ud.cand_off + c]);
         const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
         unsigned rowmax = 0u, colmax = 0u;  // bit patterns of non-negative floats order like unsigned ints
@@ -264,10 +281,18 @@ __global__ void __launch_bounds__(kThreads, 2)
         const unsigned h2 = __reduce_max_sync(0xffffffffu, max(rowmax, colmax));
         const float d = sqrtf(__uint_as_float(h2));
         if (lane == 0) {
+            if (LIST) {
+                const float old = dist32[ud.dist_off + c];
+                worst = fmaxf(worst, fabsf(d * d - old * old));
+            }
             dist32[ud.dist_off + c] = d;
             const unsigned long long k64 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c;
             best = min(best, k64);
         }
+    }
+    if (LIST && lane == 0 && worst > 0.f) {
+        const float r = fmaxf(__uint_as_float(rmax_bits[w.unit]), 1e-30f);
+        atomicMax(diag, __float_as_uint(worst / (r * r)));
     }
     if (lane == 0 && best != ~0ull) atomicMin(s_key, best);
     __syncthreads();
@@ -280,10 +305,16 @@ __global__ void __launch_bounds__(kThreads, 2)
 // the global item pool with one atomicAdd, then write (unit, candidate) items. A unit may take
 // any number of items; only when the POOL is exhausted is it flagged for the dense f64 path.
 // =============================================================================
+// mode 0: the FP32 window  d <= dmin (1 + rel) + abs_scale Rmax  (tier 2 -> f64 recheck).
+// mode 1: the tensor-core prefilter's window in SQUARED distance  d^2 <= dmin^2 + abs_scale Rmax^2  (tier 1 -> exact
+//         FP32 re-scoring); `key` is then the prefilter's own minimum.
+// prev_count (mode 0, optional): a unit whose tier-1 list overflowed its pool (< 0) was never re-scored in FP32; it is
+// passed on as an overflow so the host rechecks all of its candidates in f64.
 __global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __restrict__ dist32,
                             const unsigned long long* __restrict__ key, const unsigned* __restrict__ rmax_bits,
                             float rel, float abs_scale, unsigned pool_cap, int* __restrict__ sl_count,
-                            unsigned* __restrict__ sl_base, int2* __restrict__ items, unsigned* __restrict__ n_items) {
+                            unsigned* __restrict__ sl_base, int2* __restrict__ items, unsigned* __restrict__ n_items,
+                            int mode, const int* __restrict__ prev_count) {
     __shared__ int s_n, s_pos;
     __shared__ unsigned s_base;
     const int u = blockIdx.x;
@@ -295,10 +326,19 @@ __global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __r
         }
         return;
     }
+    if (prev_count && prev_count[u] < 0) {
+        if (threadIdx.x == 0) {
+            sl_count[u] = -ud.n_cand;
+            sl_base[u] = 0;
+        }
+        return;
+    }
     if (threadIdx.x == 0) s_n = 0, s_pos = 0;
     __syncthreads();
     const float dmin = __uint_as_float((unsigned)(key[u] >> 32));
-    const float thr = dmin * (1.0f + rel) + abs_scale * __uint_as_float(rmax_bits[u]);
+    const float rmax = __uint_as_float(rmax_bits[u]);
+    const float thr = mode == 1 ? sqrtf(fmaf(dmin, dmin, abs_scale * rmax * rmax)) * (1.0f + rel)
+                                : dmin * (1.0f + rel) + abs_scale * rmax;
     const float* d = dist32 + ud.dist_off;
     int mine = 0;
     for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x) mine += (d[c] <= thr) ? 1 : 0;

@@ -38,7 +38,8 @@ class SweepBatch(C.Structure):
 
 class SweepOpts(C.Structure):
     _fields_ = [("shortlist_rel", C.c_double), ("shortlist_abs", C.c_double), ("shortlist_cap", C.c_int32),
-                ("tie_margin", C.c_double), ("keep_dist32", C.c_int32)]
+                ("tie_margin", C.c_double), ("keep_dist32", C.c_int32), ("prefilter", C.c_int32),
+                ("prefilter_abs", C.c_double)]
 
 
 class UnitResult(C.Structure):
@@ -74,7 +75,7 @@ EXPORTS = [
     "mmrs_sweep_download", "mmrs_sweep_plan", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
     "mmrs_process_cases", "mmrs_process_stats", "mmrs_ctx_set_shard", "mmrs_export_pair", "mmrs_export_single",
-    "mmrs_align_centerline",
+    "mmrs_align_centerline", "mmrs_sweep_prefilter_info",
 ]
 
 _lib = None
@@ -189,8 +190,11 @@ class Context:
         return b, U
 
     @staticmethod
-    def _opts(shortlist_rel=0.0, shortlist_abs=0.0, shortlist_cap=0, tie_margin=0.0, keep_dist32=False):
-        return SweepOpts(shortlist_rel, shortlist_abs, shortlist_cap, tie_margin, int(keep_dist32))
+    def _opts(shortlist_rel=0.0, shortlist_abs=0.0, shortlist_cap=0, tie_margin=0.0, keep_dist32=False, prefilter=0,
+              prefilter_abs=0.0):
+        """prefilter: 0 auto, 1 off (dense FP32 sweep), 2 required (tensor-core tier, mmrs_b200.h)."""
+        return SweepOpts(shortlist_rel, shortlist_abs, shortlist_cap, tie_margin, int(keep_dist32), int(prefilter),
+                         float(prefilter_abs))
 
     def sweep_batched(self, test_xy, test_off, ref_xy, ref_off, centre_xy, grids, grid_of_unit=None, mode=0, **opts):
         """Host arrays in, structured result array (RESULT_DTYPE) out."""
@@ -245,6 +249,13 @@ class Context:
         n = C.c_int32()
         self._check(lib().mmrs_last_timings(self._p, ms, C.byref(n)))
         return dict(sweep_ms=ms[0], shortlist_ms=ms[1], recheck_ms=ms[2], total_ms=ms[3], launches=n.value)
+
+    def prefilter_info(self):
+        """mmrs_sweep_prefilter_info of the last run."""
+        o = (C.c_double * 6)()
+        lib().mmrs_sweep_prefilter_info.argtypes = [C.c_void_p, c_dp]
+        self._check(lib().mmrs_sweep_prefilter_info(self._p, o))
+        return dict(ran=bool(o[0]), tc_ms=o[1], rescore_ms=o[2], rescored=int(o[3]), max_err=o[4], window=o[5])
 
     def eval_exact(self, test_xy, ref_xy, centre, mode, angles):
         t, r, a = _f64(test_xy).reshape(-1, 2), _f64(ref_xy).reshape(-1, 2), _f64(angles).reshape(-1)
