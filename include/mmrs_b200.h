@@ -122,8 +122,9 @@ typedef struct mmrs_sweep_opts {
      * candidate and its f64 distance are identical to the dense path. With the prefilter,
      * mmrs_sweep_get_dist32 returns prefilter-quality values (|error| <~ 1e-6 * Rmax^2 / d on d) for
      * candidates outside that window and exact FP32 values inside it.
-     * 0 = auto (on when every unit has 64..2048 points per set and the batch averages >= 32
-     * candidates per unit), 1 = off (dense FP32 sweep of every candidate), 2 = required.        */
+     * 0 = auto, 1 = off (dense FP32 sweep of every candidate), 2 = required (every unit must have
+     * 64..2048 points per set). Auto currently resolves to OFF: measured on B200 the prefilter kernel
+     * is slower than the dense FP32 sweep, so it is an opt-in experimental tier.   */
     int32_t prefilter;
     double prefilter_abs; /* <= 0 selects 4e-6 (about 7x the largest error measured) */
 } mmrs_sweep_opts;

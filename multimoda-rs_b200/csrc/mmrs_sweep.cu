@@ -431,7 +431,9 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
         const char* env = std::getenv("MMRS_PREFILTER");  // experiments: 0 = off, 1 = on where the shapes allow
         int mode = ctx->opt_prefilter;
         if (env && *env) mode = (*env == '0') ? 1 : 2;
-        ctx->use_tc = mode != 1 && ctx->tc_shape_ok && live_units > 0 && (mode == 2 || live >= 32 * live_units);
+        // auto (0) currently resolves to the dense FP32 sweep: on B200 the prefilter's per-tile TMEM hand-shakes and
+        // the FMNMX-bound epilogue make K1t slower than K1 (17 vs 24 M evaluations/s).
+        ctx->use_tc = mode == 2 && ctx->tc_shape_ok && live_units > 0;
         if (mode == 2 && !ctx->use_tc && ctx->opt_prefilter == 2)
             return set_err(ctx, MMRS_ERR_ARG,
                            "prefilter required but the batch does not fit the tensor-core operand layout (64 <= points "
@@ -610,10 +612,37 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_tc));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[0], s));
+        const char* trace_path = std::getenv("MMRS_TC_TRACE");  // experiments: per-tile clock stamps of CTA 0
+        long long* d_trace = nullptr;
+        if (trace_path && *trace_path) {
+            ENSURE(ctx->d_tmp, (8 * 256 + 64 * 8) * 8);
+            d_trace = (long long*)ctx->d_tmp.p;
+            CUDA_TRY(ctx, cudaMemsetAsync(d_trace, 0, (8 * 256 + 64 * 8) * 8, s));
+        }
         k_tc_sweep<<<(unsigned)ctx->h_work_tc.size(), kTcThreads, ctx->smem_tc, s>>>(
             units, (const WorkItem*)ctx->d_work_tc.p, (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
-            (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key_tc.p);
+            (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key_tc.p, d_trace);
         CUDA_TRY(ctx, cudaGetLastError());
+        if (d_trace) {
+            std::vector<long long> h(8 * 256 + 64 * 8);
+            CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            if (FILE* f = std::fopen(trace_path, "w")) {
+                std::fprintf(f, "tile wg issuer_ready issuer_committed epi_woken epi_released\n");
+                for (int g = 0; g < 2; ++g)
+                    for (int t = 0; t < 256; ++t)
+                        std::fprintf(f, "%d %d %lld %lld %lld %lld\n", t, g, h[(g * 4 + 0) * 256 + t], h[(g * 4 + 1) * 256 + t],
+                                     h[(g * 4 + 2) * 256 + t], h[(g * 4 + 3) * 256 + t]);
+                std::fprintf(f, "fine stamps (wg 0, quarter 0): tile start ld0_done fold0_done wait1_done wait3_done fold3_done fenced\n");
+                for (int t = 0; t < 64; ++t) {
+                    std::fprintf(f, "%d", t);
+                    for (int k = 0; k < 7; ++k) std::fprintf(f, " %lld", h[2048 + t * 8 + k] - h[2048 + t * 8]);
+                    std::fprintf(f, " | woken->start %lld, fenced->released %lld\n", h[2048 + t * 8] - h[(0 * 4 + 2) * 256 + t],
+                                 h[(0 * 4 + 3) * 256 + t] - h[2048 + t * 8 + 6]);
+                }
+                std::fclose(f);
+            }
+        }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[1], s));
         // tier 1: candidates inside the prefilter's error window of the unit's minimum ...
         k_shortlist<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p,

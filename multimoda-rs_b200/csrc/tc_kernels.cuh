@@ -15,9 +15,12 @@
 //                    One tcgen05.mma (M = 128, N <= 128, K = 16, cta_group::1) per 128 x N tile, operands in the
 //                    no-swizzle K-major canonical layout, accumulators in TMEM (4 stages of 128 columns), read
 //                    back with tcgen05.ld.32x32b (one thread = one row) and folded with 3-input FMNMX.
-//                    Warp roles: warp 0 issues the MMAs, warps 1-3 rotate + split the test points of the
-//                    next candidate into shared memory, warps 4-11 (two warpgroups, each with its own pair
-//                    of TMEM stages) are the min/max epilogue. The epilogue's FMNMX rate is the bound.
+//                    Warp roles: warps 2-5 rotate + split the test points of the
+//                    next candidate into shared memory, warps 6-13 (two warpgroups, each with its own pair
+//                    of TMEM stages and its own MMA-issuing thread in warps 0-1) are the min/max epilogue. The
+//                    issuers read their operand descriptors from small tables built once per CTA: a single
+//                    thread that recomputes them per tile is slower than the tensor core AND the epilogue.
+//                    The epilogue's FMNMX rate is the bound.
 //   k_sweep<.., LIST> (sweep_kernels.cuh) then re-scores, with the exact FP32 arithmetic of K1, only the
 //                    candidates whose tensor-core distance lies inside the prefilter's error window of the unit's
 //                    minimum; K2/K3/K4 (FP32 window -> reference f64 arithmetic -> leftmost arg-min) are unchanged,
@@ -34,8 +37,8 @@
 
 namespace mmrs {
 
-constexpr int kTcThreads = 384;
-constexpr int kTcProducers = 96;
+constexpr int kTcThreads = 448;    // warps 0-1: MMA issuers, 2-5: producers, 6-13: epilogue (two warpgroups)
+constexpr int kTcProducers = 128;
 constexpr int kTcGroup = 384;  // bytes per 8 operand rows: [k0..7 | k8..15 variant 1 | k8..15 variant 2], 128 B each
 constexpr int kTcMaxPts = 2048;
 constexpr int kTcMinPts = 64;
@@ -78,7 +81,7 @@ struct TcGeom {  // row bookkeeping of one point set as an MMA operand
 __host__ __device__ inline size_t tc_smem_bytes(int n, int m, int ndyn) {
     const TcGeom a = TcGeom::make(n, false), b = TcGeom::make(m, true);
     return (size_t)(b.rows / 8) * kTcGroup + (size_t)ndyn * (a.rows / 8) * kTcGroup + (size_t)a.rows * 8 + (size_t)a.rows * 4 +
-           (size_t)b.rows * 4 + 512;
+           (size_t)b.rows * 4 + 1024;
 }
 
 // ---- tcgen05 / mbarrier helpers -------------------------------------------------------------------
@@ -163,6 +166,10 @@ struct TcShared {  // small control block at the end of the dynamic shared memor
     unsigned long long key;
     uint32_t tmem_base;
     unsigned cand_val[8], cand_cnt[8];
+    // descriptor tables of the MMA issuers (low descriptor words; dynamic-buffer entries are relative to the buffer)
+    uint2 job_a[32];   // per M-tile job: {A descriptor low word, 1 if A is the dynamic operand (P1)}
+    uint2 col_s[16];   // P1 column tiles (static operand): {B descriptor low word, instruction descriptor}
+    uint2 col_d[16];   // P2 column tiles (dynamic operand): {B descriptor low word (relative), instruction descriptor}
 };
 
 // =============================================================================
@@ -171,7 +178,10 @@ struct TcShared {  // small control block at the end of the dynamic shared memor
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc_sweep(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, const double* __restrict__ test_xy,
                const double* __restrict__ ref_xy, const float2* __restrict__ cs32, float* __restrict__ dist32,
-               unsigned long long* __restrict__ key_tc) {
+               unsigned long long* __restrict__ key_tc, long long* __restrict__ trace) {
+    // trace (experiments only, MMRS_TC_TRACE): clock64 stamps of CTA 0, [wg][kind][tile < 256];
+    // kind 0 issuer after its stage wait, 1 issuer after commit, 2 epilogue (quarter 0) woken, 3 epilogue arrives
+    const bool tracing = trace != nullptr && blockIdx.x == 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const WorkItem w = work[blockIdx.x];
     const UnitDesc ud = units[w.unit];
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     // ---- setup -------------------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init_n(&sh->dyn_full[i], kTcProducers), mbar_init_n(&sh->dyn_empty[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init_n(&sh->dyn_full[i], kTcProducers), mbar_init_n(&sh->dyn_empty[i], 2);
         for (int i = 0; i < 4; ++i) mbar_init_n(&sh->tmem_full[i], 1), mbar_init_n(&sh->tmem_empty[i], 4);
         sh->key = ~0ull;
         for (int i = 0; i < 8; ++i) sh->cand_val[i] = 0u, sh->cand_cnt[i] = 0u;
@@ -228,63 +238,69 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         *reinterpret_cast<uint4*>(row + 128) = make_uint4(yhm, ylh, ns.x, ns.y);            // P1 columns: + |b|^2
         *reinterpret_cast<uint4*>(row + 256) = make_uint4(yhm, ylh, kBf16One2, kBf16One1);  // P2 rows: x 1
     }
+    const int MA = ga.m_tiles(), MB = gb.m_tiles(), J = MA + MB;
+    const int NTA = ga.n_tiles(), NTB = gb.n_tiles();
+    {   // issuer tables
+        const uint32_t a_static = smem_u32(s_static);
+        for (int j = tid; j < J; j += kTcThreads) {
+            const bool p1 = j < MA;
+            const int mt = p1 ? j : j - MA;
+            const uint32_t off = (uint32_t)mt * 16u * kTcGroup;
+            sh->job_a[j] = p1 ? make_uint2((off >> 4) | ((128u >> 4) << 16), 1u)
+                              : make_uint2(((a_static + off) >> 4) | ((256u >> 4) << 16), 0u);
+        }
+        for (int t = tid; t < NTB; t += kTcThreads)
+            sh->col_s[t] = make_uint2(((a_static + (uint32_t)(gb.tile_row0(t) >> 3) * kTcGroup) >> 4) | ((128u >> 4) << 16),
+                                      tc_idesc(gb.tile_w(t)));
+        for (int t = tid; t < NTA; t += kTcThreads)
+            sh->col_d[t] = make_uint2((((uint32_t)(ga.tile_row0(t) >> 3) * kTcGroup) >> 4) | ((256u >> 4) << 16),
+                                      tc_idesc(ga.tile_w(t)));
+    }
     proxy_fence_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sh->tmem_base;
-    const int MA = ga.m_tiles(), MB = gb.m_tiles(), J = MA + MB;
-    const int NTA = ga.n_tiles(), NTB = gb.n_tiles();
 
-    if (warp == 0) {
-        // ===== MMA issuer (one thread) =====
+    if (warp < 2) {
+        // ===== MMA issuers: warp g feeds warpgroup g through TMEM stages {g, g + 2} (one thread each) =====
         if (lane == 0) {
-            const uint32_t a_static = smem_u32(s_static), a_dyn = smem_u32(s_dyn);
-            uint32_t cnt[2] = {0u, 0u};
+            const int g = warp;
+            const uint64_t hi = (uint64_t)((uint32_t)(kTcGroup >> 4) | (1u << 14)) << 32;  // SBO, descriptor version 1
+            const uint32_t dyn0 = smem_u32(s_dyn) >> 4, dyn_step = dyn_stride >> 4;
+            uint32_t cnt = 0;
             for (int ci = 0; ci < w.count; ++ci) {
                 const int b = ci % ndyn;
                 mbar_wait(&sh->dyn_full[b], (uint32_t)((ci / ndyn) & 1));
                 tc_fence_after();
-                const uint32_t dyn = a_dyn + (uint32_t)b * dyn_stride;
-                for (int p = 0; p < J; p += 2) {
-                    const int nt0 = p < MA ? NTB : NTA;
-                    const int nt1 = (p + 1 < J) ? ((p + 1) < MA ? NTB : NTA) : 0;
-                    const int nt = nt0 > nt1 ? nt0 : nt1;
+                const uint32_t dyn_lo = dyn0 + (uint32_t)b * dyn_step;
+                for (int j = g; j < J; j += 2) {
+                    const uint2 ja = sh->job_a[j];
+                    const bool p1 = ja.y != 0u;
+                    const uint64_t da = hi | (uint64_t)(ja.x + (p1 ? dyn_lo : 0u));
+                    const uint2* col = p1 ? sh->col_s : sh->col_d;
+                    const uint32_t add_b = p1 ? 0u : dyn_lo;
+                    const int nt = p1 ? NTB : NTA;
                     for (int t = 0; t < nt; ++t) {
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int j = p + g;
-                            if (t >= (g ? nt1 : nt0)) continue;
-                            const bool p1 = j < MA;
-                            const int mt = p1 ? j : j - MA;
-                            const uint32_t st = (uint32_t)g + 2u * (cnt[g] & 1u), use = cnt[g] >> 1;
-                            if (use > 0) {
-                                mbar_wait(&sh->tmem_empty[st], (use - 1) & 1u);
-                                tc_fence_after();
-                            }
-                            uint64_t da, db;
-                            int wdt;
-                            if (p1) {  // rows: rotated test tile mt (role A); columns: reference tile t
-                                da = tc_desc(dyn + (uint32_t)mt * 16u * kTcGroup, 128);
-                                db = tc_desc(a_static + (uint32_t)(gb.tile_row0(t) >> 3) * kTcGroup, 128);
-                                wdt = gb.tile_w(t);
-                            } else {   // rows: reference tile mt; columns: rotated test tile t (role B)
-                                da = tc_desc(a_static + (uint32_t)mt * 16u * kTcGroup, 256);
-                                db = tc_desc(dyn + (uint32_t)(ga.tile_row0(t) >> 3) * kTcGroup, 256);
-                                wdt = ga.tile_w(t);
-                            }
-                            tc_mma(tmem + st * 128u, da, db, tc_idesc(wdt));
-                            tc_commit(&sh->tmem_full[st]);
-                            ++cnt[g];
+                        const uint2 cb = col[t];
+                        const uint32_t st = (uint32_t)g + 2u * (cnt & 1u), use = cnt >> 1;
+                        if (use > 0) {
+                            mbar_wait(&sh->tmem_empty[st], (use - 1) & 1u);
+                            tc_fence_after();
                         }
+                        if (tracing && cnt < 256) trace[(g * 4 + 0) * 256 + cnt] = clock64();
+                        tc_mma(tmem + st * 128u, da, hi | (uint64_t)(cb.x + add_b), cb.y);
+                        tc_commit(&sh->tmem_full[st]);
+                        if (tracing && cnt < 256) trace[(g * 4 + 1) * 256 + cnt] = clock64();
+                        ++cnt;
                     }
                 }
-                tc_commit(&sh->dyn_empty[b]);  // every MMA that reads this buffer has completed when this arrives
+                tc_commit(&sh->dyn_empty[b]);  // arrives when every MMA this thread issued on the buffer is done
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 6) {
         // ===== producers: rotate + split the test points of candidate ci into buffer ci % ndyn =====
-        const int pid = tid - 32;
+        const int pid = tid - 64;
         for (int ci = 0; ci < w.count; ++ci) {
             const int b = ci % ndyn, use = ci / ndyn;
             if (use > 0) mbar_wait(&sh->dyn_empty[b], (uint32_t)((use - 1) & 1));
@@ -306,7 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
     } else {
         // ===== epilogue: row minima of every tile, + norm, max over rows; one value per candidate =====
-        const int wg = (warp - 4) >> 2, q = warp & 3;
+        const int wg = (warp - 6) >> 2, q = warp & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float INF = __int_as_float(0x7f800000);
         uint32_t cnt = 0;
@@ -316,7 +332,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int j = wg; j < J; j += 2) {
                 const bool p1 = j < MA;
                 const int mt = p1 ? j : j - MA;
-                const TcGeom& gc = p1 ? gb : ga;  // the column side
+                const uint2* col = p1 ? sh->col_s : sh->col_d;  // the column side
                 const int nt = p1 ? NTB : NTA;
                 const bool valid = (p1 ? ga : gb).quarter_valid(mt, q);
                 float m0 = INF, m1 = INF, m2 = INF, m3 = INF;
@@ -324,8 +340,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const uint32_t st = (uint32_t)wg + 2u * (cnt & 1u), use = cnt >> 1;
                     mbar_wait(&sh->tmem_full[st], use & 1u);
                     tc_fence_after();
+                    if (tracing && q == 0 && lane == 0 && cnt < 256) trace[(wg * 4 + 2) * 256 + cnt] = clock64();
                     if (valid) {
-                        const int wdt = gc.tile_w(t);
+                        const int wdt = (int)((col[t].y >> 17) & 0x3fu) << 3;
                         const uint32_t taddr = tmem + st * 128u + lane_base;
                         uint32_t va[32], vb[32];
                         auto fold32 = [&](const uint32_t* v) {
@@ -338,18 +355,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                             }
                         };
                         if (wdt == 128) {  // software-pipelined: the next 32 columns are in flight while 32 are folded
+                            const bool tr2 = tracing && wg == 0 && q == 0 && lane == 0 && cnt < 64;
+                            long long* t2 = trace + 2048 + cnt * 8;
+                            if (tr2) t2[0] = clock64();
                             tmem_ld32(taddr, va);
                             tmem_wait_ld();
+                            if (tr2) t2[1] = clock64();
                             tmem_ld32(taddr + 32, vb);
                             fold32(va);
+                            if (tr2) t2[2] = clock64();
                             tmem_wait_ld();
+                            if (tr2) t2[3] = clock64();
                             tmem_ld32(taddr + 64, va);
                             fold32(vb);
                             tmem_wait_ld();
                             tmem_ld32(taddr + 96, vb);
                             fold32(va);
                             tmem_wait_ld();
+                            if (tr2) t2[4] = clock64();
                             fold32(vb);
+                            if (tr2) t2[5] = clock64();
                         } else {
                             int c = 0;
                             for (; c + 32 <= wdt; c += 32) {
@@ -371,8 +396,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         }
                     }
                     tc_fence_before();
+                    if (tracing && wg == 0 && q == 0 && lane == 0 && cnt < 64) trace[2048 + cnt * 8 + 6] = clock64();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh->tmem_empty[st]);
+                    if (tracing && q == 0 && lane == 0 && cnt < 256) trace[(wg * 4 + 3) * 256 + cnt] = clock64();
                     ++cnt;
                 }
                 if (valid) {

@@ -110,5 +110,5 @@ def test_prefilter_required_rejects_unfit_shapes(ctx):
     g = nat.make_grid(0.5, 90.0)
     with pytest.raises(nat.MmrsError, match="prefilter required"):
         ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=0, prefilter=2)
-    res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=0)   # auto: falls back to the dense sweep
+    res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=0)   # auto: the dense sweep
     assert not ctx.prefilter_info()["ran"] and (res["best_idx"] >= 0).all()
