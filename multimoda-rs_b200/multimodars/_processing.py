@@ -83,8 +83,7 @@ def _pair(out, i, label_a, label_b):
 
 def _run(mode, blobs, labels, step, rng, sample_size, smooth, bruteforce, postprocessing=False, export=None):
     ctx = get_context()
-    out, logs, _ = nat.process_cases(ctx, mode, blobs, step, rng, sample_size, smooth, bruteforce, postprocessing,
-                export)
+    out, logs, _ = nat.process_cases(ctx, mode, blobs, step, rng, sample_size, smooth, bruteforce, postprocessing)
     L = labels
     lg = tuple(_logs(l) for l in logs)
     if mode == 4:

@@ -9,7 +9,7 @@ import math
 import numpy as np
 import pytest
 
-from multimodars import PyGeometry, align_combined, align_manual, align_three_point, get_context
+from multimodars import PyCenterline, PyCenterlinePoint, PyGeometry, align_combined, align_manual, align_three_point, get_context
 from multimodars import _native as nat
 from tests.test_centerline_cpu import centerline, newell, place, pullback
 from scipy.spatial.transform import Rotation
@@ -36,14 +36,22 @@ def targets_for(g, theta_deg, p0, d, ref_index, n):
 
 
 def test_combined_recovers_planted_rotation_and_index():
-    n, direction = 48, (0.0, 0.0, -1.0)
+    # a tilted centerline: the cost reads (x, y) only (process_utils.rs:78-121), so a centerline along z could not
+    # tell the indices apart. The candidates rotate the ALREADY PLACED frames in the x-y plane
+    # (rotate_by_best_rotation on the aligned target, align_algorithms.rs:398-402), which for tilted frames is close
+    # to, not exactly, a rotation about the tangent: the planted 6 degrees come back to within one grid step.
+    # The stored tangents point against the direction of travel (towards +z, like the lumen normals): with tangents
+    # along -z the placement turns every frame over (angle(normal, tangent) ~ 174 degrees) and the candidates'
+    # re-sort (Geometry::rotate_geometry, geometry.rs:241-250) makes all non-zero angles cost the same.
+    n, direction = 48, (0.1, -0.05, -1.0)
     g = pullback(n_frames=5, n=n, dz=1.0, ref_frame=0, ref_index=7, ry=1.5)
     p0 = np.array([3.0, -2.0, 25.0])
     cl = centerline(p0, direction, 60, 0.5)
     d = np.asarray(direction) / np.linalg.norm(direction)
+    cl = PyCenterline([PyCenterlinePoint(q.contour_point, tuple(-d)) for q in cl.points])
     theta0 = 30.0
     s = float(np.mean(np.linalg.norm(np.diff(np.array([f.centroid for f in g.frames]), axis=0), axis=1)))
-    main, ccw, cw = targets_for(g, theta0, p0 + 4.0 * s * d, d, 7, n)   # three-point start: resampled index 4
+    main, ccw, cw = targets_for(g, theta0, p0 + 4.0 * s * d, -d, 7, n)   # three-point start: resampled index 4
     start, spacing, rot0 = align_three_point(cl, g, main, ccw, cw)
     assert abs(rot0 - theta0) < 1e-9 and abs(spacing - s) < 1e-12
     # plant: the cloud is the geometry placed one centerline point further with 6 more degrees
@@ -51,9 +59,9 @@ def test_combined_recovers_planted_rotation_and_index():
     cloud = lumen_cloud(planted)
     res, _, rot = align_combined(cl, g, main, ccw, cw, [tuple(p) for p in cloud], angle_step_deg=1.0,
                                  angle_range_deg=10.0, index_range=2)
-    assert abs(rot - (theta0 + 6.0)) < 1e-6, rot
-    assert np.allclose(lumen_cloud(res), cloud, atol=1e-6)
-    assert np.allclose(res.frames[0].centroid, p0 + 5.0 * s * d, atol=1e-9)
+    assert abs(rot - (theta0 + 6.0)) <= 1.0 + 1e-9, rot
+    assert np.allclose(res.frames[0].centroid, p0 + 5.0 * s * d, atol=1e-9)      # the planted centerline index
+    assert np.abs(lumen_cloud(res) - cloud).max() < 0.06                          # within one degree at r = 2.25
     st = get_context().process_stats()
     assert st["units"] > 0 and st["launches"] > 0   # the candidates went through the sweep kernels
 
