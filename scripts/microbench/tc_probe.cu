@@ -173,6 +173,72 @@ __global__ void __launch_bounds__(256) k_probe_epi(float* out, int iters, int co
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "n"(512));
 }
 
+// (3) the same epilogue loop (ld x32 + 16 FMNMX3 on columns 0..255) while a ninth warp keeps the tensor core busy:
+// back-to-back M=128 N=128 K=16 MMAs into columns 256..511, `mma_per_round` of them per commit + wait.
+__global__ void __launch_bounds__(288) k_probe_epi_mma(float* out, int iters, long long* cyc, int mma_per_round) {
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint64_t bar;
+    __shared__ int stop;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 16 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3f803f80u, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); stop = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 8) {
+        if (lane == 0 && mma_per_round > 0) {
+            const uint64_t da = make_desc(smem_u32(smem), 128, 256), db = make_desc(smem_u32(smem) + 8192, 128, 256);
+            const uint32_t idesc = make_idesc(128, 128);
+            uint32_t phase = 0;
+            long long n = 0;
+            while (*((volatile int*)&stop) == 0) {
+                for (int k = 0; k < mma_per_round; ++k) mma_ss(tmem_base_s + 256 + 128 * (k & 1), da, db, idesc, 0u);
+                mma_commit(&bar);
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+                n += mma_per_round;
+            }
+            cyc[gridDim.x + blockIdx.x] = n;
+        }
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
+    const uint32_t tmem = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 128;
+    float m0 = 1e30f, m1 = 1e30f, m2 = 1e30f, m3 = 1e30f;
+    uint32_t v[32];
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        for (int c = 0; c < 128; c += 32) {
+            tmem_ld32(tmem + (uint32_t)c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+                m0 = min3(m0, __uint_as_float(v[k]), __uint_as_float(v[k + 1]));
+                m1 = min3(m1, __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+                m2 = min3(m2, __uint_as_float(v[k + 4]), __uint_as_float(v[k + 5]));
+                m3 = min3(m3, __uint_as_float(v[k + 6]), __uint_as_float(v[k + 7]));
+            }
+        }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * 256 + threadIdx.x] = m0 + m1 + m2 + m3;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+    // the eight epilogue warps meet here (named barrier 1), then the tensor-core warp is told to stop
+    asm volatile("bar.sync 1, 256;");
+    if (threadIdx.x == 0) *((volatile int*)&stop) = 1;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "n"(512));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------
@@ -319,6 +385,28 @@ int main() {
             printf("[epi] mode %d (%s): %.0f cycles, %.2f cycles per 32-column chunk per SMSP, %.3f cycles per element-lane\n", mode,
                    mode == 0 ? "ld x32 + 16 FMNMX3" : mode == 1 ? "ld x32 only" : "16 FMNMX3 only", avg, avg / chunks_per_smsp,
                    avg / chunks_per_smsp / 32.0);
+        }
+    }
+    // (3) epilogue throughput with the tensor core running beside it
+    {
+        cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+        const int sms = p.multiProcessorCount;
+        float* out; long long* cyc;
+        CK(cudaMalloc(&out, sms * 256 * 4)); CK(cudaMalloc(&cyc, 2 * sms * 8));
+        CK(cudaFuncSetAttribute(k_probe_epi_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+        const int iters = 4000;
+        std::vector<long long> h(2 * sms);
+        for (int per_round : {0, 1, 4}) {
+            CK(cudaMemset(cyc, 0, 2 * sms * 8));
+            k_probe_epi_mma<<<sms, 288, 32 * 1024>>>(out, iters, cyc, per_round);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("[epi+mma] CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+            CK(cudaMemcpy(h.data(), cyc, 2 * sms * 8, cudaMemcpyDeviceToHost));
+            double avg = 0, mm = 0; for (int i = 0; i < sms; ++i) { avg += (double)h[i]; mm += (double)h[sms + i]; }
+            avg /= sms; mm /= sms;
+            const double chunks_per_smsp = 2.0 * iters * 4;
+            printf("[epi+mma] %d MMAs (128x128x16) per commit: epilogue %.2f cycles per 32-column chunk per SMSP; %.0f MMAs in %.0f cycles = %.1f cycles per MMA\n",
+                   per_round, avg / chunks_per_smsp, mm, avg, mm > 0 ? avg / mm : 0.0);
         }
     }
     printf("done\n");
