@@ -26,6 +26,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     }
 }
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t phase) {  // non-blocking test_wait polling
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
 }
@@ -192,17 +199,17 @@ __global__ void __launch_bounds__(288) k_probe_epi_mma(float* out, int iters, lo
     __syncthreads();
     tc_fence_after();
     if (warp == 8) {
-        if (lane == 0 && mma_per_round > 0) {
+        if (lane == 0 && mma_per_round % 100 > 0) {
             const uint64_t da = make_desc(smem_u32(smem), 128, 256), db = make_desc(smem_u32(smem) + 8192, 128, 256);
             const uint32_t idesc = make_idesc(128, 128);
             uint32_t phase = 0;
             long long n = 0;
             while (*((volatile int*)&stop) == 0) {
-                for (int k = 0; k < mma_per_round; ++k) mma_ss(tmem_base_s + 256 + 128 * (k & 1), da, db, idesc, 0u);
+                for (int k = 0; k < mma_per_round % 100; ++k) mma_ss(tmem_base_s + 256 + 128 * (k & 1), da, db, idesc, 0u);
                 mma_commit(&bar);
-                mbar_wait(&bar, phase);
+                if (mma_per_round >= 100) mbar_spin(&bar, phase); else mbar_wait(&bar, phase);
                 phase ^= 1;
-                n += mma_per_round;
+                n += mma_per_round % 100;
             }
             cyc[gridDim.x + blockIdx.x] = n;
         }
@@ -396,7 +403,7 @@ int main() {
         CK(cudaFuncSetAttribute(k_probe_epi_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
         const int iters = 4000;
         std::vector<long long> h(2 * sms);
-        for (int per_round : {0, 1, 4}) {
+        for (int per_round : {0, 1, 4, 101, 104}) {
             CK(cudaMemset(cyc, 0, 2 * sms * 8));
             k_probe_epi_mma<<<sms, 288, 32 * 1024>>>(out, iters, cyc, per_round);
             cudaError_t e = cudaDeviceSynchronize();
