@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api", action="store_true", help="skip the from_array_singlepair wall-time leg")
+    ap.add_argument("--no-tc", action="store_true", help="skip the tensor-core prefilter leg (reported, not timed in the step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -344,7 +345,7 @@ def main():
 
     # ---- the opt-in tensor-core prefilter tier on a 40-unit slice of the same batch (reported, not the headline) -----
     tcp = None
-    if world == 1:
+    if world == 1 and not args.no_tc:
         Us = 40
         sl = slice(0, Us * n)
         out = {}
