@@ -185,6 +185,12 @@ def main():
         run_reference(args)
         return
 
+    # ONE JSON line on stdout: everything any library prints while we run (NCCL's version banner is written to fd 1
+    # by the C library) goes to stderr; the saved descriptor is restored just before the line is printed.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -379,6 +385,8 @@ def main():
                     "call": "mmrs_sweep_batched (host buffers in, host results out)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "api": api,
             "tc_prefilter": tcp}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -570,6 +570,13 @@ class PyCenterline:
     def points_as_tuples(self):
         return [(p.contour_point.x, p.contour_point.y, p.contour_point.z) for p in self.points]
 
+    def _ccta_side(self, *a, **k):
+        raise NotImplementedError("PyCenterline branch editing / resampling (py_centerline.rs:62-143) belongs to the "
+                                  "CCTA preprocessing side of the reference and is not part of this build (DESIGN.md §8)")
+
+    calculate_branches = find_sharp_angles = split_branch = merge_branches = get_branch = remove_branch_overlap = \
+        trim_start = resample = smooth = orient_by_max_z = orient_to_reference = _ccta_side
+
     def _rows(self):
         """(n, 8) [x, y, z, tx, ty, tz, branch_id, radius] — the row layout of mmrs_align_centerline."""
         return np.array([[p.contour_point.x, p.contour_point.y, p.contour_point.z, *p.tangent, float(p.branch_id),
