@@ -102,6 +102,69 @@ def process_cases_sharded(mode, blobs, step_deg, range_deg, sample_size, smooth,
                    for k, c in enumerate(mine)}
 
 
+def process_cases_pipelined(device, mode, blobs, step_deg, range_deg, sample_size, smooth, bruteforce,
+                            postprocessing=False, chunk_cases=8, workers=2):
+    """A cohort on ONE GPU with the host work hidden behind the device work: the cases are cut into chunks and
+    `workers` host threads, each with its own context (its own CUDA stream and device workspaces), pull chunks from
+    a queue and run mmrs_process_cases on them. While one thread's sweep kernels occupy the GPU, the other decodes
+    blobs, builds units, replays the frame chain and encodes results (ctypes releases the GIL for the whole call),
+    so the decode / chain / post-step time of chunk k+1 overlaps the sweeps of chunk k. Results come back in case
+    order: (out_blobs, logs, anomalous, stats) exactly like _native.process_cases plus the summed counters."""
+    import queue
+    import threading
+
+    from ._native import N_IN, N_OUT, Context, process_cases
+
+    n_in, n_out = N_IN[mode], N_OUT[mode]
+    n_cases = len(blobs) // n_in
+    chunks = [range(i, min(i + chunk_cases, n_cases)) for i in range(0, n_cases, chunk_cases)]
+    if len(chunks) <= 1 or workers <= 1:
+        ctx = Context(device)
+        o, l, a = process_cases(ctx, mode, blobs, step_deg, range_deg, sample_size, smooth, bruteforce, postprocessing)
+        st = ctx.process_stats()
+        ctx.close()
+        return o, l, a, st
+    q = queue.Queue()
+    for k in range(len(chunks)):
+        q.put(k)
+    res, errs = [None] * len(chunks), []
+    stats = {}
+    lock = threading.Lock()
+
+    def run():
+        ctx = Context(device)
+        try:
+            while True:
+                try:
+                    k = q.get_nowait()
+                except queue.Empty:
+                    return
+                c = chunks[k]
+                res[k] = process_cases(ctx, mode, blobs[c.start * n_in:c.stop * n_in], step_deg, range_deg, sample_size,
+                                       smooth, bruteforce, postprocessing)
+                st = ctx.process_stats()
+                with lock:
+                    for key, v in st.items():
+                        stats[key] = stats.get(key, 0) + v
+        except Exception as e:  # surfaced on the caller's thread
+            errs.append(e)
+        finally:
+            ctx.close()
+
+    threads = [threading.Thread(target=run) for _ in range(min(workers, len(chunks)))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    outs = [b for r in res for b in r[0]]
+    logs = [l for r in res for l in r[1]]
+    anom = [a for r in res for a in r[2]]
+    assert len(outs) == n_cases * n_out and len(logs) == n_cases * n_in
+    return outs, logs, anom, stats
+
+
 def make_exchange(group=None):
     """The callback mmrs_ctx_set_shard needs: an in-place all-reduce(SUM) of an int64 numpy array across the
     ranks of `group` (NCCL on GPUs, gloo on CPU). Every rank must call it the same number of times."""

@@ -73,16 +73,23 @@ if P5 > 0:
             blobs.append(nat.geometry_from_arrays(a, rp, diastole=dia, label=f"pt{p}_{k}"))
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    outs, logs, _ = nat.process_cases(ctx, 4, blobs, 0.05, 90.0, 500, False, True)
+    if os.environ.get("MMRS_COHORT_PIPELINE", "1") != "0":   # host work of chunk k+1 behind the sweeps of chunk k
+        outs, logs, _, st5 = _dist.process_cases_pipelined(local, 4, blobs, 0.05, 90.0, 500, False, True, chunk_cases=4,
+                                                           workers=2)
+    else:
+        outs, logs, _ = nat.process_cases(ctx, 4, blobs, 0.05, 90.0, 500, False, True)
+        st5 = ctx.process_stats()
     rows_ = [np.column_stack([np.full(len(l), float(i)), l]) for i, l in enumerate(logs)]
     allrows = _dist.all_gather_rows(np.concatenate(rows_) if rows_ else np.zeros((0, 8)))
     torch.cuda.synchronize(); dist.barrier()
     wall = time.perf_counter() - t0
-    st = ctx.process_stats()
+    st = st5
     tot = torch.tensor([st["evals"]], dtype=torch.float64, device="cuda")
     dist.all_reduce(tot)
     out["config5"] = dict(patients=P5, wall_s=wall, evals_total=float(tot.item()), evals_per_s=float(tot.item()) / wall,
-                          gathered_log_rows=int(len(allrows)), rank0_stats=st)
+                          gathered_log_rows=int(len(allrows)), rank0_stats=st,
+                          pipelined=os.environ.get("MMRS_COHORT_PIPELINE", "1") != "0",
+                          logs_sha=__import__("hashlib").sha256(np.ascontiguousarray(allrows).tobytes()).hexdigest())
     if rank == 0:
         print("config5", json.dumps(out["config5"]), flush=True)
 

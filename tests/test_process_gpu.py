@@ -267,3 +267,23 @@ def test_reference_defaults_write_obj(tmp_path):
     g, _ = mm.from_file_single(str(rest), write_obj=True, output_path=str(tmp_path / "single"))
     assert sorted(os.listdir(tmp_path / "single")) == sorted(
         f"{t}_ivus_rest.{e}" for t in ("lumen", "catheter", "wall") for e in ("obj", "mtl"))
+
+
+def test_pipelined_cohort_is_identical_to_one_call():
+    """_dist.process_cases_pipelined (two host threads, two contexts / streams on one GPU, chunks of cases) returns
+    exactly what one mmrs_process_cases call over the whole cohort returns."""
+    from multimodars import _dist
+    pack = gio.inputs()
+    blobs = []
+    for _ in range(5):   # five identical-input cases are still five independent cases
+        blobs += oracle_blobs(pack, FULL[:2])
+    ctx = mm.get_context()
+    want_out, want_logs, want_an = nat.process_cases(ctx, 2, blobs, 0.5, 90.0, 500, True, False, True)
+    got_out, got_logs, got_an, stats = _dist.process_cases_pipelined(0, 2, blobs, 0.5, 90.0, 500, True, False, True,
+                                                                   chunk_cases=2, workers=2)
+    assert len(got_out) == len(want_out) == 10 and got_an == want_an
+    for a, b in zip(got_out, want_out):
+        assert np.array_equal(a, b)
+    for a, b in zip(got_logs, want_logs):
+        assert np.array_equal(a, b)
+    assert stats["units"] == 5 * (ctx.process_stats()["units"] // 5)
