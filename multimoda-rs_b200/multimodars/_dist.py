@@ -103,7 +103,7 @@ def process_cases_sharded(mode, blobs, step_deg, range_deg, sample_size, smooth,
 
 
 def process_cases_pipelined(device, mode, blobs, step_deg, range_deg, sample_size, smooth, bruteforce,
-                            postprocessing=False, chunk_cases=8, workers=2):
+                            postprocessing=False, chunk_cases=1, workers=4):
     """A cohort on ONE GPU with the host work hidden behind the device work: the cases are cut into chunks and
     `workers` host threads, each with its own context (its own CUDA stream and device workspaces), pull chunks from
     a queue and run mmrs_process_cases on them. While one thread's sweep kernels occupy the GPU, the other decodes

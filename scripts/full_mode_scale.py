@@ -74,8 +74,9 @@ if P5 > 0:
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     if os.environ.get("MMRS_COHORT_PIPELINE", "1") != "0":   # host work of chunk k+1 behind the sweeps of chunk k
-        outs, logs, _, st5 = _dist.process_cases_pipelined(local, 4, blobs, 0.05, 90.0, 500, False, True, chunk_cases=4,
-                                                           workers=2)
+        outs, logs, _, st5 = _dist.process_cases_pipelined(local, 4, blobs, 0.05, 90.0, 500, False, True,
+                                                           chunk_cases=int(os.environ.get("MMRS_COHORT_CHUNK", "1")),
+                                                           workers=int(os.environ.get("MMRS_COHORT_WORKERS", "4")))
     else:
         outs, logs, _ = nat.process_cases(ctx, 4, blobs, 0.05, 90.0, 500, False, True)
         st5 = ctx.process_stats()
