@@ -127,6 +127,15 @@ typedef struct mmrs_sweep_opts {
      * is slower than the dense FP32 sweep, so it is an opt-in experimental tier.   */
     int32_t prefilter;
     double prefilter_abs; /* <= 0 selects 4e-6 (about 7x the largest error measured) */
+    /* Exact lower-bound pruning (opt-in): before the FP32 sweep every candidate gets the lower bound
+     *   LB = max( max_{a in A'} min_{b in B} |a-b| , max_{b in B'} min_{a in A} |a-b| ) <= Hausdorff(A, B)
+     * over 64 (128 for >= 1024 points) strided points A', B' of the two sets; the candidate with the smallest
+     * bound is scored exactly, and only candidates whose bound does not exceed that distance (plus twice the
+     * FP32 window) are scored by the FP32 kernel — the others cannot be the arg-min. Selection, angle and f64
+     * distance are identical to the dense path; mmrs_sweep_get_dist32 then returns the BOUND for pruned
+     * candidates. > 0 on, < 0 off, 0 = the context default (mmrs_ctx_set_prune; off unless set). Applies when
+     * every unit has >= 128 points per set and the batch averages >= 256 candidates per unit.        */
+    int32_t prune;
 } mmrs_sweep_opts;
 
 #define MMRS_FLAG_DEGENERATE 1 /* grid degenerate: best_angle = fallback, nothing evaluated */
@@ -175,7 +184,12 @@ int mmrs_sweep_get_shortlist(mmrs_ctx* ctx, int64_t unit, int64_t* idx_out, doub
  * [2] f64 recheck + select, [3] whole run. Kernel launches of the last run.   */
 int mmrs_last_timings(mmrs_ctx* ctx, float ms_out[4], int32_t* launches_out);
 
-/* Tensor-core prefilter of the last run: [0] 1 if it ran, [1] K1t device time in ms, [2] tier-1 window +
+/* Context-wide default of mmrs_sweep_opts.prune (used by mmrs_process_cases and every sweep whose opts leave it 0). */
+int mmrs_ctx_set_prune(mmrs_ctx* ctx, int32_t on);
+
+/* For a pruned run (out[0] == 2): [1] bound passes + first exact score in ms, [2] survivor selection + exact FP32
+ * scoring in ms, [3] candidates scored exactly (survivors, all units).
+ * Tensor-core prefilter of the last run: [0] 1 if it ran, [1] K1t device time in ms, [2] tier-1 window +
  * tier-2 exact FP32 re-scoring time in ms, [3] candidates re-scored in FP32 (all units), [4] largest observed
  * |d_tc^2 - d_fp32^2| / Rmax^2 over them, [5] the window prefilter_abs in force.                              */
 int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]);

@@ -95,6 +95,17 @@ struct mmrs_ctx {
     std::vector<mmrs::WorkItem> h_work_tc, h_work_list;
     mmrs::DevBuf d_work_tc, d_work_list, d_key_tc, d_l1_items, d_l1_count, d_l1_base, d_l1_n;
 
+    // exact lower-bound pruning tier (k_lb, sweep_kernels.cuh)
+    int opt_prune = 0;          // mmrs_sweep_opts.prune / mmrs_ctx_set_prune: 0 off, 1 on where the batch qualifies
+    int ctx_prune = 0;          // context-wide default used when the opts do not say
+    bool lb_shape_ok = false;   // every live unit has >= 128 points per set (decided at upload)
+    bool use_prune = false, prune_ran = false;
+    int lb_R = 64;              // rows of a lower-bound unit (32 * TA_lb)
+    size_t smem_lb = 0;
+    std::vector<mmrs::UnitDesc> h_units_lb;   // [2 U]: pass A (test rows) then pass B (reference rows)
+    std::vector<mmrs::WorkItem> h_work_lb;
+    mmrs::DevBuf d_units_lb, d_lay_lb, d_work_lb;
+
     // unit sharding across ranks (mmrs_ctx_set_shard)
     int shard_rank = 0, shard_world = 1;
     mmrs_exchange_fn exchange = nullptr;

@@ -172,7 +172,8 @@ extern "C" void mmrs_ctx_destroy(mmrs_ctx* ctx) {
 void mmrs_ctx::free_all() {
     for (DevBuf* b : {&d_test, &d_ref, &d_units, &d_work, &d_lay, &d_cs64, &d_cs32, &d_zero, &d_dist32, &d_key,
                       &d_rmax, &d_sl_base, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp, &d_work_tc,
-                      &d_work_list, &d_key_tc, &d_l1_items, &d_l1_count, &d_l1_base, &d_l1_n}) {
+                      &d_work_list, &d_key_tc, &d_l1_items, &d_l1_count, &d_l1_base, &d_l1_n, &d_units_lb, &d_lay_lb,
+                      &d_work_lb}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr;
         b->cap = 0;
@@ -322,6 +323,41 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
         ctx->tc_shape_ok = ok && smem_tc > 0 && smem_tc <= 227 * 1024;
         ctx->smem_tc = smem_tc;
     }
+    {   // lower-bound pruning tier: R strided rows of one set against all points of the other, both ways
+        bool ok = U > 0;
+        int biggest = 0;
+        for (auto& d : units) {
+            if (d.n <= 0 || d.m <= 0) continue;
+            if (d.n < 128 || d.m < 128) ok = false;
+            biggest = std::max(biggest, std::max(d.n, d.m));
+        }
+        ctx->lb_R = biggest >= 1024 ? 128 : 64;
+        ctx->lb_shape_ok = ok && biggest > 0;
+        ctx->h_units_lb.assign(2 * (size_t)U, UnitDesc{});
+        long long off = 0;
+        size_t smem_lb = 0;
+        if (ctx->lb_shape_ok)
+            for (int pass = 0; pass < 2; ++pass)
+                for (int64_t u = 0; u < U; ++u) {
+                    const UnitDesc& d = units[u];
+                    UnitDesc& l = ctx->h_units_lb[u + pass * U];
+                    l = d;
+                    l.n = ctx->lb_R;
+                    l.m = pass == 0 ? d.m : d.n;
+                    l.n_chunks = 1;
+                    l.m_pairs = (l.m + 1) / 2;
+                    l.lay_off = off;
+                    if (d.n > 0 && d.m > 0) {
+                        off += ctx->lb_R / 2 + l.m_pairs;
+                        smem_lb = std::max(smem_lb, (size_t)(ctx->lb_R / 2 + l.m_pairs) * 16);
+                    }
+                }
+        ctx->smem_lb = 16 + smem_lb;
+        if (ctx->lb_shape_ok) {
+            ENSURE(ctx->d_units_lb, 2 * U * sizeof(UnitDesc));
+            ENSURE(ctx->d_lay_lb, (size_t)off * 16);
+        }
+    }
     size_t col_bytes = 0;
     if (multi) {
         int max_pairs = 0;
@@ -361,6 +397,15 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
                                        TA);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->upload_launches = 1;
+    if (ctx->lb_shape_ok) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units_lb.p, ctx->h_units_lb.data(), 2 * U * sizeof(UnitDesc),
+                                      cudaMemcpyHostToDevice, s));
+        k_prep_lb<<<(unsigned)U, 256, 0, s>>>((const UnitDesc*)ctx->d_units.p, (const UnitDesc*)ctx->d_units_lb.p, (int)U,
+                                              (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
+                                              (float4*)ctx->d_lay_lb.p, ctx->lb_R);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->upload_launches += 1;
+    }
     return MMRS_OK;
 }
 
@@ -464,6 +509,50 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
             ENSURE(ctx->d_l1_n, 16);
         }
     }
+    // Lower-bound pruning: worth it when a unit carries enough candidates for the two extra passes to pay off.
+    {
+        long long live_units = 0;
+        for (auto& d : units)
+            if (!d.flags) ++live_units;
+        const char* env = std::getenv("MMRS_PRUNE");
+        int mode = ctx->opt_prune;
+        if (env && *env) mode = (*env == '0') ? 0 : 1;
+        ctx->use_prune = mode == 1 && !ctx->use_tc && ctx->lb_shape_ok && live_units > 0 && live >= 256 * live_units;
+        ctx->h_work_lb.clear();
+        if (ctx->use_prune) {
+            for (int pass = 0; pass < 2; ++pass)
+                for (int64_t u = 0; u < U; ++u) {
+                    UnitDesc& l = ctx->h_units_lb[u + pass * U];
+                    const UnitDesc& d = units[u];
+                    l.cand_off = d.cand_off, l.n_cand = d.n_cand, l.dist_off = d.dist_off;
+                    l.flags = d.flags | (pass == 1 ? kLbNegSin : 0);
+                }
+            const long long slots = (long long)ctx->n_sm * 2 * 4;
+            long long per_warp = (2 * live + slots * kWarpsPerCta - 1) / (slots * kWarpsPerCta);
+            per_warp = std::max<long long>(1, std::min<long long>(per_warp, 32));
+            const int tile = (int)per_warp * kWarpsPerCta;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int64_t u = 0; u < U; ++u) {
+                    const UnitDesc& d = units[u];
+                    if (d.flags) continue;
+                    for (int c0 = 0; c0 < d.n_cand; c0 += tile)
+                        ctx->h_work_lb.push_back(WorkItem{(int)(u + pass * U), c0, std::min(tile, d.n_cand - c0), 0});
+                }
+            // tier-2 list work: (unit, g, G); G grows when there are few units so that the survivors spread over the SMs
+            ctx->h_work_list.clear();
+            const int G = (int)std::max<long long>(4, std::min<long long>(64, (16LL * ctx->n_sm + live_units - 1) / live_units));
+            for (int64_t u = 0; u < U; ++u)
+                if (!units[u].flags)
+                    for (int g = 0; g < G; ++g) ctx->h_work_list.push_back(WorkItem{(int)u, g, G, 0});
+            ctx->l1_cap = (unsigned)std::min<long long>(std::max<long long>(dist_off, 1), 0x7fffffffLL);
+            ENSURE(ctx->d_work_lb, ctx->h_work_lb.size() * sizeof(WorkItem));
+            ENSURE(ctx->d_work_list, ctx->h_work_list.size() * sizeof(WorkItem));
+            ENSURE(ctx->d_l1_items, (size_t)ctx->l1_cap * 8);
+            ENSURE(ctx->d_l1_count, U * 4);
+            ENSURE(ctx->d_l1_base, U * 4);
+            ENSURE(ctx->d_l1_n, 16);
+        }
+    }
     ENSURE(ctx->d_work, ctx->h_work.size() * sizeof(WorkItem));
     ENSURE(ctx->d_cs64, (size_t)n_cs * 16);
     ENSURE(ctx->d_cs32, (size_t)n_cs * 8);
@@ -479,6 +568,14 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
     if (!ctx->h_work.empty())
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work.p, ctx->h_work.data(), ctx->h_work.size() * sizeof(WorkItem),
                                       cudaMemcpyHostToDevice, s));
+    if (ctx->use_prune && !ctx->h_work_lb.empty()) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units_lb.p, ctx->h_units_lb.data(), 2 * U * sizeof(UnitDesc),
+                                      cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_lb.p, ctx->h_work_lb.data(), ctx->h_work_lb.size() * sizeof(WorkItem),
+                                      cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_list.p, ctx->h_work_list.data(),
+                                      ctx->h_work_list.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, s));
+    }
     if (ctx->use_tc && !ctx->h_work_tc.empty()) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_tc.p, ctx->h_work_tc.data(), ctx->h_work_tc.size() * sizeof(WorkItem),
                                       cudaMemcpyHostToDevice, s));
@@ -511,8 +608,10 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
     ctx->opt_abs = (o && o->shortlist_abs > 0) ? o->shortlist_abs : 2e-6;
     ctx->cap = (o && o->shortlist_cap > 0) ? o->shortlist_cap : 64;
     ctx->tie_margin = (o && o->tie_margin > 0) ? o->tie_margin : 0.0;
+    ctx->opt_prune = (o && o->prune != 0) ? (o->prune > 0 ? 1 : 0) : ctx->ctx_prune;
     ctx->opt_prefilter = o ? o->prefilter : 0;
     if (o && o->keep_dist32 && ctx->opt_prefilter == 0) ctx->opt_prefilter = 1;  // exact FP32 for EVERY candidate
+    if (o && o->keep_dist32) ctx->opt_prune = 0;
     ctx->tc_abs = (o && o->prefilter_abs > 0) ? o->prefilter_abs : 4e-6;
     if (ctx->opt_prefilter < 0 || ctx->opt_prefilter > 2)
         return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: prefilter must be 0 (auto), 1 (off) or 2 (required)");
@@ -605,8 +704,57 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_nitems.p, 0, 16, s));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
     const bool tc = ctx->use_tc && !ctx->h_work_tc.empty();
+    const bool prune = !tc && ctx->use_prune && !ctx->h_work_lb.empty();
     ctx->tc_ran = tc;
-    if (tc) {
+    ctx->prune_ran = prune;
+    if (prune) {
+        // tier 0: lower bounds of every candidate (rows-only passes over R strided points of each set)
+        const UnitDesc* lbu = (const UnitDesc*)ctx->d_units_lb.p;
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dist32.p, 0, (size_t)ctx->total_cands * 4, s));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[0], s));
+        if (ctx->lb_R == 128) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_lb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_lb));
+            k_lb<4><<<(unsigned)ctx->h_work_lb.size(), kThreads, ctx->smem_lb, s>>>(
+                lbu, (const WorkItem*)ctx->d_work_lb.p, (const float4*)ctx->d_lay_lb.p, (const float2*)ctx->d_cs32.p,
+                (float*)ctx->d_dist32.p);
+        } else {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_lb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_lb));
+            k_lb<2><<<(unsigned)ctx->h_work_lb.size(), kThreads, ctx->smem_lb, s>>>(
+                lbu, (const WorkItem*)ctx->d_work_lb.p, (const float4*)ctx->d_lay_lb.p, (const float2*)ctx->d_cs32.p,
+                (float*)ctx->d_dist32.p);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        // the candidate with the smallest bound is scored first: its exact FP32 distance bounds the minimum from above
+        k_lb_argmin<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p, (int*)ctx->d_l1_count.p,
+                                                (unsigned*)ctx->d_l1_base.p, (int2*)ctx->d_l1_items.p);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ListArgs la;
+        la.items = (const int2*)ctx->d_l1_items.p;
+        la.count = (const int*)ctx->d_l1_count.p;
+        la.base = (const unsigned*)ctx->d_l1_base.p;
+        la.rmax = (const unsigned*)ctx->d_rmax.p;
+        la.diag = (unsigned*)ctx->d_l1_n.p + 2;
+        auto rescore = [&]() {
+            return launch_sweep(ctx->TA, ctx->multi, (int)ctx->h_work_list.size(), ctx->smem_sweep, s, units,
+                                (const WorkItem*)ctx->d_work_list.p, (const float4*)ctx->d_lay.p,
+                                (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p, &la);
+        };
+        if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[1], s));
+        // survivors: bound <= that distance + twice the FP32 window; everything else cannot be the arg-min
+        k_shortlist<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p,
+                                                (const unsigned long long*)ctx->d_key.p, (const unsigned*)ctx->d_rmax.p,
+                                                4e-6f, 4e-6f, ctx->l1_cap, (int*)ctx->d_l1_count.p,
+                                                (unsigned*)ctx->d_l1_base.p, (int2*)ctx->d_l1_items.p,
+                                                (unsigned*)ctx->d_l1_n.p, 0, nullptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[2], s));
+        ctx->launches += 5;
+    } else if (tc) {
         // tier 0: every candidate on the tensor cores (bf16x3, FP32 accumulate) -> approximate dist32 + per-unit minimum
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_key_tc.p, 0xff, U * 8, s));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
@@ -915,7 +1063,7 @@ extern "C" int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]) {
     if (!ctx->ran) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_prefilter_info: nothing has been run");
     for (int i = 0; i < 6; ++i) out[i] = 0.0;
     out[5] = ctx->tc_abs;
-    if (!ctx->tc_ran || ctx->n_units == 0) return MMRS_OK;
+    if ((!ctx->tc_ran && !ctx->prune_ran) || ctx->n_units == 0) return MMRS_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
     float a = 0.f, b = 0.f;
@@ -925,10 +1073,16 @@ extern "C" int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]) {
     CUDA_TRY(ctx, cudaMemcpy(h, ctx->d_l1_n.p, 8, cudaMemcpyDeviceToHost));
     float err;
     std::memcpy(&err, &h[1], 4);
-    out[0] = 1.0;
+    out[0] = ctx->prune_ran ? 2.0 : 1.0;
     out[1] = a;
     out[2] = b;
     out[3] = (double)h[0];
     out[4] = (double)err;
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_ctx_set_prune(mmrs_ctx* ctx, int32_t on) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_ctx_set_prune: ctx is NULL");
+    ctx->ctx_prune = on ? 1 : 0;
     return MMRS_OK;
 }

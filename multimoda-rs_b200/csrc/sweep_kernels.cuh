@@ -300,6 +300,149 @@ __global__ void __launch_bounds__(kThreads, 2)
 }
 
 // =============================================================================
+// K1p: exact lower-bound pruning tier (opt-in, mmrs_sweep_opts.prune). For ANY subsets A' of the test points and B'
+// of the reference points,
+//     H(A, B) = max( max_{a in A} min_{b in B} |a - b| , max_{b in B} min_{a in A} |a - b| )
+//            >= max( max_{a in A'} min_{b in B} |a - b| , max_{b in B'} min_{a in A} |a - b| ) =: LB,
+// because a maximum over fewer rows can only be smaller while every row minimum still runs over ALL points of the
+// other set. LB costs (|A'| M + |B'| N) pair distances instead of N M. A candidate whose LB exceeds the exact distance
+// of any evaluated candidate (plus the FP32 window) cannot be the arg-min and is never scored; every other candidate is
+// scored by the exact FP32 kernel (k_sweep LIST) and continues to K2/K3/K4 unchanged, so the selected candidate, its
+// angle and its f64 distance are identical to the dense path's.
+//   k_prep_lb   per unit two staging images: rows = R strided test points / columns = all reference points, and
+//               rows = R strided reference points / columns = all test points (rotated by -theta instead).
+//   k_lb<TA>    rows-only sweep of those images: row minima + max, no column minima, no REDUX per column;
+//               result max-combined into dist32 with atomicMax on the (non-negative) float bits.
+//   k_lb_argmin the candidate with the smallest LB of each unit (scored first: its exact distance is the bound).
+// =============================================================================
+constexpr int kLbNegSin = 0x100;  // UnitDesc.flags of a lower-bound unit: rotate its rows by -theta
+
+__global__ void k_prep_lb(const UnitDesc* __restrict__ units, const UnitDesc* __restrict__ lb_units, int n_units,
+                          const double* __restrict__ test_xy, const double* __restrict__ ref_xy,
+                          float4* __restrict__ lay, int R) {
+    const int u = blockIdx.x;
+    const UnitDesc ud = units[u];
+    if (ud.n <= 0 || ud.m <= 0) return;
+    for (int pass = 0; pass < 2; ++pass) {
+        const UnitDesc lb = lb_units[u + pass * n_units];
+        const double* rows = pass == 0 ? test_xy + 2 * ud.test_off : ref_xy + 2 * ud.ref_off;
+        const double* cols = pass == 0 ? ref_xy + 2 * ud.ref_off : test_xy + 2 * ud.test_off;
+        const int nr = pass == 0 ? ud.n : ud.m, nc = pass == 0 ? ud.m : ud.n;
+        float4* A = lay + lb.lay_off;
+        float4* B = A + (R / 2);
+        auto pick = [&](int r) { return nr <= R ? min(r, nr - 1) : (int)(((long long)r * nr) / R); };
+        for (int e = threadIdx.x; e < R / 2; e += blockDim.x) {
+            const int l = e & 31, k = e >> 5;
+            const int i0 = pick(2 * k * 32 + l), i1 = pick(2 * k * 32 + l + 32);
+            A[e] = make_float4((float)(rows[2 * i0] - ud.cx), (float)(rows[2 * i1] - ud.cx), (float)(rows[2 * i0 + 1] - ud.cy),
+                               (float)(rows[2 * i1 + 1] - ud.cy));
+        }
+        for (int j = threadIdx.x; j < lb.m_pairs; j += blockDim.x) {
+            const int j0 = min(2 * j, nc - 1), j1 = min(2 * j + 1, nc - 1);
+            B[j] = make_float4((float)(cols[2 * j0] - ud.cx), (float)(cols[2 * j0 + 1] - ud.cy), (float)(cols[2 * j1] - ud.cx),
+                               (float)(cols[2 * j1 + 1] - ud.cy));
+        }
+    }
+}
+
+template <int TA>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_lb(const UnitDesc* __restrict__ lb_units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
+         const float2* __restrict__ cs32, float* __restrict__ dist32) {
+    constexpr int H = TA / 2;
+    static_assert(TA == 2 || TA == 4, "lower-bound register tile");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float4* sA = reinterpret_cast<float4*>(smem_raw + 16);
+    const WorkItem w = work[blockIdx.x];
+    const UnitDesc ud = lb_units[w.unit];
+    const int a_elems = H * 32, b_elems = ud.m_pairs;
+    float4* sB = sA + a_elems;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const uint32_t bytes = (uint32_t)(a_elems + b_elems) * 16u;
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(sA, lay + ud.lay_off, bytes, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const float INF = __int_as_float(0x7f800000);
+    const float sgn = (ud.flags & kLbNegSin) ? -1.f : 1.f;
+    unsigned* out = reinterpret_cast<unsigned*>(dist32 + ud.dist_off);
+    for (int ci = wid; ci < w.count; ci += kWarpsPerCta) {
+        const int c = w.begin + ci;
+        float2 cs = __ldg(&cs32[ud.cand_off + c]);
+        cs.y *= sgn;
+        const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
+        uint64_t AX[H], AY[H];
+        float row[TA];
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const float4 a = sA[k * 32 + lane];
+            const uint64_t X2 = pk(a.x, a.y), Y2 = pk(a.z, a.w);
+            AX[k] = fma2(Y2, NS2, mul2(X2, C2));
+            AY[k] = fma2(X2, S2, mul2(Y2, C2));
+            row[2 * k] = INF;
+            row[2 * k + 1] = INF;
+        }
+#pragma unroll 4
+        for (int j = 0; j < ud.m_pairs; ++j) {
+            const float4 B = sB[j];
+            const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y), bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const uint64_t dx0 = sub2(AX[k], bx0), dy0 = sub2(AY[k], by0);
+                const uint64_t dx1 = sub2(AX[k], bx1), dy1 = sub2(AY[k], by1);
+                const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));
+                const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));
+                float d00, d10, d01, d11;
+                upk(d0, d00, d10);
+                upk(d1, d01, d11);
+                row[2 * k] = min3(row[2 * k], d00, d01);
+                row[2 * k + 1] = min3(row[2 * k + 1], d10, d11);
+            }
+        }
+        float rm = row[0];
+#pragma unroll
+        for (int k = 1; k < TA; ++k) rm = fmaxf(rm, row[k]);
+        const unsigned h2 = __reduce_max_sync(0xffffffffu, __float_as_uint(rm));
+        if (lane == 0) atomicMax(&out[c], __float_as_uint(sqrtf(__uint_as_float(h2))));
+    }
+}
+
+// One CTA per unit: the candidate with the smallest lower bound (ties -> lowest index) becomes the unit's one-item list.
+__global__ void k_lb_argmin(const UnitDesc* __restrict__ units, const float* __restrict__ dist32, int* __restrict__ l_count,
+                            unsigned* __restrict__ l_base, int2* __restrict__ l_items) {
+    __shared__ unsigned long long s_best;
+    const int u = blockIdx.x;
+    const UnitDesc ud = units[u];
+    if (threadIdx.x == 0) s_best = ~0ull;
+    __syncthreads();
+    if (ud.flags || ud.n_cand <= 0) {
+        if (threadIdx.x == 0) l_count[u] = 0, l_base[u] = (unsigned)u;
+        return;
+    }
+    unsigned long long best = ~0ull;
+    const float* d = dist32 + ud.dist_off;
+    for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x) {
+        const unsigned long long k = ((unsigned long long)__float_as_uint(d[c]) << 32) | (unsigned)c;
+        best = best < k ? best : k;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = best < other ? best : other;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_best, best);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        l_items[u] = make_int2(u, (int)(s_best & 0xffffffffu));
+        l_base[u] = (unsigned)u;
+        l_count[u] = 1;
+    }
+}
+
+// =============================================================================
 // K2: shortlist = candidates whose FP32 distance lies inside the FP32 error window above the
 // minimum. Two scans of the unit's FP32 row (L2-resident): count, reserve a contiguous range of
 // the global item pool with one atomicAdd, then write (unit, candidate) items. A unit may take

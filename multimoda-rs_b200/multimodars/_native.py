@@ -39,7 +39,7 @@ class SweepBatch(C.Structure):
 class SweepOpts(C.Structure):
     _fields_ = [("shortlist_rel", C.c_double), ("shortlist_abs", C.c_double), ("shortlist_cap", C.c_int32),
                 ("tie_margin", C.c_double), ("keep_dist32", C.c_int32), ("prefilter", C.c_int32),
-                ("prefilter_abs", C.c_double)]
+                ("prefilter_abs", C.c_double), ("prune", C.c_int32)]
 
 
 class UnitResult(C.Structure):
@@ -75,7 +75,7 @@ EXPORTS = [
     "mmrs_sweep_download", "mmrs_sweep_plan", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
     "mmrs_process_cases", "mmrs_process_stats", "mmrs_ctx_set_shard", "mmrs_export_pair", "mmrs_export_single",
-    "mmrs_align_centerline", "mmrs_sweep_prefilter_info",
+    "mmrs_align_centerline", "mmrs_sweep_prefilter_info", "mmrs_ctx_set_prune",
 ]
 
 _lib = None
@@ -191,10 +191,16 @@ class Context:
 
     @staticmethod
     def _opts(shortlist_rel=0.0, shortlist_abs=0.0, shortlist_cap=0, tie_margin=0.0, keep_dist32=False, prefilter=0,
-              prefilter_abs=0.0):
-        """prefilter: 0 auto, 1 off (dense FP32 sweep), 2 required (tensor-core tier, mmrs_b200.h)."""
+              prefilter_abs=0.0, prune=0):
+        """prefilter: 0 auto, 1 off (dense FP32 sweep), 2 required (tensor-core tier, mmrs_b200.h).
+        prune: > 0 exact lower-bound pruning on, < 0 off, 0 the context default (set_prune)."""
         return SweepOpts(shortlist_rel, shortlist_abs, shortlist_cap, tie_margin, int(keep_dist32), int(prefilter),
-                         float(prefilter_abs))
+                         float(prefilter_abs), int(prune))
+
+    def set_prune(self, on: bool):
+        """mmrs_ctx_set_prune: context-wide default for exact lower-bound pruning (mmrs_process_cases uses it)."""
+        lib().mmrs_ctx_set_prune.argtypes = [C.c_void_p, C.c_int32]
+        self._check(lib().mmrs_ctx_set_prune(self._p, int(bool(on))))
 
     def sweep_batched(self, test_xy, test_off, ref_xy, ref_off, centre_xy, grids, grid_of_unit=None, mode=0, **opts):
         """Host arrays in, structured result array (RESULT_DTYPE) out."""
@@ -255,7 +261,8 @@ class Context:
         o = (C.c_double * 6)()
         lib().mmrs_sweep_prefilter_info.argtypes = [C.c_void_p, c_dp]
         self._check(lib().mmrs_sweep_prefilter_info(self._p, o))
-        return dict(ran=bool(o[0]), tc_ms=o[1], rescore_ms=o[2], rescored=int(o[3]), max_err=o[4], window=o[5])
+        return dict(ran=bool(o[0]), kind={0: None, 1: "tensor-core prefilter", 2: "lower-bound pruning"}[int(o[0])],
+                    tc_ms=o[1], rescore_ms=o[2], rescored=int(o[3]), max_err=o[4], window=o[5])
 
     def eval_exact(self, test_xy, ref_xy, centre, mode, angles):
         t, r, a = _f64(test_xy).reshape(-1, 2), _f64(ref_xy).reshape(-1, 2), _f64(angles).reshape(-1)

@@ -16,15 +16,22 @@ def run(ctx, U, N, step, rng_deg, reps=3):
     off = np.arange(U + 1) * N
     g = nat.make_grid(step, rng_deg)
     out = {}
-    for name, pf in (("dense", 1), ("tc", 2)):
-        ctx.sweep_upload(t, off, r, off, np.full((U, 2), 4.5), [g], mode=0, prefilter=pf)
+    for name, pf, prune in (("dense", 1, -1), ("tc", 2, -1), ("prune", 1, 1)):
+        if name == "tc" and "--no-tc" in sys.argv:
+            continue
+        ctx.sweep_upload(t, off, r, off, np.full((U, 2), 4.5), [g], mode=0, prefilter=pf, prune=prune)
         best = None
         for _ in range(reps):
             ctx.sweep_run(); res = ctx.sweep_download(); tm = ctx.timings()
             best = tm if best is None or tm["total_ms"] < best["total_ms"] else best
         out[name] = (best, res, ctx.prefilter_info())
     evals = U * g.n_cand
-    d, tcr = out["dense"], out["tc"]
+    d, tcr = out["dense"], out.get("tc", out["prune"])
+    p = out["prune"]
+    same_p = bool((d[1]["best_idx"] == p[1]["best_idx"]).all() and (d[1]["best_dist"] == p[1]["best_dist"]).all())
+    print(f"U={U} N={N} C={g.n_cand}: dense {d[0]['total_ms']:.2f} ms | pruned total {p[0]['total_ms']:.2f} ms "
+          f"(bounds {p[2]['tc_ms']:.2f} ms, survivors {p[2]['rescore_ms']:.2f} ms, {p[2]['rescored']} scored = "
+          f"{p[2]['rescored'] / (U * g.n_cand):.3f} of all) speed-up {d[0]['total_ms'] / p[0]['total_ms']:.2f}x identical={same_p}", flush=True)
     same = bool((d[1]["best_idx"] == tcr[1]["best_idx"]).all() and (d[1]["best_dist"] == tcr[1]["best_dist"]).all())
     info = tcr[2]
     print(f"U={U} N={N} C={g.n_cand}: dense {d[0]['total_ms']:.2f} ms ({evals / d[0]['total_ms'] * 1e3:.4g} evals/s) | "
