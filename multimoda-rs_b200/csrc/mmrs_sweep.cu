@@ -203,10 +203,11 @@ static int ensure(mmrs_ctx* ctx, DevBuf& b, size_t bytes) {
     } while (0)
 
 // ---- kernel dispatch over TA ----------------------------------------------------------
-struct ListArgs {  // tier-2 (LIST) arguments of k_sweep; all null for the dense sweep
+struct ListArgs {  // LIST arguments of k_sweep; all null for the dense sweep
     const int2* items = nullptr;
-    const int* count = nullptr;
-    const unsigned* base = nullptr;
+    const unsigned* n_items = nullptr;  // device counter: items in the global list
+    unsigned cap = 0;                   // capacity of the list (upper bound of *n_items)
+    int chunk = 64;                     // list positions per CTA
     const unsigned* rmax = nullptr;
     unsigned* diag = nullptr;
 };
@@ -215,8 +216,8 @@ static void launch_sweep_k(int grid, size_t smem, cudaStream_t s, const UnitDesc
                            const float4* lay, const float2* cs32, float* dist32, unsigned long long* key,
                            const ListArgs& l) {
     cudaFuncSetAttribute(k_sweep<TA, MULTI, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sweep<TA, MULTI, LIST><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key, l.items, l.count, l.base,
-                                                          l.rmax, l.diag);
+    k_sweep<TA, MULTI, LIST><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key, l.items, l.n_items, l.cap,
+                                                          l.chunk, l.rmax, l.diag);
 }
 template <int TA>
 static void launch_sweep_ta(bool multi, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
@@ -402,7 +403,8 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
                                       cudaMemcpyHostToDevice, s));
         k_prep_lb<<<(unsigned)U, 256, 0, s>>>((const UnitDesc*)ctx->d_units.p, (const UnitDesc*)ctx->d_units_lb.p, (int)U,
                                               (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
-                                              (float4*)ctx->d_lay_lb.p, ctx->lb_R);
+                                              (float4*)ctx->d_lay_lb.p, ctx->lb_R,
+                                              std::getenv("MMRS_LB_ROWS") ? std::max(8, std::min(ctx->lb_R, std::atoi(std::getenv("MMRS_LB_ROWS")))) : ctx->lb_R);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->upload_launches += 1;
     }
@@ -731,14 +733,16 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         CUDA_TRY(ctx, cudaGetLastError());
         ListArgs la;
         la.items = (const int2*)ctx->d_l1_items.p;
-        la.count = (const int*)ctx->d_l1_count.p;
-        la.base = (const unsigned*)ctx->d_l1_base.p;
+        la.n_items = nullptr;  // k_lb_argmin's list: exactly one item per unit
+        la.cap = (unsigned)U;
+        la.chunk = 1;
         la.rmax = (const unsigned*)ctx->d_rmax.p;
         la.diag = (unsigned*)ctx->d_l1_n.p + 2;
         auto rescore = [&]() {
-            return launch_sweep(ctx->TA, ctx->multi, (int)ctx->h_work_list.size(), ctx->smem_sweep, s, units,
-                                (const WorkItem*)ctx->d_work_list.p, (const float4*)ctx->d_lay.p,
-                                (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p, &la);
+            const long long grid = ((long long)la.cap + la.chunk - 1) / la.chunk;
+            return launch_sweep(ctx->TA, ctx->multi, (int)grid, ctx->smem_sweep, s, units, nullptr,
+                                (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p,
+                                (unsigned long long*)ctx->d_key.p, &la);
         };
         if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
         CUDA_TRY(ctx, cudaGetLastError());
@@ -750,6 +754,9 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
                                                 (unsigned*)ctx->d_l1_base.p, (int2*)ctx->d_l1_items.p,
                                                 (unsigned*)ctx->d_l1_n.p, 0, nullptr);
         CUDA_TRY(ctx, cudaGetLastError());
+        la.n_items = (const unsigned*)ctx->d_l1_n.p;
+        la.cap = ctx->l1_cap;
+        la.chunk = 32;
         if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[2], s));
@@ -802,12 +809,13 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         // ... are re-scored with the exact FP32 arithmetic of the dense sweep (tier 2)
         ListArgs la;
         la.items = (const int2*)ctx->d_l1_items.p;
-        la.count = (const int*)ctx->d_l1_count.p;
-        la.base = (const unsigned*)ctx->d_l1_base.p;
+        la.n_items = (const unsigned*)ctx->d_l1_n.p;
+        la.cap = ctx->l1_cap;
+        la.chunk = 8;
         la.rmax = (const unsigned*)ctx->d_rmax.p;
         la.diag = (unsigned*)ctx->d_l1_n.p + 1;
-        if (!launch_sweep(ctx->TA, ctx->multi, (int)ctx->h_work_list.size(), ctx->smem_sweep, s, units,
-                          (const WorkItem*)ctx->d_work_list.p, (const float4*)ctx->d_lay.p,
+        if (!launch_sweep(ctx->TA, ctx->multi, (int)(((long long)ctx->l1_cap + la.chunk - 1) / la.chunk), ctx->smem_sweep, s,
+                          units, nullptr, (const float4*)ctx->d_lay.p,
                           (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p, &la))
             return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
         CUDA_TRY(ctx, cudaGetLastError());
@@ -863,6 +871,27 @@ extern "C" int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res.p, U * sizeof(UnitResultDev), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (std::getenv("MMRS_TRACE")) {  // device time of this run on stderr
+        float t[4] = {0, 0, 0, 0}, a = 0, b = 0;
+        cudaEventElapsedTime(&t[0], ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&t[1], ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&t[2], ctx->ev[2], ctx->ev[3]);
+        if (ctx->tc_ran || ctx->prune_ran) {
+            cudaEventElapsedTime(&a, ctx->ev_tc[0], ctx->ev_tc[1]);
+            cudaEventElapsedTime(&b, ctx->ev_tc[1], ctx->ev_tc[2]);
+        }
+        long long scored = 0;
+        int worst = 0;
+        if (ctx->tc_ran || ctx->prune_ran) {
+            std::vector<int> cnt((size_t)U);
+            cudaMemcpy(cnt.data(), ctx->d_l1_count.p, (size_t)U * 4, cudaMemcpyDeviceToHost);
+            for (int c : cnt) scored += c > 0 ? c : 0, worst = std::max(worst, c);
+        }
+        std::fprintf(stderr, "[mmrs]   run: %lld units, %lld candidates, sweep %.2f ms (%s tier0 %.2f + tier1 %.2f; %lld scored exactly, "
+                     "largest unit list %d), shortlist %.2f, recheck %.2f\n",
+                     (long long)U, ctx->total_cands, t[0], ctx->prune_ran ? "pruned:" : ctx->tc_ran ? "tc:" : "dense;", a, b, scored,
+                     worst, t[1], t[2]);
+    }
     const UnitResultDev* hr = (const UnitResultDev*)ctx->h_res;
     bool need_rmax = false;
     for (int64_t u = 0; u < U; ++u)

@@ -152,15 +152,17 @@ __global__ void k_cs32(const double2* __restrict__ cs64, float2* __restrict__ cs
 // K1: the FP32 sweep.
 // =============================================================================
 // LIST = false: the dense sweep, work item = (unit, first candidate, candidates in this tile).
-// LIST = true : tier 2 of the tensor-core prefilter (tc_kernels.cuh): work item = (unit, g, G); the CTA scores the
-//               positions g*8 + warp, stepping G*8, of the unit's tier-1 candidate list with the same arithmetic,
-//               overwrites the prefilter's approximate dist32 entries and records the largest observed
-//               |d_tc^2 - d_fp32^2| / Rmax^2 (the prefilter's error, checked against its window by the host).
+// LIST = true : exact re-scoring of a candidate list (after lower-bound pruning, or after the tensor-core prefilter of
+//               tc_kernels.cuh). The list is ONE global array of (unit, candidate) items, contiguous per unit; CTA b owns
+//               positions [b * l_chunk, (b + 1) * l_chunk) whatever units they belong to (it re-stages per run of equal
+//               units), so the SMs stay busy however unevenly the survivors are spread over the units. Same arithmetic;
+//               overwrites the dist32 entries and records the largest |d_old^2 - d_fp32^2| / Rmax^2 (the tensor-core
+//               prefilter's error, checked against its window).
 template <int TA, bool MULTI, bool LIST>
 __global__ void __launch_bounds__(kThreads, 2)
     k_sweep(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
             const float2* __restrict__ cs32, float* __restrict__ dist32, unsigned long long* __restrict__ key,
-            const int2* __restrict__ l_items, const int* __restrict__ l_count, const unsigned* __restrict__ l_base,
+            const int2* __restrict__ l_items, const unsigned* __restrict__ l_nitems, unsigned l_cap, int l_chunk,
             const unsigned* __restrict__ rmax_bits, unsigned* __restrict__ diag) {
     static_assert(TA >= 2 && TA <= 18, "register tile out of range");
     constexpr int H = TA / 2;          // packed pairs of test points per lane
@@ -172,40 +174,57 @@ __global__ void __launch_bounds__(kThreads, 2)
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw + 8);
     float4* sA = reinterpret_cast<float4*>(smem_raw + 16);
 
-    const WorkItem w = work[blockIdx.x];
-    int total = w.count, first = 0, step = kWarpsPerCta;
-    const int2* my_items = nullptr;
+    // LIST: this CTA owns the global list positions [g_pos, g_hi); they may span several units (runs of equal .x).
+    unsigned g_pos = 0, g_hi = 0;
     if (LIST) {
-        total = l_count[w.unit];
-        first = w.begin * kWarpsPerCta;
-        step = w.count * kWarpsPerCta;
-        if (total <= first) return;  // nothing for this CTA (uniform: before any barrier)
-        my_items = l_items + l_base[w.unit];
+        const unsigned n_items = l_nitems ? min(*l_nitems, l_cap) : l_cap;
+        g_pos = blockIdx.x * (unsigned)l_chunk;
+        g_hi = min(g_pos + (unsigned)l_chunk, n_items);
+        if (g_pos >= g_hi) return;  // nothing for this CTA (uniform: before any barrier)
     }
-    const UnitDesc ud = units[w.unit];
+    const WorkItem w = LIST ? WorkItem{0, 0, 0, 0} : work[blockIdx.x];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    uint32_t phase = 0;
+    const float INF = __int_as_float(0x7f800000);
+    float worst = 0.f;
+    for (;;) {  // one pass for the dense sweep; one pass per run of equal units in LIST mode
+    int unit = w.unit, total = w.count;
+    const int2* my_items = nullptr;
+    unsigned run_end = 0;
+    if (LIST) {
+        unit = l_items[g_pos].x;
+        run_end = g_pos + 1;
+        while (run_end < g_hi && l_items[run_end].x == unit) ++run_end;
+        total = (int)(run_end - g_pos);
+        my_items = l_items + g_pos;
+        if (unit < 0) {  // neutralised entries of an overflowed reservation
+            g_pos = run_end;
+            if (g_pos >= g_hi) break;
+            continue;
+        }
+    }
+    const UnitDesc ud = units[unit];
     const int a_elems = ud.n_chunks * S * 32;
     const int b_elems = ud.m_pairs;          // float4 per PAIR of reference points
     const int b_pts = 2 * ud.m_pairs;
     float4* sB = sA + a_elems;
     unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems);  // MULTI only: [warp][b_pts]
 
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         *s_key = ~0ull;
-        mbar_init(bar, 1);
         const uint32_t bytes = (uint32_t)(a_elems + b_elems) * 16u;
         mbar_expect_tx(bar, bytes);
         tma_bulk_g2s(sA, lay + ud.lay_off, bytes, bar);
     }
     __syncthreads();
-    mbar_wait(bar, 0);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
 
     unsigned long long best = ~0ull;
     unsigned* my_col = s_col + wid * b_pts;
-    const float INF = __int_as_float(0x7f800000);
 
-    float worst = 0.f;
-    for (int ci = first + wid; ci < total; ci += step) {
+    for (int ci = wid; ci < total; ci += kWarpsPerCta) {
         const int c = LIST ? my_items[ci].y : w.begin + ci;
         const float2 cs = __ldg(&cs32[ud.cand_off + c]);
         const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
@@ -291,12 +310,18 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
     }
     if (LIST && lane == 0 && worst > 0.f) {
-        const float r = fmaxf(__uint_as_float(rmax_bits[w.unit]), 1e-30f);
+        const float r = fmaxf(__uint_as_float(rmax_bits[unit]), 1e-30f);
         atomicMax(diag, __float_as_uint(worst / (r * r)));
+        worst = 0.f;
     }
     if (lane == 0 && best != ~0ull) atomicMin(s_key, best);
     __syncthreads();
-    if (threadIdx.x == 0 && *s_key != ~0ull) atomicMin(&key[w.unit], *s_key);
+    if (threadIdx.x == 0 && *s_key != ~0ull) atomicMin(&key[unit], *s_key);
+    if (!LIST) break;
+    g_pos = run_end;
+    if (g_pos >= g_hi) break;
+    __syncthreads();  // every warp is done with the staged unit and s_key before the next run re-stages
+    }
 }
 
 // =============================================================================
@@ -319,7 +344,7 @@ constexpr int kLbNegSin = 0x100;  // UnitDesc.flags of a lower-bound unit: rotat
 
 __global__ void k_prep_lb(const UnitDesc* __restrict__ units, const UnitDesc* __restrict__ lb_units, int n_units,
                           const double* __restrict__ test_xy, const double* __restrict__ ref_xy,
-                          float4* __restrict__ lay, int R) {
+                          float4* __restrict__ lay, int R, int R_eff) {
     const int u = blockIdx.x;
     const UnitDesc ud = units[u];
     if (ud.n <= 0 || ud.m <= 0) return;
@@ -330,7 +355,8 @@ __global__ void k_prep_lb(const UnitDesc* __restrict__ units, const UnitDesc* __
         const int nr = pass == 0 ? ud.n : ud.m, nc = pass == 0 ? ud.m : ud.n;
         float4* A = lay + lb.lay_off;
         float4* B = A + (R / 2);
-        auto pick = [&](int r) { return nr <= R ? min(r, nr - 1) : (int)(((long long)r * nr) / R); };
+        // R_eff < R (experiments): only R_eff distinct rows, repeated, to measure how the bound degrades
+        auto pick = [&](int r) { return nr <= R ? min(r, nr - 1) : (int)(((long long)(r % R_eff) * nr) / R_eff); };
         for (int e = threadIdx.x; e < R / 2; e += blockDim.x) {
             const int l = e & 31, k = e >> 5;
             const int i0 = pick(2 * k * 32 + l), i1 = pick(2 * k * 32 + l + 32);
@@ -420,7 +446,7 @@ __global__ void k_lb_argmin(const UnitDesc* __restrict__ units, const float* __r
     if (threadIdx.x == 0) s_best = ~0ull;
     __syncthreads();
     if (ud.flags || ud.n_cand <= 0) {
-        if (threadIdx.x == 0) l_count[u] = 0, l_base[u] = (unsigned)u;
+        if (threadIdx.x == 0) l_count[u] = 0, l_base[u] = (unsigned)u, l_items[u] = make_int2(-1, 0);
         return;
     }
     unsigned long long best = ~0ull;

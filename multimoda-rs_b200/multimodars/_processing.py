@@ -106,14 +106,15 @@ def _run(mode, blobs, labels, step, rng, sample_size, smooth, bruteforce, postpr
 def _four_from_paths(path_ab, path_cd, labels, image_center, radius, n_points):
     # prepare_n_geometries(Full), preprocessing.rs:174-199: (a dia, a sys, b dia, b sys)
     use = labels is not None and len(labels) == 4
-    blobs, names = [], []
+    jobs, names = [], []
     k = 0
     for p in (path_ab, path_cd):
         for dia in (True, False):
             name = labels[k] if use else _basename(p)
-            blobs.append(nat.geometry_from_dir(p, name, dia, image_center, radius, n_points))
+            jobs.append((p, name, dia))
             names.append(name)
             k += 1
+    blobs = _parallel(lambda j: nat.geometry_from_dir(j[0], j[1], j[2], image_center, radius, n_points), jobs)
     return blobs, names
 
 
@@ -168,9 +169,19 @@ def from_file_single(input_path, labels=None, diastole=True, step_rotation_deg=0
                 export=export)
 
 
+def _parallel(fn, args):
+    """The pullbacks of a case are ingested concurrently (the C side releases the GIL), like the reference's
+    crossbeam scope over its 4 geometries (binding/entry.rs:140-203)."""
+    if len(args) <= 1:
+        return [fn(a) for a in args]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(args)) as ex:
+        return list(ex.map(fn, args))
+
+
 def _from_inputs(mode, inputs, step, rng, sample_size, image_center, radius, n_points, smooth, bruteforce,
                  postprocessing=False, export=None):
-    blobs = [_blob_from_input(i, image_center, radius, n_points) for i in inputs]
+    blobs = _parallel(lambda i: _blob_from_input(i, image_center, radius, n_points), list(inputs))
     return _run(mode, blobs, [i.label for i in inputs], step, rng, sample_size, smooth, bruteforce, postprocessing,
                 export)
 
