@@ -497,13 +497,10 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
                 const int per = (d.n_cand + parts - 1) / parts;
                 for (int c0 = 0; c0 < d.n_cand; c0 += per)
                     ctx->h_work_tc.push_back(WorkItem{(int)u, c0, std::min(per, d.n_cand - c0), 0});
-                const int G = 4;
-                for (int g = 0; g < G; ++g) ctx->h_work_list.push_back(WorkItem{(int)u, g, G, 0});
             }
             ctx->l1_cap = (unsigned)std::min<unsigned long long>(
                 std::max<unsigned long long>((unsigned long long)U * 256, 1ull << 20), 0x7fffffffull);
             ENSURE(ctx->d_work_tc, ctx->h_work_tc.size() * sizeof(WorkItem));
-            ENSURE(ctx->d_work_list, ctx->h_work_list.size() * sizeof(WorkItem));
             ENSURE(ctx->d_key_tc, U * 8);
             ENSURE(ctx->d_l1_items, (size_t)ctx->l1_cap * 8);
             ENSURE(ctx->d_l1_count, U * 4);
@@ -540,15 +537,8 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
                     for (int c0 = 0; c0 < d.n_cand; c0 += tile)
                         ctx->h_work_lb.push_back(WorkItem{(int)(u + pass * U), c0, std::min(tile, d.n_cand - c0), 0});
                 }
-            // tier-2 list work: (unit, g, G); G grows when there are few units so that the survivors spread over the SMs
-            ctx->h_work_list.clear();
-            const int G = (int)std::max<long long>(4, std::min<long long>(64, (16LL * ctx->n_sm + live_units - 1) / live_units));
-            for (int64_t u = 0; u < U; ++u)
-                if (!units[u].flags)
-                    for (int g = 0; g < G; ++g) ctx->h_work_list.push_back(WorkItem{(int)u, g, G, 0});
             ctx->l1_cap = (unsigned)std::min<long long>(std::max<long long>(dist_off, 1), 0x7fffffffLL);
             ENSURE(ctx->d_work_lb, ctx->h_work_lb.size() * sizeof(WorkItem));
-            ENSURE(ctx->d_work_list, ctx->h_work_list.size() * sizeof(WorkItem));
             ENSURE(ctx->d_l1_items, (size_t)ctx->l1_cap * 8);
             ENSURE(ctx->d_l1_count, U * 4);
             ENSURE(ctx->d_l1_base, U * 4);
@@ -575,14 +565,10 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
                                       cudaMemcpyHostToDevice, s));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_lb.p, ctx->h_work_lb.data(), ctx->h_work_lb.size() * sizeof(WorkItem),
                                       cudaMemcpyHostToDevice, s));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_list.p, ctx->h_work_list.data(),
-                                      ctx->h_work_list.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, s));
     }
     if (ctx->use_tc && !ctx->h_work_tc.empty()) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_tc.p, ctx->h_work_tc.data(), ctx->h_work_tc.size() * sizeof(WorkItem),
                                       cudaMemcpyHostToDevice, s));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_work_list.p, ctx->h_work_list.data(),
-                                      ctx->h_work_list.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, s));
     }
     if (n_cs) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cs64.p, ctx->h_cs.data(), (size_t)n_cs * 16, cudaMemcpyHostToDevice, s));
