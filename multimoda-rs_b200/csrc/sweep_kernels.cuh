@@ -334,10 +334,10 @@ __global__ void __launch_bounds__(kThreads, 2)
 // of any evaluated candidate (plus the FP32 window) cannot be the arg-min and is never scored; every other candidate is
 // scored by the exact FP32 kernel (k_sweep LIST) and continues to K2/K3/K4 unchanged, so the selected candidate, its
 // angle and its f64 distance are identical to the dense path's.
-//   k_prep_lb   per unit two staging images: rows = R strided test points / columns = all reference points, and
-//               rows = R strided reference points / columns = all test points (rotated by -theta instead).
-//   k_lb<TA>    rows-only sweep of those images: row minima + max, no column minima, no REDUX per column;
-//               result max-combined into dist32 with atomicMax on the (non-negative) float bits.
+//   k_prep_lb   per unit two staging images: rows = 32 strided test points / columns = all reference points, and
+//               rows = 32 strided reference points / columns = all test points (rotated by -theta instead).
+//   k_lb<CB>    rows-only sweep of those images, CB candidates per warp: row minima + max, no column minima, no REDUX
+//               per column; result max-combined into dist32 with atomicMax on the (non-negative) float bits.
 //   k_lb_argmin the candidate with the smallest LB of each unit (scored first: its exact distance is the bound).
 // =============================================================================
 constexpr int kLbNegSin = 0x100;  // UnitDesc.flags of a lower-bound unit: rotate its rows by -theta
@@ -353,15 +353,13 @@ __global__ void k_prep_lb(const UnitDesc* __restrict__ units, const UnitDesc* __
         const double* rows = pass == 0 ? test_xy + 2 * ud.test_off : ref_xy + 2 * ud.ref_off;
         const double* cols = pass == 0 ? ref_xy + 2 * ud.ref_off : test_xy + 2 * ud.test_off;
         const int nr = pass == 0 ? ud.n : ud.m, nc = pass == 0 ? ud.m : ud.n;
-        float4* A = lay + lb.lay_off;
-        float4* B = A + (R / 2);
+        float2* A = reinterpret_cast<float2*>(lay + lb.lay_off);   // R rows (x, y); lane l of k_lb owns row l
+        float4* B = lay + lb.lay_off + R / 2;
         // R_eff < R (experiments): only R_eff distinct rows, repeated, to measure how the bound degrades
         auto pick = [&](int r) { return nr <= R ? min(r, nr - 1) : (int)(((long long)(r % R_eff) * nr) / R_eff); };
-        for (int e = threadIdx.x; e < R / 2; e += blockDim.x) {
-            const int l = e & 31, k = e >> 5;
-            const int i0 = pick(2 * k * 32 + l), i1 = pick(2 * k * 32 + l + 32);
-            A[e] = make_float4((float)(rows[2 * i0] - ud.cx), (float)(rows[2 * i1] - ud.cx), (float)(rows[2 * i0 + 1] - ud.cy),
-                               (float)(rows[2 * i1 + 1] - ud.cy));
+        for (int r = threadIdx.x; r < R; r += blockDim.x) {
+            const int i = pick(r);
+            A[r] = make_float2((float)(rows[2 * i] - ud.cx), (float)(rows[2 * i + 1] - ud.cy));
         }
         for (int j = threadIdx.x; j < lb.m_pairs; j += blockDim.x) {
             const int j0 = min(2 * j, nc - 1), j1 = min(2 * j + 1, nc - 1);
@@ -371,18 +369,21 @@ __global__ void k_prep_lb(const UnitDesc* __restrict__ units, const UnitDesc* __
     }
 }
 
-template <int TA>
+// One warp = CB consecutive candidates x 32 sampled rows (lane l owns row l): the packed f32x2 lanes carry TWO CANDIDATES
+// of the same row, so one broadcast LDS.128 of two column points feeds CB/2 blocks of 8 packed FP32 + 2 FMNMX3 — the
+// instruction mix of K1's inner loop without its column side.
+template <int CB>
 __global__ void __launch_bounds__(kThreads, 2)
     k_lb(const UnitDesc* __restrict__ lb_units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
          const float2* __restrict__ cs32, float* __restrict__ dist32) {
-    constexpr int H = TA / 2;
-    static_assert(TA == 2 || TA == 4, "lower-bound register tile");
+    constexpr int P = CB / 2;
+    static_assert(CB == 8 || CB == 4, "candidates per warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float4* sA = reinterpret_cast<float4*>(smem_raw + 16);
     const WorkItem w = work[blockIdx.x];
     const UnitDesc ud = lb_units[w.unit];
-    const int a_elems = H * 32, b_elems = ud.m_pairs;
+    const int a_elems = 16, b_elems = ud.m_pairs;   // 32 rows x 8 B
     float4* sB = sA + a_elems;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -396,44 +397,43 @@ __global__ void __launch_bounds__(kThreads, 2)
     const float INF = __int_as_float(0x7f800000);
     const float sgn = (ud.flags & kLbNegSin) ? -1.f : 1.f;
     unsigned* out = reinterpret_cast<unsigned*>(dist32 + ud.dist_off);
-    for (int ci = wid; ci < w.count; ci += kWarpsPerCta) {
-        const int c = w.begin + ci;
-        float2 cs = __ldg(&cs32[ud.cand_off + c]);
-        cs.y *= sgn;
-        const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
-        uint64_t AX[H], AY[H];
-        float row[TA];
+    const float2 a = reinterpret_cast<const float2*>(sA)[lane];
+    const uint64_t X2 = pk(a.x, a.x), Y2 = pk(a.y, a.y);
+    for (int g = wid * CB; g < w.count; g += kWarpsPerCta * CB) {
+        uint64_t AX[P], AY[P];
+        float row[CB];
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-            const float4 a = sA[k * 32 + lane];
-            const uint64_t X2 = pk(a.x, a.y), Y2 = pk(a.z, a.w);
-            AX[k] = fma2(Y2, NS2, mul2(X2, C2));
-            AY[k] = fma2(X2, S2, mul2(Y2, C2));
-            row[2 * k] = INF;
-            row[2 * k + 1] = INF;
+        for (int p = 0; p < P; ++p) {
+            const int c0 = w.begin + min(g + 2 * p, w.count - 1), c1 = w.begin + min(g + 2 * p + 1, w.count - 1);
+            const float2 s0 = __ldg(&cs32[ud.cand_off + c0]), s1 = __ldg(&cs32[ud.cand_off + c1]);
+            const uint64_t C2 = pk(s0.x, s1.x), S2 = pk(s0.y * sgn, s1.y * sgn), NS2 = pk(-s0.y * sgn, -s1.y * sgn);
+            AX[p] = fma2(Y2, NS2, mul2(X2, C2));   // (x cos0 - y sin0, x cos1 - y sin1)
+            AY[p] = fma2(X2, S2, mul2(Y2, C2));
+            row[2 * p] = INF;
+            row[2 * p + 1] = INF;
         }
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < ud.m_pairs; ++j) {
             const float4 B = sB[j];
             const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y), bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
 #pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const uint64_t dx0 = sub2(AX[k], bx0), dy0 = sub2(AY[k], by0);
-                const uint64_t dx1 = sub2(AX[k], bx1), dy1 = sub2(AY[k], by1);
-                const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));
-                const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));
-                float d00, d10, d01, d11;
-                upk(d0, d00, d10);
-                upk(d1, d01, d11);
-                row[2 * k] = min3(row[2 * k], d00, d01);
-                row[2 * k + 1] = min3(row[2 * k + 1], d10, d11);
+            for (int p = 0; p < P; ++p) {
+                const uint64_t dx0 = sub2(AX[p], bx0), dy0 = sub2(AY[p], by0);
+                const uint64_t dx1 = sub2(AX[p], bx1), dy1 = sub2(AY[p], by1);
+                const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));  // column point 0: (candidate 2p, candidate 2p+1)
+                const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));  // column point 1
+                float d00, d01, d10, d11;
+                upk(d0, d00, d01);
+                upk(d1, d10, d11);
+                row[2 * p] = min3(row[2 * p], d00, d10);
+                row[2 * p + 1] = min3(row[2 * p + 1], d01, d11);
             }
         }
-        float rm = row[0];
 #pragma unroll
-        for (int k = 1; k < TA; ++k) rm = fmaxf(rm, row[k]);
-        const unsigned h2 = __reduce_max_sync(0xffffffffu, __float_as_uint(rm));
-        if (lane == 0) atomicMax(&out[c], __float_as_uint(sqrtf(__uint_as_float(h2))));
+        for (int k = 0; k < CB; ++k) {
+            const unsigned h2 = __reduce_max_sync(0xffffffffu, __float_as_uint(row[k]));
+            if (lane == k && g + k < w.count) atomicMax(&out[w.begin + g + k], __float_as_uint(sqrtf(__uint_as_float(h2))));
+        }
     }
 }
 
