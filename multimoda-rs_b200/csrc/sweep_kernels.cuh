@@ -223,12 +223,22 @@ __global__ void __launch_bounds__(kThreads, 2)
 
     unsigned long long best = ~0ull;
     unsigned* my_col = s_col + wid * b_pts;
+    // LIST: squared give-up threshold from the unit's best exact distance so far (bits; 0xffffffff = none yet)
+    unsigned give_up = 0xffffffffu;
+    if (LIST) {
+        const unsigned ub_bits = (unsigned)(key[unit] >> 32);
+        if (ub_bits != 0xffffffffu) {
+            const float t = __uint_as_float(ub_bits) * (1.0f + 4e-6f) + 4e-6f * __uint_as_float(rmax_bits[unit]);
+            give_up = __float_as_uint(t * t * (1.0f + 1e-6f));
+        }
+    }
 
     for (int ci = wid; ci < total; ci += kWarpsPerCta) {
         const int c = LIST ? my_items[ci].y : w.begin + ci;
         const float2 cs = __ldg(&cs32[ud.cand_off + c]);
         const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
         unsigned rowmax = 0u, colmax = 0u;  // bit patterns of non-negative floats order like unsigned ints
+        bool gave_up = false;
 
         for (int ch = 0; ch < ud.n_chunks; ++ch) {
             uint64_t AX[H], AY[H];
@@ -287,10 +297,17 @@ __global__ void __launch_bounds__(kThreads, 2)
                 unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
                 if (!MULTI || ch == ud.n_chunks - 1) {
                     colmax = max(colmax, max(r0, r1));  // all test points seen: these are the column minima
+                    // LIST: a column minimum above the unit's best exact distance (+ window) already proves that this
+                    // candidate cannot win: stop, and keep the proven lower bound (uniform across the warp)
+                    if (LIST && colmax > give_up) {
+                        gave_up = true;
+                        break;
+                    }
                 } else if (lane == 0) {
                     *reinterpret_cast<uint2*>(&my_col[2 * j]) = make_uint2(r0, r1);
                 }
             }
+            if (LIST && gave_up) break;  // the row minima are incomplete: only the column bound counts
             float rm = row[0];
 #pragma unroll
             for (int k = 1; k < TA; ++k) rm = fmaxf(rm, row[k]);
