@@ -372,6 +372,14 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
                            std::to_string(ctx->smem_sweep) + " B > 227 KB)");
     const size_t n_test = (size_t)b->test_off[U], n_ref = (size_t)b->ref_off[U];
     if ((n_test && !b->test_xy) || (n_ref && !b->ref_xy)) return set_err(ctx, MMRS_ERR_ARG, "point arrays are NULL");
+    if (ctx->lb_shape_ok || ctx->tc_shape_ok) {
+        // The optional tiers order candidates by the bit patterns of non-negative finite floats; a non-finite
+        // coordinate (the reference skips non-finite minima, process_utils.rs:112) sends the batch down the dense path.
+        bool finite = true;
+        for (size_t i = 0; i < 2 * n_test && finite; ++i) finite = std::isfinite(b->test_xy[i]);
+        for (size_t i = 0; i < 2 * n_ref && finite; ++i) finite = std::isfinite(b->ref_xy[i]);
+        if (!finite) ctx->lb_shape_ok = ctx->tc_shape_ok = false;
+    }
     ENSURE(ctx->d_test, n_test * 16);
     ENSURE(ctx->d_ref, n_ref * 16);
     ENSURE(ctx->d_units, U * sizeof(UnitDesc));
