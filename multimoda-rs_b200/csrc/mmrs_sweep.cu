@@ -412,7 +412,8 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
         k_prep_lb<<<(unsigned)U, 256, 0, s>>>((const UnitDesc*)ctx->d_units.p, (const UnitDesc*)ctx->d_units_lb.p, (int)U,
                                               (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
                                               (float4*)ctx->d_lay_lb.p, ctx->lb_R,
-                                              std::getenv("MMRS_LB_ROWS") ? std::max(8, std::min(ctx->lb_R, std::atoi(std::getenv("MMRS_LB_ROWS")))) : ctx->lb_R);
+                                              std::getenv("MMRS_LB_ROWS") ? std::max(8, std::min(ctx->lb_R, std::atoi(std::getenv("MMRS_LB_ROWS")))) : ctx->lb_R,
+                                              std::getenv("MMRS_LB_PICK") ? std::atoi(std::getenv("MMRS_LB_PICK")) : 2);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->upload_launches += 1;
     }
