@@ -332,7 +332,7 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
             if (d.n < 128 || d.m < 128) ok = false;
             biggest = std::max(biggest, std::max(d.n, d.m));
         }
-        ctx->lb_R = 32;  // one sampled row per lane of k_lb
+        ctx->lb_R = biggest >= 1024 ? 128 : 32;  // rows per lower-bound pass: k_lb<1,8> or k_lb<4,2>
         ctx->lb_shape_ok = ok && biggest > 0;
         ctx->h_units_lb.assign(2 * (size_t)U, UnitDesc{});
         long long off = 0;
@@ -710,10 +710,17 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dist32.p, 0, (size_t)ctx->total_cands * 4, s));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[0], s));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_lb<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_lb));
-        k_lb<8><<<(unsigned)ctx->h_work_lb.size(), kThreads, ctx->smem_lb, s>>>(
-            lbu, (const WorkItem*)ctx->d_work_lb.p, (const float4*)ctx->d_lay_lb.p, (const float2*)ctx->d_cs32.p,
-            (float*)ctx->d_dist32.p);
+        if (ctx->lb_R == 128) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_lb<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_lb));
+            k_lb<4, 2><<<(unsigned)ctx->h_work_lb.size(), kThreads, ctx->smem_lb, s>>>(
+                lbu, (const WorkItem*)ctx->d_work_lb.p, (const float4*)ctx->d_lay_lb.p, (const float2*)ctx->d_cs32.p,
+                (float*)ctx->d_dist32.p);
+        } else {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_lb<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_lb));
+            k_lb<1, 8><<<(unsigned)ctx->h_work_lb.size(), kThreads, ctx->smem_lb, s>>>(
+                lbu, (const WorkItem*)ctx->d_work_lb.p, (const float4*)ctx->d_lay_lb.p, (const float2*)ctx->d_cs32.p,
+                (float*)ctx->d_dist32.p);
+        }
         CUDA_TRY(ctx, cudaGetLastError());
         // the candidate with the smallest bound is scored first: its exact FP32 distance bounds the minimum from above
         k_lb_argmin<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p, (int*)ctx->d_l1_count.p,

@@ -351,12 +351,14 @@ __global__ void __launch_bounds__(kThreads, 2)
 // of any evaluated candidate (plus the FP32 window) cannot be the arg-min and is never scored; every other candidate is
 // scored by the exact FP32 kernel (k_sweep LIST) and continues to K2/K3/K4 unchanged, so the selected candidate, its
 // angle and its f64 distance are identical to the dense path's.
-//   k_prep_lb   per unit two staging images: rows = 32 sampled test points / columns = all reference points, and
-//               rows = 32 sampled reference points / columns = all test points (rotated by -theta instead). The sample
-//               is, per window of n/32 consecutive points, the point farthest from the rotation centre: the directed
+//   k_prep_lb   per unit two staging images: rows = R sampled test points / columns = all reference points, and
+//               rows = R sampled reference points / columns = all test points (rotated by -theta instead). The sample
+//               is, per window of n/R consecutive points, the point farthest from the rotation centre: the directed
 //               maxima sit where a contour sticks out (measured: 4x fewer survivors than plain striding).
-//   k_lb<CB>    rows-only sweep of those images, CB candidates per warp: row minima + max, no column minima, no REDUX
-//               per column; result max-combined into dist32 with atomicMax on the (non-negative) float bits.
+//   k_lb<RS,CB> rows-only sweep of those images, 32 RS rows x CB candidates per warp: row minima + max, no column minima,
+//               no REDUX per column; result max-combined into dist32 with atomicMax on the (non-negative) float bits.
+//               32 rows for sets below 1 024 points, 128 rows above (dense 2 000-point lumina of consecutive frames
+//               differ so little that a coarser sample lets half of the candidates through).
 //   k_lb_argmin the candidate with the smallest LB of each unit (scored first: its exact distance is the bound).
 // =============================================================================
 constexpr int kLbNegSin = 0x100;  // UnitDesc.flags of a lower-bound unit: rotate its rows by -theta
@@ -378,7 +380,20 @@ __global__ void k_prep_lb(const UnitDesc* __restrict__ units, const UnitDesc* __
         auto pick = [&](int r) { return nr <= R ? min(r, nr - 1) : (int)(((long long)(r % R_eff) * nr) / R_eff); };
         for (int r = threadIdx.x; r < R; r += blockDim.x) {
             int i = pick(r);
-            if (pick_mode != 0 && nr > R) {
+            if (pick_mode == 3 && nr > R) {
+                // half strided, half farthest: windows of 2 nr / R points; even rows take the window's first point,
+                // odd rows its point farthest from the rotation centre
+                const int w = r >> 1, W = R >> 1;
+                const int lo = (int)(((long long)w * nr) / W), hi = (int)(((long long)(w + 1) * nr) / W);
+                i = lo;
+                if (r & 1) {
+                    double best = -1.0;
+                    for (int k = lo; k < hi; ++k) {
+                        const double dx = rows[2 * k] - ud.cx, dy = rows[2 * k + 1] - ud.cy, rr = dx * dx + dy * dy;
+                        if (rr > best) best = rr, i = k;
+                    }
+                }
+            } else if (pick_mode != 0 && nr > R) {
                 // Any subset gives a valid bound; the directed maxima sit where a contour sticks out or caves in, so
                 // take, per index window, the point farthest from (even windows / mode 2: all) or nearest to (odd
                 // windows) the rotation centre instead of the window's first point.
@@ -400,21 +415,21 @@ __global__ void k_prep_lb(const UnitDesc* __restrict__ units, const UnitDesc* __
     }
 }
 
-// One warp = CB consecutive candidates x 32 sampled rows (lane l owns row l): the packed f32x2 lanes carry TWO CANDIDATES
-// of the same row, so one broadcast LDS.128 of two column points feeds CB/2 blocks of 8 packed FP32 + 2 FMNMX3 — the
-// instruction mix of K1's inner loop without its column side.
-template <int CB>
+// One warp = CB consecutive candidates x 32 RS sampled rows (lane l owns rows l, l + 32, ...): the packed f32x2 lanes
+// carry TWO CANDIDATES of the same row, so one broadcast LDS.128 of two column points feeds RS CB/2 = 4 blocks of
+// 8 packed FP32 + 2 FMNMX3 — the instruction mix of K1's inner loop without its column side.
+template <int RS, int CB>
 __global__ void __launch_bounds__(kThreads, 2)
     k_lb(const UnitDesc* __restrict__ lb_units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
          const float2* __restrict__ cs32, float* __restrict__ dist32) {
     constexpr int P = CB / 2;
-    static_assert(CB == 8 || CB == 4, "candidates per warp");
+    static_assert(RS * CB == 8 && CB >= 2, "rows per lane x candidates per warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float4* sA = reinterpret_cast<float4*>(smem_raw + 16);
     const WorkItem w = work[blockIdx.x];
     const UnitDesc ud = lb_units[w.unit];
-    const int a_elems = 16, b_elems = ud.m_pairs;   // 32 rows x 8 B
+    const int a_elems = 16 * RS, b_elems = ud.m_pairs;   // 32 RS rows x 8 B
     float4* sB = sA + a_elems;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -428,41 +443,55 @@ __global__ void __launch_bounds__(kThreads, 2)
     const float INF = __int_as_float(0x7f800000);
     const float sgn = (ud.flags & kLbNegSin) ? -1.f : 1.f;
     unsigned* out = reinterpret_cast<unsigned*>(dist32 + ud.dist_off);
-    const float2 a = reinterpret_cast<const float2*>(sA)[lane];
-    const uint64_t X2 = pk(a.x, a.x), Y2 = pk(a.y, a.y);
+    uint64_t X2[RS], Y2[RS];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+        const float2 a = reinterpret_cast<const float2*>(sA)[lane + 32 * r];
+        X2[r] = pk(a.x, a.x);
+        Y2[r] = pk(a.y, a.y);
+    }
     for (int g = wid * CB; g < w.count; g += kWarpsPerCta * CB) {
-        uint64_t AX[P], AY[P];
-        float row[CB];
+        uint64_t AX[RS][P], AY[RS][P];
+        float row[RS][CB];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const int c0 = w.begin + min(g + 2 * p, w.count - 1), c1 = w.begin + min(g + 2 * p + 1, w.count - 1);
             const float2 s0 = __ldg(&cs32[ud.cand_off + c0]), s1 = __ldg(&cs32[ud.cand_off + c1]);
             const uint64_t C2 = pk(s0.x, s1.x), S2 = pk(s0.y * sgn, s1.y * sgn), NS2 = pk(-s0.y * sgn, -s1.y * sgn);
-            AX[p] = fma2(Y2, NS2, mul2(X2, C2));   // (x cos0 - y sin0, x cos1 - y sin1)
-            AY[p] = fma2(X2, S2, mul2(Y2, C2));
-            row[2 * p] = INF;
-            row[2 * p + 1] = INF;
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+                AX[r][p] = fma2(Y2[r], NS2, mul2(X2[r], C2));   // (x cos0 - y sin0, x cos1 - y sin1)
+                AY[r][p] = fma2(X2[r], S2, mul2(Y2[r], C2));
+                row[r][2 * p] = INF;
+                row[r][2 * p + 1] = INF;
+            }
         }
 #pragma unroll 2
         for (int j = 0; j < ud.m_pairs; ++j) {
             const float4 B = sB[j];
             const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y), bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const uint64_t dx0 = sub2(AX[p], bx0), dy0 = sub2(AY[p], by0);
-                const uint64_t dx1 = sub2(AX[p], bx1), dy1 = sub2(AY[p], by1);
-                const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));  // column point 0: (candidate 2p, candidate 2p+1)
-                const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));  // column point 1
-                float d00, d01, d10, d11;
-                upk(d0, d00, d01);
-                upk(d1, d10, d11);
-                row[2 * p] = min3(row[2 * p], d00, d10);
-                row[2 * p + 1] = min3(row[2 * p + 1], d01, d11);
+            for (int r = 0; r < RS; ++r) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const uint64_t dx0 = sub2(AX[r][p], bx0), dy0 = sub2(AY[r][p], by0);
+                    const uint64_t dx1 = sub2(AX[r][p], bx1), dy1 = sub2(AY[r][p], by1);
+                    const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));  // column point 0: (candidate 2p, candidate 2p+1)
+                    const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));  // column point 1
+                    float d00, d01, d10, d11;
+                    upk(d0, d00, d01);
+                    upk(d1, d10, d11);
+                    row[r][2 * p] = min3(row[r][2 * p], d00, d10);
+                    row[r][2 * p + 1] = min3(row[r][2 * p + 1], d01, d11);
+                }
             }
         }
 #pragma unroll
         for (int k = 0; k < CB; ++k) {
-            const unsigned h2 = __reduce_max_sync(0xffffffffu, __float_as_uint(row[k]));
+            float rm = row[0][k];
+#pragma unroll
+            for (int r = 1; r < RS; ++r) rm = fmaxf(rm, row[r][k]);
+            const unsigned h2 = __reduce_max_sync(0xffffffffu, __float_as_uint(rm));
             if (lane == k && g + k < w.count) atomicMax(&out[w.begin + g + k], __float_as_uint(sqrtf(__uint_as_float(h2))));
         }
     }
