@@ -389,7 +389,7 @@ def main():
             ms.append(ctx.timings()["total_ms"])
         info = ctx.prefilter_info()
         pm = float(np.mean(ms[1:]))
-        pruned = {"kernels": "k_lb<8> (rows-only bounds over 32 strided points of each set, 8 candidates per warp) + k_sweep<..,LIST> on the survivors",
+        pruned = {"kernels": "k_lb<1,8> (rows-only bounds over 32 sampled points of each set, 8 candidates per warp) + k_sweep<..,LIST> on the survivors",
                   "ms_per_step": pm, "candidates_decided_per_s": evals_rank / (pm * 1e-3),
                   "speedup_vs_dense": float(np.mean(dev_ms)) / pm, "scored_fraction": info["rescored"] / evals_rank,
                   "bounds_ms": info["tc_ms"], "survivors_ms": info["rescore_ms"],

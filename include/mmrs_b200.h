@@ -129,7 +129,7 @@ typedef struct mmrs_sweep_opts {
     double prefilter_abs; /* <= 0 selects 4e-6 (about 7x the largest error measured) */
     /* Exact lower-bound pruning (opt-in): before the FP32 sweep every candidate gets the lower bound
      *   LB = max( max_{a in A'} min_{b in B} |a-b| , max_{b in B'} min_{a in A} |a-b| ) <= Hausdorff(A, B)
-     * over 32 strided points A', B' of the two sets; the candidate with the smallest
+     * over 32 (128 for sets of >= 1024 points) sampled points A', B' of the two sets; the candidate with the smallest
      * bound is scored exactly, and only candidates whose bound does not exceed that distance (plus twice the
      * FP32 window) are scored by the FP32 kernel — the others cannot be the arg-min. Selection, angle and f64
      * distance are identical to the dense path; mmrs_sweep_get_dist32 then returns the BOUND for pruned
