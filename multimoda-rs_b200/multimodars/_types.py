@@ -354,6 +354,56 @@ class PyGeometry:
 
     get_contours = get_contours_by_type
 
+    def get_contours(self, contour_type: str):
+        """py_geometry.rs:98-100."""
+        return self.get_contours_by_type(contour_type)
+
+    def sort_frame_points(self):
+        """py_geometry.rs:152-156 -> Geometry::sort_frame_points_by_z (geometry.rs:257-276): every contour of every
+        frame is rotated so that the (last) highest-z point of frame 0's lumen comes first; point_index re-assigned."""
+        if not self.frames:
+            return PyGeometry([], self.label)
+        z = self.frames[0].lumen._sync()[:, 4]
+        shift = 0
+        for i in range(len(z)):          # Iterator::max_by keeps the LAST maximum
+            if not (z[i] < z[shift]):
+                shift = i
+        out = []
+        for f in self.frames:
+            g = f._clone()
+            for c in [g.lumen, *g.extras.values()]:
+                n = len(c._rows)
+                if n == 0 or shift == 0:
+                    continue
+                c._rows = np.roll(c._rows, -(shift % n), axis=0).copy()
+                c._rows[:, 1] = np.arange(n, dtype=np.float64)
+                c._pts = None
+            out.append(g)
+        return PyGeometry(out, self.label)
+
+    def center_to_contour(self, contour_type):
+        """py_geometry.rs:267-273 -> Geometry::center_to_contour (geometry.rs:383-442): every frame after the first is
+        translated in x, y so that the centroid of its `contour_type` contour lands on frame 0's."""
+        name = contour_type.name if isinstance(contour_type, PyContourType) else str(contour_type)
+        if not self.frames:
+            return PyGeometry([], self.label)
+
+        def centroid_of(f):
+            c = f.lumen if name == "Lumen" else f.extras.get(name)
+            if c is None or len(c._sync()) == 0:
+                return f.centroid
+            return tuple(float(v) for v in _centroid_rows(c._sync()))
+
+        frames = [self.frames[0]._clone()]
+        c0 = frames[0].lumen if name == "Lumen" else frames[0].extras.get(name)
+        if c0 is not None and len(c0._sync()):
+            c0.centroid, c0._has_centroid = tuple(float(v) for v in _centroid_rows(c0._sync())), True
+        ref = centroid_of(frames[0])
+        for f in self.frames[1:]:
+            cur = centroid_of(f)
+            frames.append(f.translate(ref[0] - cur[0], ref[1] - cur[1], 0.0))
+        return PyGeometry(frames, self.label)
+
     def get_lumen_contours(self):
         return [f.lumen for f in self.frames]
 
@@ -509,8 +559,32 @@ class PyGeometryPair:
     def __init__(self, geom_a, geom_b, label):
         self.geom_a, self.geom_b, self.label = geom_a, geom_b, str(label)
 
-    def __repr__(self):
-        return f"GeometryPair(label='{self.label}', geom_a={self.geom_a!r}, geom_b={self.geom_b!r})"
+    def __repr__(self):  # py_geometry_pair.rs:48-55
+        return (f"GeometryPair {self.label} (diastolic: {len(self.geom_a.frames)} frames, "
+                f"systolic: {len(self.geom_b.frames)} frames)")
+
+    def get_summary(self):
+        """py_geometry_pair.rs:70-201 -> (((dia_mla, dia_max_stenosis, dia_len_mm), (sys ...)), table); table rows are
+        [id, area_dia, ellip_dia, area_sys, ellip_sys, z]; the table is also printed like the reference does."""
+        dia, sys_ = self.geom_a.get_summary(), self.geom_b.get_summary()
+        a, b = self.geom_a.get_lumen_contours(), self.geom_b.get_lumen_contours()
+        n = len(a)
+        if len(b) != n:
+            print("ERROR: mismatched lengths between contour vectors")
+        mat = [[float(a[i].id), a[i].get_area(), a[i].get_elliptic_ratio(), b[i].get_area(), b[i].get_elliptic_ratio(),
+                a[i].centroid[2]] for i in range(n)]
+        headers = ["id", "area_dia", "ellip_dia", "area_sys", "ellip_sys", "z"]
+        rows = [[str(a[i].id)] + [f"{v:.2f}" for v in mat[i][1:]] for i in range(n)]
+        widths = [max([len(h)] + [len(r[k]) for r in rows]) for k, h in enumerate(headers)]
+        border = "+" + "".join("-" * (w + 2) + "+" for w in widths)
+        print(border)
+        print("|" + "".join(" " + " " * ((w - len(h)) // 2) + h + " " * ((w - len(h)) - (w - len(h)) // 2) + " |"
+                            for h, w in zip(headers, widths)))
+        print(border)
+        for r in rows:
+            print("|" + "".join(" " + c + " " * (w - len(c)) + " |" for c, w in zip(r, widths)))
+        print(border)
+        return (dia, sys_), mat
 
 
 class PyCenterlinePoint:

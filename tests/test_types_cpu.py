@@ -110,3 +110,37 @@ def test_helpers_follow_the_reference_arithmetic():
     assert g.get_frame_at_z(2.2).id == 2 and g.get_frame_at_index(3).id == 3
     with pytest.raises(IndexError):
         g.get_frame_at_index(9)
+
+
+def test_geometry_helpers_added_for_source_compatibility(capsys):
+    """py_geometry.rs:98-100 (get_contours), :152-156 (sort_frame_points -> sort_frame_points_by_z), :267-273
+    (center_to_contour); py_geometry_pair.rs:48-55 (repr) and :70-201 (get_summary + printed table)."""
+    from multimodars import PyContourType, PyGeometryPair
+
+    def geom(label, shift):
+        frames = []
+        for i in range(3):
+            c = _ring(i, (1.0 + shift * i, 2.0 - shift * i, float(i)), 2.0 + 0.1 * i, 2.0 + 0.1 * i, n=12)
+            frames.append(PyFrame(i, c.centroid, c, {}, None))
+        return PyGeometry(frames, label)
+
+    g = geom("dia", 0.3)
+    assert [c.id for c in g.get_contours("Lumen")] == [0, 1, 2]
+    centred = g.center_to_contour(PyContourType.Lumen)
+    for f in centred.frames:
+        assert abs(f.lumen.centroid[0] - 1.0) < 1e-12 and abs(f.lumen.centroid[1] - 2.0) < 1e-12
+        assert abs(f.centroid[0] - 1.0) < 1e-12
+    assert centred.frames[2].centroid[2] == 2.0 and g.frames[2].centroid[0] != 1.0      # a copy; z untouched
+    # sort_frame_points_by_z: frame 0's highest-z lumen point (the LAST maximum) becomes index 0 everywhere
+    g.frames[0].lumen.points[5].z = 9.0
+    s = g.sort_frame_points()
+    assert s.frames[0].lumen.points[0].z == 9.0
+    assert [p.point_index for p in s.frames[1].lumen.points] == list(range(12))
+    assert s.frames[1].lumen.points[0].x == g.frames[1].lumen.points[5].x
+    pair = PyGeometryPair(g, geom("sys", 0.1), "dia - sys")
+    assert repr(pair) == "GeometryPair dia - sys (diastolic: 3 frames, systolic: 3 frames)"
+    (dia, sys_), table = pair.get_summary()
+    assert dia == g.get_summary() and len(table) == 3 and len(table[0]) == 6
+    assert table[1][0] == 1.0 and table[1][1] == g.frames[1].lumen.get_area() and table[2][5] == 2.0
+    out = capsys.readouterr().out.splitlines()
+    assert out[1].replace(" ", "") == "|id|area_dia|ellip_dia|area_sys|ellip_sys|z|" and out[0].startswith("+----+")
