@@ -274,7 +274,8 @@ int mmrs_export_pair(mmrs_ctx* ctx, const double* blob_a, int64_t len_a, const d
                      int32_t watertight, const int32_t* kinds, int32_t n_kinds);
 /* One geometry, no UV coordinates. naming 0: the export of single_processing_rs
  * (binding/entry.rs:741-818, files "{type}_{name}.obj/.mtl"); naming 1:
- * to_object::write_single_geometry (process.rs:63-121, files "{name}_{type}.obj/.mtl").      */
+ * to_object::write_single_geometry (process.rs:63-121, files "{name}_{type}.obj/.mtl"); naming 2: the to_obj
+ * entry point (binding/functions.rs:1435-1501, files "{name}_{type}" or, for an empty name, "{type}").        */
 int mmrs_export_single(mmrs_ctx* ctx, const double* blob, int64_t len, const char* name, const char* output_dir,
                        int32_t watertight, const int32_t* kinds, int32_t n_kinds, int32_t naming);
 

@@ -1805,7 +1805,7 @@ extern "C" int mmrs_export_pair(mmrs_ctx* ctx, const double* blob_a, int64_t len
 extern "C" int mmrs_export_single(mmrs_ctx* ctx, const double* blob, int64_t len, const char* name,
                                   const char* output_dir, int32_t watertight, const int32_t* kinds, int32_t n_kinds,
                                   int32_t naming) {
-    if (!blob || !name || !output_dir || (n_kinds > 0 && !kinds) || (naming != 0 && naming != 1))
+    if (!blob || !name || !output_dir || (n_kinds > 0 && !kinds) || (naming < 0 || naming > 2))
         return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_export_single: bad arguments");
     return guarded(ctx, [&] {
         export_single(decode(blob, len), name, output_dir, watertight != 0, kinds_vec(kinds, n_kinds), naming);

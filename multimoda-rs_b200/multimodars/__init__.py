@@ -2,7 +2,8 @@
 Hausdorff rotation-sweep path, running on B200 through libmmrs_b200.so."""
 from ._types import (PyCenterline, PyCenterlinePoint, PyContour, PyContourPoint, PyContourType, PyFrame, PyGeometry, PyGeometryPair, PyInputData,
                      PyRecord, numpy_to_inputdata)
-from ._processing import (align_combined, align_manual, align_three_point, from_array_doublepair, from_array_full, from_array_single,
+from ._converters import numpy_to_centerline, numpy_to_geometry, to_array
+from ._processing import (align_combined, align_manual, align_three_point, to_obj, from_array_doublepair, from_array_full, from_array_single,
                           from_array_singlepair, from_file_doublepair, from_file_full, from_file_single,
                           from_file_singlepair, get_context)
 from ._native import MmrsError

@@ -290,3 +290,11 @@ def align_combined(centerline, geometry, main_ref_pt, counterclockwise_ref_pt, c
                              cw_ref_pt=clockwise_ref_pt, angle_step_rad=angle_step_deg * rad, points=points,
                              angle_range_rad=angle_range_deg * rad, index_range=index_range,
                              align_wall_anomalous=align_wall_anomalous)
+
+
+def to_obj(geometry, output_path, watertight=True, contour_types=None, filename_prefix=""):
+    """binding/functions.rs:1435-1501: one OBJ (no UV coordinates) + MTL per requested contour type,
+    "{prefix}_{type}.obj" or "{type}.obj"; contour types a geometry does not carry are skipped with a warning."""
+    if not isinstance(geometry, PyGeometry):
+        raise TypeError("geometry must be a PyGeometry")
+    nat.export_single(geometry.to_blob(), str(filename_prefix), output_path, watertight, _kind_ids(contour_types), 2)
