@@ -72,6 +72,11 @@ def to_array(generic):
     raise TypeError(f"Unsupported type for to_array: {type(generic)}")
 
 
+def geometry_to_frames_array(geometry) -> dict:
+    """_converters.py:967-1015: {str(frame.id): {layer: (N, 4) array, ..., "reference": (0|1, 4) array}}."""
+    return {str(f.id): _frame_dict(f) for f in geometry.frames}
+
+
 def _numeric(arr, name):
     if arr is None:
         return np.zeros((0, 4), dtype=float)
