@@ -6,7 +6,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._types import (PyCenterline, PyContour, PyContourPoint, PyFrame, PyGeometry, PyGeometryPair, PyInputData)
+from ._types import (PyCenterline, PyContour, PyContourPoint, PyFrame, PyGeometry, PyGeometryPair, PyInputData,
+                     numpy_to_inputdata)  # noqa: F401  (the reference exports numpy_to_inputdata from this module)
 
 _LAYERS = ("lumen", "eem", "calcification", "sidebranch", "catheter", "wall")
 

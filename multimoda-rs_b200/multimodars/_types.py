@@ -605,9 +605,9 @@ class PyCenterlinePoint:
 
 
 class PyCenterline:
-    """src/types/binding/py_centerline.rs:8-60 (constructor, from_contour_points, __len__, points_as_tuples).
-    The branch editing helpers (calculate_branches, split/merge, resample, smooth, ...) belong to the CCTA
-    preprocessing side of the reference and are not part of this build."""
+    """src/types/binding/py_centerline.rs:8-330: constructor, from_contour_points, __len__, points_as_tuples and the
+    branch bookkeeping a raw centerline goes through before alignment (calculate_branches, find_sharp_angles, split /
+    merge / get_branch, remove_branch_overlap, trim_start, resample, smooth, orient_*; `_centerline.py`)."""
 
     def __init__(self, points):
         self.points = list(points)
@@ -635,21 +635,60 @@ class PyCenterline:
     def __len__(self):
         return len(self.points)
 
-    def __repr__(self):
-        n_br = len(self.branch_start_indices)
-        return f"Centerline(len={len(self.points)}, branches={n_br}, spacing=N/A)"
+    def __repr__(self):  # py_centerline.rs:66-73
+        from . import _centerline as c
+        return (f"Centerline(len={len(self.points)}, spacing={c.mean_spacing(self):.2f} mm, "
+                f"branches={len(self.branch_start_indices)})")
 
     __str__ = __repr__
 
     def points_as_tuples(self):
         return [(p.contour_point.x, p.contour_point.y, p.contour_point.z) for p in self.points]
 
-    def _ccta_side(self, *a, **k):
-        raise NotImplementedError("PyCenterline branch editing / resampling (py_centerline.rs:62-143) belongs to the "
-                                  "CCTA preprocessing side of the reference and is not part of this build (DESIGN.md §8)")
+    # Branch bookkeeping (py_centerline.rs:118-330): each returns a new PyCenterline, see _centerline.py.
+    def calculate_branches(self, spacing_tolerance=1.0):
+        from . import _centerline as c
+        return c.calculate_branches(self, float(spacing_tolerance))
 
-    calculate_branches = find_sharp_angles = split_branch = merge_branches = get_branch = remove_branch_overlap = \
-        trim_start = resample = smooth = orient_by_max_z = orient_to_reference = _ccta_side
+    def find_sharp_angles(self, branch_id, cos_threshold):
+        from . import _centerline as c
+        return c.find_sharp_angles(self, branch_id, float(cos_threshold))
+
+    def split_branch(self, branch_id, point_index):
+        from . import _centerline as c
+        return c.split_branch(self, branch_id, point_index)
+
+    def merge_branches(self, branch_id_a, branch_id_b):
+        from . import _centerline as c
+        return c.merge_branches(self, branch_id_a, branch_id_b)
+
+    def get_branch(self, branch_id):
+        from . import _centerline as c
+        return c.get_branch(self, branch_id)
+
+    def remove_branch_overlap(self):
+        from . import _centerline as c
+        return c.remove_branch_overlap(self)
+
+    def trim_start(self, mm):
+        from . import _centerline as c
+        return c.trim_start(self, float(mm))
+
+    def resample(self, spacing_mm):
+        from . import _centerline as c
+        return c.resample(self, float(spacing_mm))
+
+    def smooth(self, sigma):
+        from . import _centerline as c
+        return c.smooth(self, float(sigma))
+
+    def orient_by_max_z(self):
+        from . import _centerline as c
+        return c.orient_by_max_z(self)
+
+    def orient_to_reference(self, reference):
+        from . import _centerline as c
+        return c.orient_to_reference(self, reference)
 
     def _rows(self):
         """(n, 8) [x, y, z, tx, ty, tz, branch_id, radius] — the row layout of mmrs_align_centerline."""
@@ -716,18 +755,58 @@ class PyInputData:
         return out
 
 
+def _records_from_array(arr):
+    """_converters.py:301-356: rows [frame, phase, m1, m2] (plain, object or structured arrays; numeric phase 0 -> "D",
+    anything else numeric -> "S"; NaN / unparsable measurements -> None); empty -> None."""
+    if arr is None:
+        return None
+    arr = np.asarray(arr)
+    if arr.ndim == 1 and arr.dtype.names:
+        arr = np.array([tuple(r) for r in arr.tolist()], dtype=object).reshape(len(arr), -1)
+    if arr.size == 0:
+        return None
+    if arr.ndim == 1:
+        arr = arr.reshape(1, -1)
+
+    def opt(v):
+        try:
+            f = float(v)
+        except (TypeError, ValueError):
+            return None
+        return None if math.isnan(f) else f
+
+    recs = []
+    for row in arr:
+        ph = row[1] if len(row) > 1 else ""
+        if isinstance(ph, (bytes, bytearray)):
+            ph = ph.decode("utf-8", errors="replace")
+        elif isinstance(ph, (int, float, np.number)) and not isinstance(ph, bool):
+            ph = "D" if int(ph) == 0 else "S"
+        recs.append(PyRecord(int(row[0]), str(ph), opt(row[2]) if len(row) > 2 else None,
+                             opt(row[3]) if len(row) > 3 else None))
+    return recs or None
+
+
 def numpy_to_inputdata(lumen_arr, ref_point, diastole, record=None, eem_arr=None, calcification=None,
                        sidebranch=None, label=""):
     """multimodars/_converters.py:204-437 — (N,4) [frame, x, y, z] arrays -> PyInputData, one
-    PyContour per frame id, built from array slices (no per-point Python objects)."""
-    def num(a):
+    PyContour per frame id, built from array slices (no per-point Python objects). Like the reference: the frames
+    are the LUMEN's frame ids in ascending order, the other layers contribute only on those frames, layers without
+    a contour become None, an unusable `ref_point` falls back to (0, 0, 0) on frame 0."""
+    def num(a, name):
         if a is None:
-            return None
+            return np.zeros((0, 4))
+        a = np.asarray(a)
+        if a.ndim == 1 and a.dtype.names:
+            try:
+                a = np.vstack([a[n] for n in a.dtype.names]).T
+            except Exception:
+                raise ValueError(f"Could not convert structured array for {name}") from None
         a = np.asarray(a, dtype=float)
         return a.reshape(1, -1) if a.ndim == 1 else a
 
-    def contours(a, kind):
-        if a is None:
+    def contours(a, kind, keep):
+        if a.size == 0:
             return None
         out = []
         frames = a[:, 0].astype(np.int64)
@@ -736,26 +815,33 @@ def numpy_to_inputdata(lumen_arr, ref_point, diastole, record=None, eem_arr=None
         cuts = np.flatnonzero(np.diff(sf)) + 1
         for idx in np.split(order, cuts):
             sel = a[idx]
-            fid = int(sel[0, 0])
+            fid = int(frames[idx[0]])
+            if keep is not None and fid not in keep:
+                continue
             rows = np.zeros((len(sel), 6))
-            rows[:, 0] = sel[:, 0]
+            rows[:, 0] = fid
             rows[:, 1] = np.arange(len(sel))
             rows[:, 2:5] = sel[:, 1:4]
             out.append(PyContour(fid, fid, rows, (float(np.mean(sel[:, 1])), float(np.mean(sel[:, 2])),
                                                   float(np.mean(sel[:, 3]))), None, None, kind))
-        return out
+        return out or None
 
-    lumen_arr = num(lumen_arr)
-    if lumen_arr is None or lumen_arr.size == 0:
-        raise ValueError("lumen_arr is empty")
-    rp = np.asarray(ref_point, dtype=float).reshape(-1)
-    recs = None
-    if record is not None:
-        recs = []
-        for row in np.asarray(record, dtype=object).reshape(-1, 4):
-            m1 = None if row[2] is None or (isinstance(row[2], float) and math.isnan(row[2])) else float(row[2])
-            m2 = None if row[3] is None or (isinstance(row[3], float) and math.isnan(row[3])) else float(row[3])
-            recs.append(PyRecord(int(row[0]), str(row[1]), m1, m2))
-    return PyInputData(contours(lumen_arr, "Lumen"), contours(num(eem_arr), "Eem"),
-                       contours(num(calcification), "Calcification"), contours(num(sidebranch), "Sidebranch"), recs,
-                       PyContourPoint(int(rp[0]), 0, rp[1], rp[2], rp[3], False), diastole, label)
+    lumen_arr = num(lumen_arr, "lumen_arr")
+    eem_arr, calcification, sidebranch = num(eem_arr, "eem_arr"), num(calcification, "calcification"), num(sidebranch, "sidebranch")
+    ref = None
+    if ref_point is not None:
+        try:
+            rp = np.asarray(ref_point, dtype=float)
+            rp = rp[:4] if rp.ndim == 1 else rp[0, :4]
+            ref = PyContourPoint(int(rp[0]), 0, float(rp[1]), float(rp[2]), float(rp[3]), False)
+        except Exception:
+            ref = None
+    if ref is None:
+        ref = PyContourPoint(0, 0, 0.0, 0.0, 0.0, False)
+    if lumen_arr.size == 0:
+        raise ValueError("lumen_arr cannot be empty")
+    lumen = contours(lumen_arr, "Lumen", None)
+    keep = {c.id for c in lumen}
+    return PyInputData(lumen, contours(eem_arr, "Eem", keep), contours(calcification, "Calcification", keep),
+                       contours(sidebranch, "Sidebranch", keep), _records_from_array(record), ref, bool(diastole),
+                       label or "")
