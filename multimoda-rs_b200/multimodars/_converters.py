@@ -7,6 +7,7 @@ from __future__ import annotations
 import numpy as np
 
 from ._types import (PyCenterline, PyContour, PyContourPoint, PyFrame, PyGeometry, PyGeometryPair, PyInputData,
+                     PyRecord, _records_from_array,
                      numpy_to_inputdata)  # noqa: F401  (the reference exports numpy_to_inputdata from this module)
 
 _LAYERS = ("lumen", "eem", "calcification", "sidebranch", "catheter", "wall")
@@ -76,6 +77,94 @@ def to_array(generic):
 def geometry_to_frames_array(geometry) -> dict:
     """_converters.py:967-1015: {str(frame.id): {layer: (N, 4) array, ..., "reference": (0|1, 4) array}}."""
     return {str(f.id): _frame_dict(f) for f in geometry.frames}
+
+
+def array_to_pyinputdata(lumen=None, eem=None, calcification=None, sidebranch=None, records=None, reference=None,
+                         diastole=True, label=""):
+    """_converters.py:689-966: the inverse of `to_array(PyInputData)`. Layers are lists of PyContour (taken as they
+    are) or (N, 4) [frame, x, y, z] arrays grouped by ascending frame id; records are PyRecord lists, row lists, plain
+    or structured arrays; the reference point is the first non-zero row of `reference` ((0, 0, 0) on frame 0 if None)."""
+    def layer(v, kind):
+        if v is None:
+            return []
+        if isinstance(v, list) and v and hasattr(v[0], "points") and hasattr(v[0], "id"):
+            return v
+        a = np.asarray(v, dtype=object) if isinstance(v, (list, tuple)) else np.asarray(v)
+        if a.dtype.names:
+            try:
+                a = np.vstack([a[n] for n in a.dtype.names]).T
+            except Exception as e:
+                raise ValueError(f"Could not convert structured array for layer: {e}") from None
+        if a.size == 0:
+            return []
+        if a.ndim == 1:
+            if a.shape[0] != 4:
+                raise ValueError(f"layer 1D array must have length 4, got {a.shape}")
+            a = a[np.newaxis, :]
+        if a.ndim != 2 or a.shape[1] < 4:
+            raise ValueError(f"layer must be (N,4)-like, got shape {a.shape}")
+        a = a[:, :4].astype(float)
+        frames = a[:, 0].astype(np.int64)
+        out = []
+        for fid in np.unique(frames).tolist():
+            sel = a[frames == fid]
+            rows = np.zeros((len(sel), 6))
+            rows[:, 0] = fid
+            rows[:, 1] = np.arange(len(sel))
+            rows[:, 2:5] = sel[:, 1:4]
+            out.append(PyContour(fid, fid, rows, (float(np.mean(sel[:, 1])), float(np.mean(sel[:, 2])),
+                                                  float(np.mean(sel[:, 3]))), None, None, kind))
+        return out
+
+    def recs(r):
+        if r is None:
+            return None
+        if isinstance(r, (list, tuple)):
+            out = []
+            for item in r:
+                if hasattr(item, "frame") and hasattr(item, "phase"):
+                    out.append(item)
+                else:
+                    out.append(PyRecord(int(item[0]), str(item[1]),
+                                        None if len(item) < 3 or item[2] is None else float(item[2]),
+                                        None if len(item) < 4 or item[3] is None else float(item[3])))
+            return out
+        if isinstance(r, np.ndarray):
+            if r.dtype.names:
+                low = {n.lower(): n for n in r.dtype.names}
+                if "frame" not in low or "phase" not in low:
+                    raise ValueError("Structured records must contain 'frame' and 'phase'")
+                m1 = low.get("measurement_1", low.get("m1"))
+                m2 = low.get("measurement_2", low.get("m2"))
+                return [PyRecord(int(r[low["frame"]][i]), str(r[low["phase"]][i]),
+                                 None if m1 is None else float(r[m1][i]), None if m2 is None else float(r[m2][i]))
+                        for i in range(len(r))]
+            a = r[np.newaxis, :] if r.ndim == 1 else r
+
+            def opt(row, k):
+                v = row[k] if len(row) > k else None
+                return None if v is None or (isinstance(v, float) and np.isnan(v)) else float(v)
+
+            return [PyRecord(int(row[0]), str(row[1]), opt(row, 2), opt(row, 3)) for row in a]
+        raise ValueError("Unsupported records format")
+
+    if reference is None:
+        ref = PyContourPoint(0, 0, 0.0, 0.0, 0.0, False)
+    else:
+        a = np.asarray(reference)
+        if a.ndim == 1:
+            if a.shape[0] < 4:
+                raise ValueError("reference must be length 4 or shape (1,4)")
+            row = a[:4]
+        else:
+            if a.shape[1] < 4:
+                raise ValueError("reference must be (N,4)-like")
+            nz = np.any(a != 0, axis=1)
+            row = (a[nz][0] if np.any(nz) else a[0])[:4]
+        ref = PyContourPoint(int(row[0]), 0, float(row[1]), float(row[2]), float(row[3]), False)
+
+    return PyInputData(layer(lumen, "Lumen"), layer(eem, "Eem") or None, layer(calcification, "Calcification") or None,
+                       layer(sidebranch, "Sidebranch") or None, recs(records), ref, bool(diastole), str(label))
 
 
 def _numeric(arr, name):

@@ -12,6 +12,7 @@ import numpy as np
 
 from . import _native as nat
 from ._types import PyCenterline, PyContourType, PyGeometry, PyGeometryPair, PyInputData
+from ._vtp import read_centerline_vtp  # noqa: F401  (the reference defines it in _processing.py:1355)
 
 _ctx = None
 

@@ -29,11 +29,12 @@ class PyContourType(enum.Enum):
 
     @staticmethod
     def from_string(name: str) -> "PyContourType":
-        key = name.strip().lower()
+        key = name.lower()
         for t in PyContourType:
             if t.name.lower() == key:
                 return t
-        raise ValueError(f"Unknown contour type: {name}")
+        raise ValueError(f"Unknown contour type: '{name}'. Valid types are: lumen, eem, calcification, sidebranch, "
+                         "catheter, wall")
 
     @staticmethod
     def all_types():
@@ -41,6 +42,9 @@ class PyContourType(enum.Enum):
 
     def __str__(self):
         return self.name
+
+    def __repr__(self):  # py_contour.rs:357-359
+        return f"PyContourType.{self.name}"
 
 
 class PyContourPoint:

@@ -72,3 +72,63 @@ def test_to_obj_names_and_content(tmp_path):
     one = mm.PyGeometry(g.frames[:1], "one")
     with pytest.raises(mm.MmrsError, match="Failed to write lumen OBJ: .*Need at least two contours"):
         mm.to_obj(one, str(tmp_path / "x"))
+
+
+# ---- numpy_to_inputdata / array_to_pyinputdata (multimodars/_converters.py:204-437, 689-966) -------------------------
+def test_numpy_to_inputdata_reference_semantics():
+    from multimodars._converters import numpy_to_inputdata
+    lum = np.array([[3, 1.0, 2.0, 3.0], [1, 0.0, 0.0, 1.0], [3, 2.0, 2.0, 3.0], [1, 1.0, 1.0, 1.0]])
+    eem = np.array([[1, 9.0, 9.0, 1.0], [7, 5.0, 5.0, 5.0]])                 # frame 7 has no lumen: ignored
+    rec = np.array([(1, "D", 1.5, np.nan), (3, "S", np.nan, 2.5)],
+                   dtype=[("frame", "i4"), ("phase", "U1"), ("m1", "f8"), ("m2", "f8")])
+    inp = numpy_to_inputdata(lum, np.array([[3, 7.0, 8.0, 9.0]]), 1, record=rec, eem_arr=eem,
+                             calcification=np.zeros((0, 4)), label=None)
+    assert [c.id for c in inp.lumen] == [1, 3] and [len(c) for c in inp.lumen] == [2, 2]
+    assert [p.point_index for p in inp.lumen[1].points] == [0, 1] and inp.lumen[1].points[0].x == 1.0   # row order kept
+    assert inp.lumen[0].centroid == (0.5, 0.5, 1.0)
+    assert [c.id for c in inp.eem] == [1] and inp.calcification is None and inp.sidebranch is None
+    assert [(r.frame, r.phase, r.measurement_1, r.measurement_2) for r in inp.record] == [(1, "D", 1.5, None),
+                                                                                           (3, "S", None, 2.5)]
+    assert (inp.ref_point.frame_index, inp.ref_point.x, inp.ref_point.z) == (3, 7.0, 9.0)
+    assert inp.diastole is True and inp.label == ""
+    # numeric phases: 0 -> "D", anything else -> "S"; short rows leave the measurements empty
+    r = numpy_to_inputdata(lum, None, False, record=np.array([[1, 0], [3, 1]])).record
+    assert [(x.phase, x.measurement_1) for x in r] == [("D", None), ("S", None)]
+    # unusable reference point -> origin on frame 0; empty record array -> None
+    inp = numpy_to_inputdata(lum, np.array([1.0, 2.0]), True, record=np.zeros((0, 4)))
+    assert (inp.ref_point.frame_index, inp.ref_point.x) == (0, 0.0) and inp.record is None
+    with pytest.raises(ValueError, match="lumen_arr cannot be empty"):
+        numpy_to_inputdata(np.zeros((0, 4)), np.zeros(4), True)
+
+
+def test_array_to_pyinputdata_inverts_to_array():
+    from multimodars._converters import array_to_pyinputdata, numpy_to_inputdata, to_array
+    lum = np.array([[0, 1.0, 2.0, 3.0], [0, 2.0, 2.0, 3.0], [1, 5.0, 5.0, 5.0]])
+    side = np.array([[1, 4.0, 4.0, 5.0]])
+    inp = numpy_to_inputdata(lum, np.array([0, 9.0, 9.0, 9.0]), False, sidebranch=side, label="x",
+                             record=np.array([[0, "D", 1.0, None], [1, "S", None, 2.0]], dtype=object))
+    d = to_array(inp)
+    back = array_to_pyinputdata(d["lumen"], d["eem"], d["calcification"], d["sidebranch"], d["records"], d["reference"],
+                                d["diastole"], d["label"])
+    assert np.array_equal(to_array(back)["lumen"], lum) and np.array_equal(to_array(back)["sidebranch"], side)
+    assert back.eem is None and back.calcification is None and back.diastole is False and back.label == "x"
+    assert [(r.frame, r.phase, r.measurement_1, r.measurement_2) for r in back.record] == [(0, "D", 1.0, None),
+                                                                                            (1, "S", None, 2.0)]
+    assert (back.ref_point.frame_index, back.ref_point.x) == (0, 9.0)
+    # existing objects pass through untouched; row lists and structured records work; the first NON-ZERO reference row
+    same = array_to_pyinputdata(lumen=inp.lumen, records=[inp.record[0], (5, "S", 3.0)],
+                                reference=np.array([[0, 0, 0, 0], [2, 1.0, 1.0, 1.0]]))
+    assert same.lumen[0] is inp.lumen[0] and same.record[0] is inp.record[0]
+    assert (same.record[1].frame, same.record[1].measurement_1, same.record[1].measurement_2) == (5, 3.0, None)
+    assert same.ref_point.frame_index == 2 and same.diastole is True
+    st = np.array([(4, "D", 0.5)], dtype=[("Frame", "i4"), ("PHASE", "U1"), ("m1", "f8")])
+    r = array_to_pyinputdata(lumen=lum, records=st).record
+    assert (r[0].frame, r[0].phase, r[0].measurement_1, r[0].measurement_2) == (4, "D", 0.5, None)
+    assert array_to_pyinputdata(lumen=lum).ref_point.x == 0.0
+    for bad, msg in ((np.array([1.0, 2.0, 3.0]), "1D array must have length 4"), (np.zeros((2, 3)), r"must be \(N,4\)-like")):
+        with pytest.raises(ValueError, match=msg):
+            array_to_pyinputdata(lumen=bad)
+    with pytest.raises(ValueError, match="reference must be length 4"):
+        array_to_pyinputdata(lumen=lum, reference=np.zeros(3))
+    with pytest.raises(ValueError, match="Unsupported records format"):
+        array_to_pyinputdata(lumen=lum, records="nope")
