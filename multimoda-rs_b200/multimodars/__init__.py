@@ -8,5 +8,6 @@ from ._processing import (align_combined, align_manual, align_three_point, to_ob
                           from_file_singlepair, get_context)
 from ._native import MmrsError
 from ._vtp import read_centerline_vtp
+from ._centerline import load_centerline, prepare_centerline
 
 __all__ = [n for n in dir() if not n.startswith("_")]

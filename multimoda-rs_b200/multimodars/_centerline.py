@@ -456,3 +456,45 @@ def smooth(cl, sigma):
 
 def _copy(cl):
     return _make([_clone_point(p) for p in cl.points], cl.branch_start_indices)
+
+
+# ---- loading and the standard preparation chain (multimodars/ccta/centerline_prep.py:10-140) ------------------------
+def load_centerline(source, name):
+    """A PyCenterline (returned as it is), an (N, 3) array, a `.vtp` path or a comma-separated x,y,z file ->
+    PyCenterline, not yet prepared. `name` only labels the progress line, as in the reference."""
+    from ._converters import numpy_to_centerline
+    from ._vtp import read_centerline_vtp
+    t = _types()
+    if isinstance(source, t.PyCenterline):
+        cl, how = source, f"Using provided {name} centerline"
+    elif isinstance(source, np.ndarray):
+        cl, how = numpy_to_centerline(source), f"Using provided {name} centerline"
+    else:
+        is_vtp = str(source).lower().endswith(".vtp")
+        try:
+            cl = read_centerline_vtp(str(source)) if is_vtp else numpy_to_centerline(np.genfromtxt(source, delimiter=","))
+        except Exception as e:
+            print(f"Error reading {name} centerline from {source}: {e}")
+            raise
+        how = f"Loaded {name} centerline from VTP" if is_vtp else f"Loaded {name} centerline"
+    print(f"{how}: {len(cl.points)} points")
+    return cl
+
+
+def prepare_centerline(centerline, ref_centerline=None, spacing_mm=None, branch_spacing_tolerance=2.0, rm_start_mm=0.0,
+                       smooth_sigma=2.5):
+    """Branch detection (only for a coronary, i.e. when a reference is given, that has no branch structure yet) ->
+    overlap removal -> optional inlet trim -> optional resampling -> orientation (towards the reference's branch 0, or
+    highest z first without one) -> optional smoothing."""
+    cl = centerline
+    if ref_centerline is not None and len(cl.branch_start_indices) <= 1:
+        cl = calculate_branches(cl, branch_spacing_tolerance)
+    cl = remove_branch_overlap(cl)
+    if rm_start_mm > 0:
+        cl = trim_start(cl, rm_start_mm)
+    if spacing_mm:
+        cl = resample(cl, spacing_mm)
+    cl = orient_to_reference(cl, ref_centerline) if ref_centerline is not None else orient_by_max_z(cl)
+    if smooth_sigma > 0:
+        cl = smooth(cl, smooth_sigma)
+    return cl

@@ -295,3 +295,33 @@ def test_rca_pipeline_keeps_invariants(rca):
     for br in branches(cl):
         d = np.diff(np.array([(p.contour_point.x, p.contour_point.y, p.contour_point.z) for p in br]), axis=0)
         assert len(br) >= 2 and np.all(np.linalg.norm(d, axis=1) < 1.0 + 1e-9)
+
+
+def test_load_and_prepare(rca, tmp_path, capsys):
+    """multimodars/ccta/centerline_prep.py:10-140."""
+    import multimodars as mm
+    xyz = np.load(GOLDEN / "centerline_rca_short.npz")["xyz"]
+    assert mm.load_centerline(rca, "RCA") is rca
+    from_arr = mm.load_centerline(xyz, "RCA")
+    p = tmp_path / "cl.csv"
+    np.savetxt(p, xyz, delimiter=",", fmt="%.17g")
+    from_csv = mm.load_centerline(p, "RCA")
+    assert from_csv.points_as_tuples() == from_arr.points_as_tuples() == rca.points_as_tuples()
+    out = capsys.readouterr().out.splitlines()
+    assert out == ["Using provided RCA centerline: 788 points", "Using provided RCA centerline: 788 points",
+                   "Loaded RCA centerline: 788 points"]
+    with pytest.raises(Exception):
+        mm.load_centerline(tmp_path / "missing.csv", "LCA")
+    assert "Error reading LCA centerline from" in capsys.readouterr().out
+
+    aorta = line([(0, 0, 100 + 0.5 * i) for i in range(40)])
+    ao = mm.prepare_centerline(aorta)                        # no reference: no branch search, highest z first
+    assert ao.branch_start_indices == [0] and ao.points[0].contour_point.z > ao.points[-1].contour_point.z
+    want = rca.calculate_branches(2.0).remove_branch_overlap().trim_start(3.0).resample(0.5).orient_to_reference(ao).smooth(2.5)
+    got = mm.prepare_centerline(rca, ref_centerline=ao, spacing_mm=0.5, rm_start_mm=3.0)
+    assert got.points_as_tuples() == want.points_as_tuples() and got.branch_start_indices == want.branch_start_indices
+    assert [p.tangent for p in got.points] == [p.tangent for p in want.points]
+    # an already branched centerline is not searched again; sigma 0 and no spacing skip those steps
+    pre = rca.calculate_branches(2.0)
+    kept = mm.prepare_centerline(pre, ref_centerline=ao, smooth_sigma=0.0)
+    assert kept.points_as_tuples() == pre.remove_branch_overlap().orient_to_reference(ao).points_as_tuples()
