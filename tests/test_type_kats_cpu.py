@@ -1,0 +1,111 @@
+"""Known answers of the reference's Rust unit tests for its value types, held against the Python value types of this
+package (multimodars/_types.py): types/native/contour.rs:606-1040, types/native/frame.rs:214-640 (through the
+PyFrame surface: degrees, about the frame centroid — py_frame.rs:90-116)."""
+import math
+
+import pytest
+
+from multimodars import PyContour, PyContourPoint, PyFrame, PyGeometry
+
+
+def contour(xy, cid=1, centroid=None, kind="Lumen", z=0.0):
+    pts = [PyContourPoint(cid, i, float(x), float(y), z, False) for i, (x, y) in enumerate(xy)]
+    return PyContour(cid, cid, pts, centroid, None, None, kind)
+
+
+def xy(c):
+    return [(p.x, p.y) for p in c.points]
+
+
+def test_compute_centroid():  # contour.rs:606-654
+    c = contour([(0, 0), (2, 0), (2, 2), (0, 2)])
+    c.compute_centroid()
+    assert c.centroid == (1.0, 1.0, 0.0)
+
+
+def test_farthest_points():  # contour.rs:657-707
+    (a, b), d = contour([(0, 0), (2, 0), (2, 2), (0, 2)], centroid=(1.0, 1.0, 0.0)).find_farthest_points()
+    assert abs(d - math.sqrt(8.0)) < 1e-6
+    assert {(a.x, a.y), (b.x, b.y)} == {(0.0, 0.0), (2.0, 2.0)}
+
+
+def test_closest_opposite():  # contour.rs:710-761
+    c = contour([(0, 1), (1, 0), (0, -0.5), (-1, 0)], centroid=(0.0, 0.125, 0.0))
+    (a, b), d = c.find_closest_opposite()
+    assert abs(d - 1.5) < 1e-6 and {a.point_index, b.point_index} == {0, 2}
+
+
+def test_sort_contour_points():  # contour.rs:764-831: highest y first, then counter-clockwise
+    s = contour([(-2, 0), (0, 2), (2, 0), (0, -2)], centroid=(0.0, 0.0, 0.0)).sort_contour_points()
+    assert xy(s) == [(0.0, 2.0), (-2.0, 0.0), (0.0, -2.0), (2.0, 0.0)]
+    assert [p.point_index for p in s.points] == [0, 1, 2, 3]
+
+
+def test_areas():  # contour.rs:834-972
+    assert abs(contour([(0, 0), (3, 0), (0, 4)]).get_area() - 6.0) < 1e-12
+    assert abs(contour([(0, 0), (2, 0), (2, 2), (0, 2)]).get_area() - 4.0) < 1e-12          # counter-clockwise
+    assert abs(contour([(0, 0), (0, 2), (2, 2), (2, 0)]).get_area() - 4.0) < 1e-12          # clockwise: same
+    assert contour([(0, 0), (1, 1)]).get_area() == 0.0 and contour([(0, 0)]).get_area() == 0.0
+
+
+def test_elliptic_ratio_and_area():  # contour.rs:983-1040
+    c = contour([(1, 0), (0, 2), (1, 4), (2, 2)], centroid=(1.0, 2.0, 0.0))
+    assert abs(c.get_elliptic_ratio() - 2.0) < 1e-6 and abs(c.get_area() - 4.0) < 1e-6
+
+
+def test_contour_rotate_translate_leave_the_original():  # py_contour.rs:216-262
+    c = contour([(1, 0), (0, 1), (-1, 0), (0, -1)], centroid=(0.0, 0.0, 0.0))
+    r = c.rotate(90.0)
+    assert xy(c) == [(1.0, 0.0), (0.0, 1.0), (-1.0, 0.0), (0.0, -1.0)]
+    for (x, y), (wx, wy) in zip(xy(r), [(0, 1), (-1, 0), (0, -1), (1, 0)]):
+        assert abs(x - wx) < 1e-12 and abs(y - wy) < 1e-12
+    t = c.translate(1.0, 2.0, 3.0)
+    assert [(p.x, p.y, p.z) for p in t.points] == [(2.0, 2.0, 3.0), (1.0, 3.0, 3.0), (0.0, 2.0, 3.0), (1.0, 1.0, 3.0)]
+    assert t.centroid == (0.0, 0.0, 0.0)          # Contour::translate moves the points only (contour.rs:60-66)
+
+
+def _frame():
+    lumen = contour([(0, 2), (2, 4), (4, 2), (2, 0)], 1, (2.0, 2.0, 0.0))
+    eem = contour([(-1, 2), (2, 5), (5, 2), (0, -1)], 2, None, "Eem")
+    return PyFrame(1, (1.0, 1.0, 0.0), lumen, {"Eem": eem}, PyContourPoint(1, 0, 0.0, 4.0, 0.0, False))
+
+
+def _extra(frame, kind):
+    return next(c for k, c in frame.extras.items() if str(k) == kind)
+
+
+def test_frame_rotate_with_eem_90deg():  # frame.rs:214-445: lumen, extras and reference point turn about frame.centroid
+    f = _frame()
+    r = f.rotate(90.0)
+    for got, want in ((xy(r.lumen), [(0, 0), (-2, 2), (0, 4), (2, 2)]),
+                      (xy(_extra(r, "Eem")), [(0, -1), (-3, 2), (0, 5), (3, 0)]),
+                      ([(r.reference_point.x, r.reference_point.y)], [(-2, 0)])):
+        for (x, y), (wx, wy) in zip(got, want):
+            assert abs(x - wx) < 1e-6 and abs(y - wy) < 1e-6
+    back = r.rotate(-90.0)
+    for got, want in ((xy(back.lumen), xy(f.lumen)), (xy(_extra(back, "Eem")), xy(_extra(f, "Eem"))),
+                      ([(back.reference_point.x, back.reference_point.y)], [(0.0, 4.0)])):
+        for (x, y), (wx, wy) in zip(got, want):
+            assert abs(x - wx) < 1e-6 and abs(y - wy) < 1e-6
+    assert xy(f.lumen) == [(0.0, 2.0), (2.0, 4.0), (4.0, 2.0), (2.0, 0.0)]                   # the input is untouched
+
+
+def test_frame_translate_with_eem_and_reference():  # frame.rs:555-695
+    lumen = contour([(0, 0), (2, 0), (2, 2), (0, 2)], 1, (1.0, 1.0, 0.0))
+    eem = contour([(-1, 2), (2, 5), (5, 2), (0, -1)], 2, None, "Eem")
+    f = PyFrame(1, (1.0, 1.0, 0.0), lumen, {"Eem": eem}, PyContourPoint(1, 0, 0.5, -0.5, 0.0, False))
+    t = f.translate(1.0, 2.0, 3.0)
+    assert t.centroid == (2.0, 3.0, 3.0)
+    assert [(p.x, p.y, p.z) for p in t.lumen.points] == [(1.0, 2.0, 3.0), (3.0, 2.0, 3.0), (3.0, 4.0, 3.0), (1.0, 4.0, 3.0)]
+    assert [(p.x, p.y, p.z) for p in _extra(t, "Eem").points] == [(0.0, 4.0, 3.0), (3.0, 7.0, 3.0), (6.0, 4.0, 3.0),
+                                                                   (1.0, 1.0, 3.0)]
+    rp = t.reference_point
+    assert (rp.x, rp.y, rp.z) == (1.5, 1.5, 3.0)
+    assert t.lumen.centroid == (2.0, 3.0, 3.0)                                               # recomputed, frame.rs:20
+
+
+def test_geometry_rotate_is_per_frame_and_a_copy():
+    g = PyGeometry([_frame()], "g")
+    r = g.rotate(90.0)
+    assert abs(r.frames[0].lumen.points[1].x + 2.0) < 1e-9 and g.frames[0].lumen.points[1].x == 2.0
+    assert r.label == "g" and len(r) == 1
