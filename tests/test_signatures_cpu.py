@@ -96,3 +96,29 @@ def test_instance_attributes():
     with pytest.raises(ValueError, match="Unknown contour type: 'x'. Valid types are: lumen, eem"):
         mm.PyContourType.from_string("x")
     assert np.isfinite(cl.points[0].radius)
+
+
+def test_native_module_names_and_defaults():
+    """`from multimodars.multimodars import ...` (the PyO3 module of the reference, src/lib.rs:25-102) resolves here, and
+    its entry points carry the Rust-level defaults: sample_size = 200 for from_array_* and from_file_single
+    (functions.rs:645, :810, :1021, :1196, :1339), write_obj = False only for from_array_single (:1343)."""
+    from multimodars import multimodars as native
+    for name in ("PyInputData", "PyContourPoint", "PyContour", "PyContourType", "PyFrame", "PyGeometry",
+                 "PyGeometryPair", "PyCenterlinePoint", "PyCenterline", "PyRecord"):          # lib.rs:90-99
+        assert getattr(native, name) is getattr(mm, name)
+    want = {"from_file_full": (500, True), "from_file_doublepair": (500, True), "from_file_singlepair": (500, True),
+            "from_file_single": (200, True), "from_array_full": (200, True), "from_array_doublepair": (200, True),
+            "from_array_singlepair": (200, True), "from_array_single": (200, False)}
+    for name, (sample, write) in want.items():
+        p = inspect.signature(getattr(native, name)).parameters
+        assert (p["sample_size"].default, p["write_obj"].default) == (sample, write), name
+        assert list(p) == list(inspect.signature(getattr(mm, name)).parameters), name
+    for name in ("align_three_point", "align_manual", "align_combined", "to_obj"):
+        assert getattr(native, name) is getattr(mm, name)
+    assert list(inspect.signature(native.read_centerline_vtp).parameters) == ["path"]     # functions.rs:1541
+    # the replaced default really reaches the call: the wrapper raises its own TypeError for a non-PyInputData
+    # argument only after binding, so a bad keyword is still refused with the native parameter list
+    with pytest.raises(TypeError):
+        native.from_array_single("not input data", sample=3)
+    import multimodars._processing as proc
+    assert native.from_array_single.__wrapped__ is proc.from_array_single
