@@ -486,18 +486,97 @@ bool row_to_point(const std::vector<std::string>& f, RawPoint& p) {
     }
     return true;
 }
+// Contour files are the bulk of from_file_* wall time (10 000 rows of 16-digit decimals per pullback phase), so they are
+// parsed in place: the file is read once, rows and fields are [begin, end) views, numbers go through std::from_chars
+// (correctly rounded, like strtod). Anything a view cannot decide exactly like the general path above — a '\r' inside
+// a row, a number that is not plain decimal — is handed to that path, so both accept and produce the same rows.
+struct View {
+    const char *b, *e;
+    size_t size() const { return (size_t)(e - b); }
+};
+inline View strip_view(View v) {
+    auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; };
+    while (v.b < v.e && ws(*v.b)) ++v.b;
+    while (v.e > v.b && ws(v.e[-1])) --v.e;
+    return v;
+}
+inline bool view_to_u32(View v, uint32_t& out) {
+    if (v.size() == 0 || v.size() > 10) return v.size() != 0 && to_u32(std::string(v.b, v.e), out);
+    uint64_t t = 0;
+    for (const char* p = v.b; p < v.e; ++p) {
+        if (*p < '0' || *p > '9') return false;
+        t = t * 10 + (uint64_t)(*p - '0');
+    }
+    if (t > 0xffffffffull) return false;
+    out = (uint32_t)t;
+    return true;
+}
+inline bool view_to_f64(View v, double& out) {
+    if (v.size() == 0) return false;
+    bool plain = true;
+    for (const char* p = v.b; p < v.e; ++p)
+        plain &= (*p >= '0' && *p <= '9') || *p == '.' || *p == '-' || *p == 'e' || *p == 'E';
+    if (plain) {
+        const auto r = std::from_chars(v.b, v.e, out);
+        if (r.ec == std::errc() && r.ptr == v.e) return true;
+    }
+    return to_f64(std::string(v.b, v.e), out);  // "+1.5", "1e+3", "inf", out-of-range ...: strtod decides, as before
+}
 std::vector<RawPoint> read_points(const std::string& path) {  // input.rs:172-194
     const char d = sniff(path);
-    std::ifstream f(path);
+    std::string buf;
+    {
+        std::ifstream f(path, std::ios::binary);
+        f.seekg(0, std::ios::end);
+        const std::streamoff n = f.tellg();
+        f.seekg(0, std::ios::beg);
+        if (n > 0) {
+            buf.resize((size_t)n);
+            f.read(&buf[0], n);
+            buf.resize((size_t)f.gcount());
+        }
+    }
     std::vector<RawPoint> out;
-    std::string line;
+    out.reserve(buf.size() / 40 + 16);
     size_t width = 0;
-    while (std::getline(f, line)) {
-        if (strip(line).empty()) continue;
-        auto fl = fields_of(line, d);
-        if (!width) width = fl.size();
-        RawPoint p;
-        if (fl.size() == width && row_to_point(fl, p)) out.push_back(p);
+    const char* p = buf.data();
+    const char* const end = p + buf.size();
+    while (p < end) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        View line{p, nl ? nl : end};
+        p = nl ? nl + 1 : end;
+        if (strip_view(line).size() == 0) continue;
+        if (line.e > line.b && line.e[-1] == '\r') --line.e;
+        RawPoint pt;
+        size_t nf = 0;
+        bool ok;
+        if (std::memchr(line.b, '\r', line.size())) {  // fields_of drops a '\r' wherever it stands: general path
+            const auto fl = fields_of(std::string(line.b, line.e), d);
+            nf = fl.size();
+            ok = row_to_point(fl, pt);
+        } else {
+            View f[5];
+            const char* q = line.b;
+            for (;;) {
+                const char* sep = (const char*)std::memchr(q, d, (size_t)(line.e - q));
+                if (nf < 5) f[nf] = strip_view(View{q, sep ? sep : line.e});
+                ++nf;
+                if (!sep) break;
+                q = sep + 1;
+            }
+            ok = (nf == 4 || nf == 5) && view_to_u32(f[0], pt.frame) && view_to_f64(f[1], pt.x) &&
+                 view_to_f64(f[2], pt.y) && view_to_f64(f[3], pt.z);
+            pt.aortic = false;
+            if (ok && nf == 5) {
+                const size_t n = f[4].size();
+                if (n == 4 && std::memcmp(f[4].b, "true", 4) == 0)
+                    pt.aortic = true;
+                else if (!(n == 5 && std::memcmp(f[4].b, "false", 5) == 0))
+                    ok = false;
+            }
+        }
+        if (!width) width = nf;
+        if (nf == width && ok) out.push_back(pt);
     }
     return out;
 }

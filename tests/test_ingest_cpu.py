@@ -69,3 +69,58 @@ def test_argument_errors_follow_the_reference():
         mm.from_file_full("does/not/exist/a", "does/not/exist/b")
     with pytest.raises(TypeError):          # binding/align.rs:151
         mm.align_three_point(None, None, None, None, None)
+
+
+def _write_case(d, rows, delim="\t", eol="\n", header=None, extra_blank=False):
+    d.mkdir(parents=True, exist_ok=True)
+    for phase in ("diastolic", "systolic"):
+        with open(d / f"{phase}_contours.csv", "w", newline="") as f:
+            if header:
+                f.write(header + eol)
+            for k, r in enumerate(rows):
+                f.write(delim.join(r) + eol)
+                if extra_blank and k % 7 == 3:
+                    f.write("  " + eol)
+        with open(d / f"{phase}_reference_points.csv", "w", newline="") as f:
+            f.write(delim.join(["1", "3.5", "2.0", "0.5"]) + eol)
+    return d
+
+
+@pytest.mark.parametrize("variant", ["tab", "comma_crlf", "header_blank", "aortic_column", "number_forms", "bad_rows",
+                                     "no_trailing_newline"])
+def test_contour_file_dialects_match_oracle(tmp_path, variant):
+    """The in-place contour-file reader (csrc/mmrs_host.cpp read_points) against the oracle's line-by-line reader on the
+    file dialects io/input.rs:149-194 accepts: tab or comma, CRLF, a header row, blank lines, a fifth true/false
+    column, exponent / signed / padded numbers, rows that fail to parse (dropped) or have another width (dropped)."""
+    import math
+    n = 12
+    pts = [[(2.0 + 0.25 * f) * math.cos(2 * math.pi * k / n) + 3.0, (1.5 + 0.25 * f) * math.sin(2 * math.pi * k / n) + 3.0,
+            0.5 * f] for f in range(3) for k in range(n)]
+    fr = [f for f in range(3) for _ in range(n)]
+    rows = [[str(f), repr(x), repr(y), repr(z)] for f, (x, y, z) in zip(fr, pts)]
+    kw = {}
+    if variant == "comma_crlf":
+        kw = dict(delim=",", eol="\r\n")
+    elif variant == "header_blank":
+        kw = dict(header="frame\tx\ty\tz", extra_blank=True)
+    elif variant == "aortic_column":
+        rows = [r + ["true" if i % 2 else "false"] for i, r in enumerate(rows)]
+    elif variant == "number_forms":
+        forms = [lambda v: f"{v:.6e}", lambda v: f"+{v:.9f}", lambda v: f"  {v:.12f} ", lambda v: f"{v:.5E}",
+                 lambda v: f"{v * 1000:.3f}e-3", lambda v: f"{v:.4f}".lstrip("0") if 0 < v < 1 else f"{v:.4f}"]
+        rows = [[f"0{f}"] + [forms[(i + j) % len(forms)](v) for j, v in enumerate(p)] for i, (f, p) in enumerate(zip(fr, pts))]
+    elif variant == "bad_rows":
+        rows = rows[:5] + [["1", "abc", "2.0", "0.5"], ["-1", "1.0", "2.0", "0.5"], ["1", "1.0", "2.0"],
+                           ["1", "1.0", "2.0", "0.5", "maybe"], ["1.5", "1.0", "2.0", "0.5"], ["1", "", "2.0", "0.5"],
+                           ["99999999999", "1.0", "2.0", "0.5"]] + rows[5:]
+    elif variant == "no_trailing_newline":
+        d = _write_case(tmp_path / variant, rows)
+        for phase in ("diastolic", "systolic"):
+            p = d / f"{phase}_contours.csv"
+            p.write_text(p.read_text().rstrip("\n"))
+    d = _write_case(tmp_path / variant, rows, **kw) if variant != "no_trailing_newline" else tmp_path / variant
+    got = nat.geometry_from_dir(d, "x", True)
+    want = ora.build_geometry_from_dir(d, "x", True)
+    assert np.array_equal(got, want)
+    g = mm.PyGeometry.from_blob(got, "x")
+    assert len(g.frames) == 3 and all(len(f.lumen) == n for f in g.frames)
