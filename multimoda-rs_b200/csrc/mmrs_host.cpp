@@ -78,8 +78,8 @@ struct Trace {
 // Host-side parallelism over independent geometries (the reference runs its 4 pullbacks in a
 // crossbeam scope, binding/entry.rs:140-203). The first exception wins and is rethrown.
 template <class F>
-void parallel_for(size_t n, F&& f) {
-    const size_t nt = std::min<size_t>(n, std::max(1u, std::thread::hardware_concurrency()));
+void parallel_for(size_t n, F&& f, size_t max_threads = ~(size_t)0) {
+    const size_t nt = std::min(max_threads, std::min<size_t>(n, std::max(1u, std::thread::hardware_concurrency())));
     if (nt <= 1) {
         for (size_t i = 0; i < n; ++i) f(i);
         return;
@@ -182,11 +182,11 @@ struct Contour {
         }
     }
     void permute(const std::vector<size_t>& order) {
-        Contour t = *this;
-        for (size_t i = 0; i < order.size(); ++i) {
-            const size_t s = order[i];
-            fi[i] = t.fi[s], pi[i] = t.pi[s], x[i] = t.x[s], y[i] = t.y[s], z[i] = t.z[s], ao[i] = t.ao[s];
-        }
+        auto apply = [&](auto& v) {
+            auto t = v;
+            for (size_t i = 0; i < order.size(); ++i) v[i] = t[order[i]];
+        };
+        apply(fi), apply(pi), apply(x), apply(y), apply(z), apply(ao);
     }
     // Contour::sort_contour_points, contour.rs:368-405: stable ascending atan2 about the
     // mean, the LAST highest-y point rotated to the front, point_index = position.
@@ -199,11 +199,11 @@ struct Contour {
             sy = sy + y[i];
         }
         const double mx = sx / (double)n, my = sy / (double)n;
-        std::vector<double> key(n);
-        for (size_t i = 0; i < n; ++i) key[i] = std::atan2(y[i] - my, x[i] - mx);
+        std::vector<std::pair<double, size_t>> keyed(n);
+        for (size_t i = 0; i < n; ++i) keyed[i] = {std::atan2(y[i] - my, x[i] - mx), i};
+        std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
         std::vector<size_t> order(n);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key[a] < key[b]; });
+        for (size_t i = 0; i < n; ++i) order[i] = keyed[i].second;
         size_t start = 0;
         for (size_t i = 1; i < n; ++i)
             if (!(y[order[i]] < y[order[start]])) start = i;
@@ -334,41 +334,59 @@ Contour read_contour(Reader& r) {
     }
     return c;
 }
+Frame read_frame(Reader& r) {
+    Frame f;
+    f.id = (uint32_t)r.get();
+    f.c[0] = r.get(), f.c[1] = r.get(), f.c[2] = r.get();
+    f.has_ref = r.get() != 0.0;
+    f.ref.fi = (uint32_t)r.get(), f.ref.pi = (uint32_t)r.get();
+    f.ref.x = r.get(), f.ref.y = r.get(), f.ref.z = r.get();
+    f.ref.ao = r.get() != 0.0;
+    const size_t nc = (size_t)r.get();
+    for (size_t q = 0; q < nc; ++q) {
+        Contour c = read_contour(r);
+        if (q == 0)
+            f.lumen = std::move(c);
+        else
+            f.extras[c.kind] = std::move(c);
+    }
+    return f;
+}
+// Big geometries (OCT-resolution pullbacks are ~100 MB of blob) are decoded / encoded frame-parallel: the work is
+// first-touch page faults on fresh memory, which spread over threads. The frame boundaries come from the headers.
+constexpr size_t kParallelBlobDoubles = 1u << 17;
+constexpr size_t kBlobThreads = 8;
 Geometry decode(const double* data, int64_t len) {
     if (!data || len < 1) throw InputErr("geometry blob is empty");
     Reader r{data, data + len};
     Geometry g;
     const size_t nf = (size_t)r.get();
-    g.frames.reserve(nf);
-    for (size_t k = 0; k < nf; ++k) {
-        Frame f;
-        f.id = (uint32_t)r.get();
-        f.c[0] = r.get(), f.c[1] = r.get(), f.c[2] = r.get();
-        f.has_ref = r.get() != 0.0;
-        f.ref.fi = (uint32_t)r.get(), f.ref.pi = (uint32_t)r.get();
-        f.ref.x = r.get(), f.ref.y = r.get(), f.ref.z = r.get();
-        f.ref.ao = r.get() != 0.0;
-        const size_t nc = (size_t)r.get();
-        for (size_t q = 0; q < nc; ++q) {
-            Contour c = read_contour(r);
-            if (q == 0)
-                f.lumen = std::move(c);
-            else
-                f.extras[c.kind] = std::move(c);
-        }
-        g.frames.push_back(std::move(f));
+    if ((size_t)len < kParallelBlobDoubles || nf < 2 * kBlobThreads) {
+        g.frames.reserve(nf);
+        for (size_t k = 0; k < nf; ++k) g.frames.push_back(read_frame(r));
+        return g;
     }
+    std::vector<const double*> at(nf);
+    for (size_t k = 0; k < nf; ++k) {  // skip over frame k using the counts in its headers
+        at[k] = r.p;
+        if (r.e - r.p < 12) throw InputErr("geometry blob truncated");
+        const size_t nc = (size_t)r.p[11];
+        r.p += 12;
+        for (size_t q = 0; q < nc; ++q) {
+            if (r.e - r.p < 12) throw InputErr("geometry blob truncated");
+            const size_t n = (size_t)r.p[11];
+            if ((size_t)(r.e - r.p - 12) < 6 * n) throw InputErr("geometry blob truncated");
+            r.p += 12 + 6 * n;
+        }
+    }
+    g.frames.resize(nf);
+    parallel_for(nf, [&](size_t k) {
+        Reader rk{at[k], r.e};
+        g.frames[k] = read_frame(rk);
+    }, kBlobThreads);
     return g;
 }
 size_t contour_doubles(const Contour& c) { return 12 + 6 * c.size(); }
-size_t geometry_doubles(const Geometry& g) {
-    size_t n = 1;
-    for (auto& f : g.frames) {
-        n += 12 + contour_doubles(f.lumen);
-        for (auto& kv : f.extras) n += contour_doubles(kv.second);
-    }
-    return n;
-}
 double* write_contour(double* w, const Contour& c) {
     const double h[12] = {(double)c.kind, (double)c.id,        (double)c.original_frame, c.has_c ? 1.0 : 0.0,
                           c.has_c ? c.c[0] : 0.0, c.has_c ? c.c[1] : 0.0, c.has_c ? c.c[2] : 0.0, c.has_at ? 1.0 : 0.0,
@@ -387,21 +405,34 @@ double* write_contour(double* w, const Contour& c) {
     return w;
 }
 // Encodes straight into a malloc'ed buffer (what the C ABI hands out; release with mmrs_free).
+double* write_frame(double* w, const Frame& f) {
+    const double h[12] = {(double)f.id, f.c[0], f.c[1], f.c[2], f.has_ref ? 1.0 : 0.0,
+                          f.has_ref ? (double)f.ref.fi : 0.0, f.has_ref ? (double)f.ref.pi : 0.0,
+                          f.has_ref ? f.ref.x : 0.0, f.has_ref ? f.ref.y : 0.0, f.has_ref ? f.ref.z : 0.0,
+                          (f.has_ref && f.ref.ao) ? 1.0 : 0.0, (double)(1 + f.extras.size())};
+    std::memcpy(w, h, sizeof h);
+    w += 12;
+    w = write_contour(w, f.lumen);
+    for (auto& kv : f.extras) w = write_contour(w, kv.second);
+    return w;
+}
 double* encode_malloc(const Geometry& g, int64_t* len_out) {
-    const size_t n = geometry_doubles(g);
+    const size_t nf = g.frames.size();
+    std::vector<size_t> at(nf + 1);
+    at[0] = 1;
+    for (size_t k = 0; k < nf; ++k) {
+        size_t n = 12 + contour_doubles(g.frames[k].lumen);
+        for (auto& kv : g.frames[k].extras) n += contour_doubles(kv.second);
+        at[k + 1] = at[k] + n;
+    }
+    const size_t n = at[nf];
     double* base = (double*)std::malloc(n * sizeof(double));
     if (!base) throw std::bad_alloc();
-    double* w = base;
-    *w++ = (double)g.frames.size();
-    for (auto& f : g.frames) {
-        const double h[12] = {(double)f.id, f.c[0], f.c[1], f.c[2], f.has_ref ? 1.0 : 0.0,
-                              f.has_ref ? (double)f.ref.fi : 0.0, f.has_ref ? (double)f.ref.pi : 0.0,
-                              f.has_ref ? f.ref.x : 0.0, f.has_ref ? f.ref.y : 0.0, f.has_ref ? f.ref.z : 0.0,
-                              (f.has_ref && f.ref.ao) ? 1.0 : 0.0, (double)(1 + f.extras.size())};
-        std::memcpy(w, h, sizeof h);
-        w += 12;
-        w = write_contour(w, f.lumen);
-        for (auto& kv : f.extras) w = write_contour(w, kv.second);
+    base[0] = (double)nf;
+    if (n < kParallelBlobDoubles || nf < 2 * kBlobThreads) {
+        for (size_t k = 0; k < nf; ++k) write_frame(base + at[k], g.frames[k]);
+    } else {
+        parallel_for(nf, [&](size_t k) { write_frame(base + at[k], g.frames[k]); }, kBlobThreads);
     }
     *len_out = (int64_t)n;
     return base;
@@ -426,12 +457,33 @@ struct Rec {
     bool has1, has2;
     double m1, m2;
 };
+// Read-only rows of one layer: rows parsed from a file, or the caller's (n, 4) [frame, x, y, z] f64 array as it is
+// (mmrs_geometry_from_arrays borrows it: no intermediate copy of a 2-million-point pullback).
+struct Points {
+    const RawPoint* raw = nullptr;
+    const double* rows = nullptr;
+    size_t n = 0;
+    size_t size() const { return n; }
+    uint32_t frame(size_t i) const { return raw ? raw[i].frame : (uint32_t)rows[4 * i]; }
+    double x(size_t i) const { return raw ? raw[i].x : rows[4 * i + 1]; }
+    double y(size_t i) const { return raw ? raw[i].y : rows[4 * i + 2]; }
+    double z(size_t i) const { return raw ? raw[i].z : rows[4 * i + 3]; }
+    bool aortic(size_t i) const { return raw ? raw[i].aortic : false; }
+};
 struct Input {
     std::vector<RawPoint> lumen;
     bool has_eem = false, has_calc = false, has_side = false, has_rec = false;
     std::vector<RawPoint> eem, calc, side;
+    Points a_lumen, a_eem, a_calc, a_side;  // set instead of the vectors by the array entry point
     std::vector<Rec> rec;
     RawPoint ref{};
+    static Points of(const std::vector<RawPoint>& v, const Points& a) {
+        return a.rows ? a : Points{v.data(), nullptr, v.size()};
+    }
+    Points lumen_pts() const { return of(lumen, a_lumen); }
+    Points eem_pts() const { return of(eem, a_eem); }
+    Points calc_pts() const { return of(calc, a_calc); }
+    Points side_pts() const { return of(side, a_side); }
 };
 
 std::string strip(const std::string& s) {
@@ -705,25 +757,59 @@ void integrity(const Geometry& g) {  // integrity_check.rs:8-247
 
 Geometry build_geometry(const Input& in, const std::string& label, bool diastole, double icx, double icy, double radius,
                         uint32_t n_points) {  // build.rs:9-205
+    Trace tr;
+    // Rows of one frame are consecutive in every input we have seen, so the per-point map / set work below is done
+    // once per RUN of equal frame ids (same result for any row order).
     std::set<uint32_t> seen;
-    for (auto& p : in.lumen) seen.insert(p.frame);
-    if (in.has_eem)
-        for (auto& p : in.eem) seen.insert(p.frame);
-    if (in.has_calc)
-        for (auto& p : in.calc) seen.insert(p.frame);
-    if (in.has_side)
-        for (auto& p : in.side) seen.insert(p.frame);
+    auto note = [&](const Points& pts) {
+        for (size_t i = 0; i < pts.size(); ++i)
+            if (i == 0 || pts.frame(i) != pts.frame(i - 1)) seen.insert(pts.frame(i));
+    };
+    note(in.lumen_pts());
+    if (in.has_eem) note(in.eem_pts());
+    if (in.has_calc) note(in.calc_pts());
+    if (in.has_side) note(in.side_pts());
     seen.insert(in.ref.frame);
     std::map<uint32_t, uint32_t> slot;  // original frame -> sequential id
     for (uint32_t f : seen) slot.emplace(f, (uint32_t)slot.size());
 
     // group by original frame (Contour::build_contour_with_mapping, contour.rs:158-211)
-    auto group = [&](const std::vector<RawPoint>& pts, int kind) {
+    auto group = [&](const Points& pts, int kind) {
         std::map<uint32_t, Contour> by;
-        for (auto& p : pts) {
-            Contour& c = by[p.frame];
-            c.push(p.frame, 0, p.x, p.y, p.z, p.aortic);
+        struct Run {
+            size_t i, j, at;
+        };
+        std::vector<std::pair<Contour*, std::vector<Run>>> jobs;  // map nodes do not move
+        std::map<uint32_t, size_t> job_of;
+        std::vector<size_t> total;
+        for (size_t i = 0; i < pts.size();) {  // one append per run of equal frame ids
+            size_t j = i + 1;
+            const uint32_t fr = pts.frame(i);
+            while (j < pts.size() && pts.frame(j) == fr) ++j;
+            auto it = job_of.find(fr);
+            if (it == job_of.end()) {
+                it = job_of.emplace(fr, jobs.size()).first;
+                jobs.push_back({&by[fr], {}});
+                total.push_back(0);
+            }
+            jobs[it->second].second.push_back(Run{i, j, total[it->second]});
+            total[it->second] += j - i;
+            i = j;
         }
+        auto fill = [&](size_t q) {
+            Contour& c = *jobs[q].first;
+            c.resize(total[q]);
+            for (const Run& r : jobs[q].second)
+                for (size_t k = r.i; k < r.j; ++k) {
+                    const size_t w = r.at + (k - r.i);
+                    c.fi[w] = pts.frame(k), c.pi[w] = 0, c.x[w] = pts.x(k), c.y[w] = pts.y(k), c.z[w] = pts.z(k);
+                    c.ao[w] = pts.aortic(k) ? 1 : 0;
+                }
+        };
+        if (pts.size() >= (1u << 15))
+            parallel_for(jobs.size(), fill, kBlobThreads);  // first-touch of fresh memory: spreads over threads
+        else
+            for (size_t q = 0; q < jobs.size(); ++q) fill(q);
         for (auto& kv : by) {
             auto s = slot.find(kv.first);
             if (s == slot.end()) throw InputErr("No mapping found for original frame " + std::to_string(kv.first));
@@ -733,9 +819,11 @@ Geometry build_geometry(const Input& in, const std::string& label, bool diastole
         }
         return by;
     };
+    tr.lap("ingest: frame ids");
     std::map<uint32_t, Frame> by_id;
     {
-        auto lum = group(in.lumen, kLumen);
+        auto lum = group(in.lumen_pts(), kLumen);
+        tr.lap("ingest: group lumen");
         std::map<uint32_t, const Rec*> meas;
         if (in.has_rec)
             for (auto& r : in.rec) meas[r.frame] = &r;  // later rows overwrite earlier ones
@@ -759,21 +847,23 @@ Geometry build_geometry(const Input& in, const std::string& label, bool diastole
             by_id[f.id] = std::move(f);
         }
     }
-    auto attach = [&](const std::vector<RawPoint>& pts, int kind) {
+    auto attach = [&](const Points& pts, int kind) {
         for (auto& kv : group(pts, kind)) {
             kv.second.centroid();
             auto it = by_id.find(kv.second.id);
             if (it != by_id.end()) it->second.extras[kind] = std::move(kv.second);
         }
     };
-    if (in.has_eem) attach(in.eem, kEem);
-    if (in.has_calc) attach(in.calc, kCalc);
-    if (in.has_side) attach(in.side, kSide);
+    if (in.has_eem) attach(in.eem_pts(), kEem);
+    if (in.has_calc) attach(in.calc_pts(), kCalc);
+    if (in.has_side) attach(in.side_pts(), kSide);
+    tr.lap("ingest: frames + extras");
     if (n_points > 0) {  // Frame::create_catheter_points, frame.rs:163-204
         std::map<uint32_t, double> z_of;
         for (auto& kv : by_id) {
             const Contour& l = kv.second.lumen;
-            for (size_t i = 0; i < l.size(); ++i) z_of.emplace(l.fi[i], l.z[i]);
+            for (size_t i = 0; i < l.size(); ++i)
+                if (i == 0 || l.fi[i] != l.fi[i - 1]) z_of.emplace(l.fi[i], l.z[i]);  // emplace keeps the first z per frame
         }
         std::vector<RawPoint> cath;
         for (auto& kv : z_of)
@@ -781,7 +871,7 @@ Geometry build_geometry(const Input& in, const std::string& label, bool diastole
                 const double a = 2.0 * kPi * (double)i / (double)n_points;
                 cath.push_back(RawPoint{kv.first, icx + radius * std::cos(a), icy + radius * std::sin(a), kv.second, false});
             }
-        auto by = group(cath, kCatheter);
+        auto by = group(Points{cath.data(), nullptr, cath.size()}, kCatheter);
         for (auto& kv : by) {
             for (size_t i = 0; i < kv.second.size(); ++i) kv.second.pi[i] = (uint32_t)i;
             kv.second.centroid();
@@ -789,6 +879,7 @@ Geometry build_geometry(const Input& in, const std::string& label, bool diastole
             if (it != by_id.end()) it->second.extras[kCatheter] = std::move(kv.second);
         }
     }
+    tr.lap("ingest: catheter");
     Geometry g;
     g.label = label;
     for (auto& kv : by_id) g.frames.push_back(std::move(kv.second));
@@ -828,7 +919,9 @@ Geometry build_geometry(const Input& in, const std::string& label, bool diastole
         }
         g.frames = std::move(ordered);
     }
-    for (auto& f : g.frames) f.sort_points();
+    tr.lap("ingest: reorder");
+    parallel_for(g.frames.size(), [&](size_t i) { g.frames[i].sort_points(); }, 8);  // frames are independent
+    tr.lap("ingest: sort points");
     {  // ensure_proximal_at_position_zero, geometry.rs:325-381
         const size_t n = g.frames.size();
         if (n) {
@@ -851,7 +944,9 @@ Geometry build_geometry(const Input& in, const std::string& label, bool diastole
             }
         }
     }
+    tr.lap("ingest: proximal first");
     integrity(g);
+    tr.lap("ingest: integrity");
     return g;
 }
 
@@ -1724,16 +1819,13 @@ extern "C" int mmrs_geometry_from_arrays(mmrs_ctx* ctx, const double* lumen, int
     if (!lumen || !ref_point || !label || !blob_out || !len_out)
         return mmrs::set_err(ctx, MMRS_ERR_ARG, "mmrs_geometry_from_arrays: NULL argument");
     return guarded(ctx, [&] {
-        auto conv = [](const double* a, int64_t n) {
-            std::vector<RawPoint> v((size_t)n);
-            for (int64_t i = 0; i < n; ++i) v[i] = RawPoint{(uint32_t)a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], false};
-            return v;
-        };
+        auto borrow = [](const double* a, int64_t n) { return Points{nullptr, a, (size_t)std::max<int64_t>(n, 0)}; };
+        static const double kNoRows[4] = {0, 0, 0, 0};  // an empty layer still needs a non-null `rows` to be "set"
         Input in;
-        in.lumen = conv(lumen, n_lumen);
-        if (eem) in.eem = conv(eem, n_eem), in.has_eem = true;
-        if (calc) in.calc = conv(calc, n_calc), in.has_calc = true;
-        if (side) in.side = conv(side, n_side), in.has_side = true;
+        in.a_lumen = borrow(n_lumen > 0 ? lumen : kNoRows, n_lumen);
+        if (eem) in.a_eem = borrow(n_eem > 0 ? eem : kNoRows, n_eem), in.has_eem = true;
+        if (calc) in.a_calc = borrow(n_calc > 0 ? calc : kNoRows, n_calc), in.has_calc = true;
+        if (side) in.a_side = borrow(n_side > 0 ? side : kNoRows, n_side), in.has_side = true;
         if (records) {
             in.has_rec = true;
             for (int64_t i = 0; i < n_rec; ++i) {
@@ -1748,8 +1840,12 @@ extern "C" int mmrs_geometry_from_arrays(mmrs_ctx* ctx, const double* lumen, int
                 in.rec.push_back(r);
             }
         }
-        in.ref = conv(ref_point, 1)[0];
-        *blob_out = encode_malloc(build_geometry(in, label, diastole != 0, icx, icy, radius, n_points), len_out);
+        in.ref = RawPoint{(uint32_t)ref_point[0], ref_point[1], ref_point[2], ref_point[3], false};
+        Trace tr;
+        const Geometry g = build_geometry(in, label, diastole != 0, icx, icy, radius, n_points);
+        tr.lap("ingest: build_geometry");
+        *blob_out = encode_malloc(g, len_out);
+        tr.lap("ingest: encode");
     });
 }
 

@@ -742,8 +742,15 @@ class PyInputData:
             return None
         if not contours:
             return np.zeros((0, 4))
-        rows = np.concatenate([c._sync() for c in contours], axis=0)
-        return np.ascontiguousarray(rows[:, [0, 2, 3, 4]])
+        parts = [c._sync() for c in contours]
+        out = np.empty((sum(len(r) for r in parts), 4))
+        o = 0
+        for r in parts:                      # [frame, x, y, z] of every point, written in place (no (N, 6) temporary)
+            n = len(r)
+            out[o:o + n, 0] = r[:, 0]
+            out[o:o + n, 1:4] = r[:, 2:5]
+            o += n
+        return out
 
     def _records(self):
         if self.record is None:
