@@ -819,22 +819,26 @@ def numpy_to_inputdata(lumen_arr, ref_point, diastole, record=None, eem_arr=None
     def contours(a, kind, keep):
         if a.size == 0:
             return None
-        out = []
         frames = a[:, 0].astype(np.int64)
-        order = np.argsort(frames, kind="stable")          # one pass: group rows by frame id, keeping row order
-        sf = frames[order]
-        cuts = np.flatnonzero(np.diff(sf)) + 1
-        for idx in np.split(order, cuts):
-            sel = a[idx]
-            fid = int(frames[idx[0]])
+        n = len(frames)
+        if n > 1 and not np.all(frames[1:] >= frames[:-1]):    # group rows by frame id, keeping row order
+            order = np.argsort(frames, kind="stable")
+            a, frames = a[order], frames[order]
+        starts = np.concatenate(([0], np.flatnonzero(np.diff(frames)) + 1, [n]))
+        # one (N, 6) [frame, point_index, x, y, z, aortic] array for the layer; every contour is a row-slice VIEW of it
+        big = np.empty((n, 6))
+        big[:, 0] = frames
+        big[:, 1] = np.arange(n) - np.repeat(starts[:-1], np.diff(starts))
+        big[:, 2:5] = a[:, 1:4]
+        big[:, 5] = 0.0
+        out = []
+        for s, e in zip(starts[:-1].tolist(), starts[1:].tolist()):
+            fid = int(frames[s])
             if keep is not None and fid not in keep:
                 continue
-            rows = np.zeros((len(sel), 6))
-            rows[:, 0] = fid
-            rows[:, 1] = np.arange(len(sel))
-            rows[:, 2:5] = sel[:, 1:4]
-            out.append(PyContour(fid, fid, rows, (float(np.mean(sel[:, 1])), float(np.mean(sel[:, 2])),
-                                                  float(np.mean(sel[:, 3]))), None, None, kind))
+            rows = big[s:e]
+            out.append(PyContour(fid, fid, rows, (float(np.mean(rows[:, 2])), float(np.mean(rows[:, 3])),
+                                                  float(np.mean(rows[:, 4]))), None, None, kind))
         return out or None
 
     lumen_arr = num(lumen_arr, "lumen_arr")
