@@ -208,6 +208,18 @@ def test_degenerate_and_empty_units(ctx):
     assert res["best_idx"][0] == ora.sweep(p, p, (4.5, 4.5), 0, 1.0, 10.0)["index"]
 
 
+def test_oversize_unit_is_refused(ctx):
+    """A unit that does not fit the shared-memory staging of K1 (N = M beyond ~4 800 points) is a clean
+    error of the call, not a crash or a silent fallback; the context stays usable."""
+    rng = np.random.default_rng(5)
+    big = contour(rng, 6000)
+    with pytest.raises(nat.MmrsError, match="unit too large"):
+        ctx.sweep_batched(big, [0, 6000], big, [0, 6000], np.zeros((1, 2)) + 4.5, [nat.make_grid(1.0, 5.0)], mode=0)
+    ok = contour(rng, 4000)
+    res = ctx.sweep_batched(ok, [0, 4000], ok, [0, 4000], np.zeros((1, 2)) + 4.5, [nat.make_grid(1.0, 5.0)], mode=0)
+    assert res["best_idx"][0] == 5 and res["best_dist"][0] == 0.0          # the identity rotation of a set on itself
+
+
 def test_three_step_api_and_timings(ctx):
     rng = np.random.default_rng(12)
     tests, refs, cents, txy, toff, rxy, roff = make_units(rng, [(256, 256)] * 4)
