@@ -49,9 +49,11 @@ class _Export:
 
     def pairs(self, pairs, blobs):
         if self.on:
-            for k, (pair, path) in enumerate(zip(pairs, self.paths)):
-                nat.export_pair(blobs[2 * k], blobs[2 * k + 1], pair.geom_a.label, pair.label, path, self.steps,
-                                self.watertight, self.kinds)
+            # the pairs go to different directories: written concurrently (the C side releases the GIL); the first
+            # failing pair, in the reference's order, is the error that surfaces
+            jobs = list(enumerate(zip(pairs, self.paths)))
+            _parallel(lambda j: nat.export_pair(blobs[2 * j[0]], blobs[2 * j[0] + 1], j[1][0].geom_a.label,
+                                                j[1][0].label, j[1][1], self.steps, self.watertight, self.kinds), jobs)
 
     def single(self, geom, blob):
         if self.on:
