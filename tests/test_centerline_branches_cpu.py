@@ -325,3 +325,13 @@ def test_load_and_prepare(rca, tmp_path, capsys):
     pre = rca.calculate_branches(2.0)
     kept = mm.prepare_centerline(pre, ref_centerline=ao, smooth_sigma=0.0)
     assert kept.points_as_tuples() == pre.remove_branch_overlap().orient_to_reference(ao).points_as_tuples()
+
+
+def test_reference_import_paths():
+    import multimodars as mm
+    from multimodars.ccta.centerline_prep import load_centerline, prepare_centerline
+    from multimodars.ccta import load_centerline as lc2
+    assert load_centerline is mm.load_centerline is lc2 and prepare_centerline is mm.prepare_centerline
+    import multimodars.ccta as ccta
+    with pytest.raises(AttributeError, match="not part of this build"):
+        ccta.stitching
