@@ -361,6 +361,7 @@ Geometry decode(const double* data, int64_t len) {
     Reader r{data, data + len};
     Geometry g;
     const size_t nf = (size_t)r.get();
+    if (nf > (size_t)len / 24) throw InputErr("geometry blob truncated");  // a frame is at least two 12-double headers
     if ((size_t)len < kParallelBlobDoubles || nf < 2 * kBlobThreads) {
         g.frames.reserve(nf);
         for (size_t k = 0; k < nf; ++k) g.frames.push_back(read_frame(r));

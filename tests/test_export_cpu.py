@@ -204,3 +204,18 @@ def test_export_errors_follow_the_reference(tmp_path):
     uneven.frames[1].lumen = ring(1, 0.5, 2.0, 6)
     with pytest.raises(nat.MmrsError, match="All contours must have the same number of points"):
         nat.export_single(uneven.to_blob(), "u", str(tmp_path / "u"), True, [0], 0)
+
+
+def test_malformed_blobs_are_refused(tmp_path):
+    """The blob decoder (csrc/mmrs_host.cpp decode) never trusts the counts inside a blob: a frame count the buffer cannot
+    hold, a cut-off contour, an empty buffer are errors of the call."""
+    import numpy as np
+    from multimodars import _native as nat
+    for bad in (np.array([1e15, 0.0, 0.0, 0.0]), np.array([2.0] + [0.0] * 30), np.zeros(0)):
+        with pytest.raises(nat.MmrsError, match="truncated|empty"):
+            nat.export_single(bad, "x", tmp_path, True, [0], 0)
+    frame = np.concatenate([np.zeros(11), [1.0], np.zeros(11), [600.0], np.zeros(6 * 600)])   # one 600-point lumen
+    big = np.concatenate([[40.0], np.tile(frame, 40)])
+    assert len(big) > (1 << 17)                                # large enough for the frame-parallel decoder
+    with pytest.raises(nat.MmrsError, match="truncated"):     # ... whose header walk notices the missing tail
+        nat.export_single(big[:-100], "x", tmp_path, True, [0], 0)
