@@ -189,26 +189,36 @@ def numpy_to_geometry(lumen_arr, eem_arr=None, catheter_arr=None, wall_arr=None,
     if ref.size > 0:
         fr, x, y, z = (ref if ref.ndim == 1 else ref[0])[:4]
         rp = (int(fr), 0, float(x), float(y), float(z), False)
-    ids = sorted({int(v) for a in layers.values() if a.size for v in a[:, 0].astype(int)})
-
-    def contour(kind, fid):
+    def grouped(kind):
+        """{frame id: PyContour} of one layer in ONE pass (rows keep their order inside a frame; every contour is a
+        row-slice view of one (N, 6) array) instead of one boolean mask per frame and layer."""
         a = layers[kind]
         if a.size == 0:
-            return None
-        pts = a[a[:, 0].astype(int) == fid]
-        if len(pts) == 0:
-            return None
-        rows = np.column_stack([pts[:, 0].astype(int).astype(float), np.arange(len(pts), dtype=float), pts[:, 1:4],
-                                np.zeros(len(pts))])
-        c = (float(np.mean(pts[:, 1])), float(np.mean(pts[:, 2])), float(np.mean(pts[:, 3])))
-        return PyContour(fid, fid, rows, c, None, None, kind)
+            return {}
+        frames = a[:, 0].astype(int)
+        n = len(frames)
+        if n > 1 and not np.all(frames[1:] >= frames[:-1]):
+            order = np.argsort(frames, kind="stable")
+            a, frames = a[order], frames[order]
+        starts = np.concatenate(([0], np.flatnonzero(np.diff(frames)) + 1, [n]))
+        big = np.empty((n, 6))
+        big[:, 0] = frames
+        big[:, 1] = np.arange(n) - np.repeat(starts[:-1], np.diff(starts))
+        big[:, 2:5] = a[:, 1:4]
+        big[:, 5] = 0.0
+        out = {}
+        for s0, e0 in zip(starts[:-1].tolist(), starts[1:].tolist()):
+            fid = int(frames[s0])
+            rows = big[s0:e0]
+            c = (float(np.mean(rows[:, 2])), float(np.mean(rows[:, 3])), float(np.mean(rows[:, 4])))
+            out[fid] = PyContour(fid, fid, rows, c, None, None, kind)
+        return out
 
+    by_kind = {k: grouped(k) for k in ("Lumen", "Eem", "Catheter", "Wall")}
     frames = []
-    for fid in ids:
-        lum = contour("Lumen", fid)
-        if lum is None:
-            continue
-        extras = {k: c for k in ("Eem", "Catheter", "Wall") if (c := contour(k, fid)) is not None}
+    for fid in sorted(by_kind["Lumen"]):          # a frame without a lumen contour is skipped, like the reference
+        lum = by_kind["Lumen"][fid]
+        extras = {k: by_kind[k][fid] for k in ("Eem", "Catheter", "Wall") if fid in by_kind[k]}
         frames.append(PyFrame(fid, lum.centroid, lum, extras, None if rp is None else PyContourPoint(*rp)))
     return PyGeometry(frames, label)
 
