@@ -160,12 +160,37 @@ class PyContour:
         r = self._sync()
         if len(r) == 0:
             raise ValueError("contour has no points")
-        d = np.sqrt(((r[:, None, 2:5] - r[None, :, 2:5]) ** 2).sum(axis=2))
-        iu = np.triu_indices(len(r), 1)
-        if len(iu[0]) == 0:
+        n = len(r)
+        if n < 2:
             return (self._point(0), self._point(0)), 0.0
-        k = int(np.argmax(d[iu]))  # first maximum in (i, j>i) row-major order == the Rust loop order
-        return (self._point(int(iu[0][k])), self._point(int(iu[1][k]))), float(d[iu][k])
+        x, y, z = r[:, 2], r[:, 3], r[:, 4]
+        # Rows are taken in blocks of 64 so that the temporaries stay small (a full n x n matrix of a 500-point contour
+        # is 2 MB per array: fresh pages every call). Block b holds the squared distances of rows [64 b, 64 b + 64) to
+        # all points, with the pairs j <= i masked out.
+        blocks, top = [], -1.0
+        cols = np.arange(n)
+        for i0 in range(0, n, 64):
+            i1 = min(i0 + 64, n)
+            dx, dy, dz = x[i0:i1, None] - x[None, :], y[i0:i1, None] - y[None, :], z[i0:i1, None] - z[None, :]
+            d2 = dx * dx + dy * dy + dz * dz                # same order of operations as Point3D::distance_to
+            d2[cols[None, :] <= np.arange(i0, i1)[:, None]] = -1.0
+            blocks.append(d2)
+            top = max(top, float(d2.max()))
+        # The reference compares the SQUARE ROOTS with a strict `>`: two different squares can round to the same root,
+        # so every pair whose square is within a few ulps of the largest is rooted, and the first largest root wins
+        # (pairs in (i, j > i) row-major order, like the Rust loops).
+        best, best_k = -1.0, 0
+        for b, d2 in enumerate(blocks):
+            flat = np.flatnonzero(d2.ravel() >= top * (1.0 - 1e-15))
+            if len(flat):
+                roots = np.sqrt(d2.ravel()[flat])
+                m = int(np.argmax(roots))
+                if float(roots[m]) > best:
+                    best, best_k = float(roots[m]), b * 64 * n + int(flat[m])
+        if not best > 0.0:                                   # nothing beats the initial (points[0], points[0]), 0.0
+            return (self._point(0), self._point(0)), 0.0
+        i, j = divmod(best_k, n)
+        return (self._point(i), self._point(j)), best
 
     def find_closest_opposite(self):
         """contour.rs:247-309 — the pair closest to opposite (by angle about the centroid) with the shortest chord."""
@@ -205,12 +230,11 @@ class PyContour:
         n = len(r)
         if n < 3:
             return 0.0
-        p1, p2 = r[:, 2:5], np.roll(r[:, 2:5], -1, axis=0)
-        cx = cy = cz = 0.0
-        for a, b in zip(p1, p2):
-            cx += a[1] * b[2] - a[2] * b[1]
-            cy += a[2] * b[0] - a[0] * b[2]
-            cz += a[0] * b[1] - a[1] * b[0]
+        a, b = r[:, 2:5], np.roll(r[:, 2:5], -1, axis=0)
+        # cumsum adds left to right, so its last element is the reference's sequential fold, bit for bit
+        cx = float(np.cumsum(a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1])[-1])
+        cy = float(np.cumsum(a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2])[-1])
+        cz = float(np.cumsum(a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0])[-1])
         return 0.5 * math.sqrt(cx * cx + cy * cy + cz * cz)
 
     def rotate(self, angle_deg):

@@ -109,3 +109,43 @@ def test_geometry_rotate_is_per_frame_and_a_copy():
     r = g.rotate(90.0)
     assert abs(r.frames[0].lumen.points[1].x + 2.0) < 1e-9 and g.frames[0].lumen.points[1].x == 2.0
     assert r.label == "g" and len(r) == 1
+
+
+def test_farthest_points_and_area_equal_the_reference_loops():
+    """find_farthest_points / get_area are vectorised here; they must return exactly what the reference's loops do
+    (contour.rs:227-243: strict `>` on the rooted distances in (i, j > i) order, starting from (p0, p0), 0.0;
+    contour.rs:345-363: sequential sums of the cross-product terms) — including exact ties and degenerate sets."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+
+    def loops(p):
+        best, md = (0, 0), 0.0
+        for i in range(len(p)):
+            for j in range(i + 1, len(p)):
+                d = math.sqrt((p[i][0] - p[j][0]) ** 2 + (p[i][1] - p[j][1]) ** 2 + (p[i][2] - p[j][2]) ** 2)
+                if d > md:
+                    md, best = d, (i, j)
+        cx = cy = cz = 0.0
+        for i in range(len(p)):
+            a, b = p[i], p[(i + 1) % len(p)]
+            cx += a[1] * b[2] - a[2] * b[1]
+            cy += a[2] * b[0] - a[0] * b[2]
+            cz += a[0] * b[1] - a[1] * b[0]
+        return best, md, (0.5 * math.sqrt(cx * cx + cy * cy + cz * cz) if len(p) >= 3 else 0.0)
+
+    for trial in range(40):
+        n = int(rng.integers(1, 150))
+        if trial % 4 == 0:
+            ang = 2 * np.pi * np.arange(n) / n
+            xyz = np.stack([2 * np.cos(ang), 2 * np.sin(ang), np.zeros(n)], 1)       # many (nearly) tied diameters
+        elif trial % 4 == 1:
+            xyz = np.round(rng.normal(0, 2, (n, 3)))                                  # integer grid: exact ties
+        elif trial % 4 == 2:
+            xyz = np.tile(rng.normal(0, 1, (1, 3)), (n, 1))                           # all points identical
+        else:
+            xyz = rng.normal(0, 2, (n, 3))
+        c = PyContour(0, 0, [PyContourPoint(0, i, *map(float, p), False) for i, p in enumerate(xyz)], (0.0, 0.0, 0.0))
+        (a, b), d = c.find_farthest_points()
+        (i, j), md, area = loops(xyz.tolist())
+        assert (a.point_index, b.point_index, d) == (i, j, md), (trial, n)
+        assert c.get_area() == area, (trial, n)
