@@ -198,20 +198,26 @@ class PyContour:
         n = len(r)
         if n <= 2:
             raise ValueError("Need at least 3 points")
-        cx, cy = self.centroid[0], self.centroid[1]
-        th = np.arctan2(r[:, 3] - cy, r[:, 2] - cx)
-        th = np.where(th < 0, th + 2 * math.pi, th)
-        best, best_d = (0, 1), float("inf")
-        for i in range(n):
-            delta = np.abs(th - th[i])
-            delta = np.where(delta > math.pi, 2 * math.pi - delta, delta)
+        if getattr(self, "_has_centroid", True):
+            cx, cy = self.centroid[0], self.centroid[1]
+        else:                                               # no centroid stored: the sequential mean of the points
+            cx, cy = float(np.cumsum(r[:, 2])[-1]) / n, float(np.cumsum(r[:, 3])[-1]) / n
+        x, y = r[:, 2], r[:, 3]
+        th = np.array(list(map(math.atan2, (y - cy).tolist(), (x - cx).tolist())))       # glibc atan2, like Rust's
+        th = np.where(th < 0.0, th + 2.0 * math.pi, th)
+        two_pi, idx = 2.0 * math.pi, np.arange(n)
+        partner = np.empty(n, dtype=np.int64)
+        for i0 in range(0, n, 64):                          # blocks of rows: small temporaries
+            i1 = min(i0 + 64, n)
+            delta = np.abs(th[None, :] - th[i0:i1, None])
+            delta = np.where(delta > math.pi, two_pi - delta, delta)
             diff = np.abs(delta - math.pi)
-            diff[i] = np.inf
-            j = int(np.argmin(diff))
-            dist = math.hypot(r[i, 2] - r[j, 2], r[i, 3] - r[j, 3])
-            if dist < best_d:
-                best_d, best = dist, (i, j)
-        return (self._point(best[0]), self._point(best[1])), best_d
+            diff[idx[i0:i1] - i0, idx[i0:i1]] = np.inf      # j != i
+            partner[i0:i1] = np.argmin(diff, axis=1)        # first minimum == the strict `<` scan over j
+        dx, dy = x - x[partner], y - y[partner]
+        chord = np.sqrt(dx * dx + dy * dy)                  # Point3D::distance_2d_to
+        i = int(np.argmin(chord))                           # first minimum == the strict `<` scan over i
+        return (self._point(i), self._point(int(partner[i]))), float(chord[i])
 
     def get_elliptic_ratio(self):
         """contour.rs:313-343."""
@@ -275,17 +281,20 @@ def _sort_rows(rows):
     n = len(rows)
     if n == 0:
         return rows
-    sx = sy = 0.0
-    for r in rows:
-        sx += r[2]
-        sy += r[3]
-    cx, cy = sx / n, sy / n
-    key = np.array([math.atan2(r[3] - cy, r[2] - cx) for r in rows])
+    # cumsum adds left to right: its last element is the reference's sequential sum, bit for bit
+    cx, cy = float(np.cumsum(rows[:, 2])[-1]) / n, float(np.cumsum(rows[:, 3])[-1]) / n
+    # math.atan2 is glibc's (what Rust's f64::atan2 calls); numpy's arctan2 may be a SIMD variant that differs in the
+    # last bit, which could reorder nearly tied keys
+    key = np.array(list(map(math.atan2, (rows[:, 3] - cy).tolist(), (rows[:, 2] - cx).tolist())))
     rows = rows[np.argsort(key, kind="stable")]
-    start = 0
-    for i in range(1, n):
-        if not (rows[i, 3] < rows[start, 3]):
-            start = i
+    y = rows[:, 3]
+    if np.isnan(y).any():
+        start = 0
+        for i in range(1, n):
+            if not (y[i] < y[start]):
+                start = i
+    else:
+        start = n - 1 - int(np.argmax(y[::-1]))          # the LAST of the highest-y points
     rows = np.roll(rows, -start, axis=0)
     rows[:, 1] = np.arange(n)
     return rows

@@ -149,3 +149,47 @@ def test_farthest_points_and_area_equal_the_reference_loops():
         (i, j), md, area = loops(xyz.tolist())
         assert (a.point_index, b.point_index, d) == (i, j, md), (trial, n)
         assert c.get_area() == area, (trial, n)
+
+
+def test_closest_opposite_equals_the_reference_loops():
+    """contour.rs:247-296, literally: partner = first j != i whose angle about the centroid is nearest to opposite,
+    chord = sqrt(dx*dx + dy*dy), first strictly shortest chord wins; without a stored centroid the mean of the points."""
+    import numpy as np
+    rng = np.random.default_rng(4)
+
+    def loops(p, cx, cy):
+        n, th = len(p), []
+        for q in p:
+            t = math.atan2(q[1] - cy, q[0] - cx)
+            th.append(t + 2 * math.pi if t < 0 else t)
+        md, best = float("inf"), (0, 1)
+        for i in range(n):
+            bd, bj = float("inf"), i
+            for j in range(n):
+                if j == i:
+                    continue
+                d = abs(th[j] - th[i])
+                d = 2 * math.pi - d if d > math.pi else d
+                if abs(d - math.pi) < bd:
+                    bd, bj = abs(d - math.pi), j
+            dist = math.sqrt((p[i][0] - p[bj][0]) ** 2 + (p[i][1] - p[bj][1]) ** 2)
+            if dist < md:
+                md, best = dist, (i, bj)
+        return best, md
+
+    for t in range(45):
+        n = int(rng.integers(3, 150))
+        if t % 3 == 0:
+            ang = 2 * np.pi * np.arange(n) / n
+            xy = np.stack([2 * np.cos(ang), 1.5 * np.sin(ang)], 1)
+        elif t % 3 == 1:
+            xy = np.round(rng.normal(0, 2, (n, 2)))
+        else:
+            xy = rng.normal(0, 2, (n, 2))
+        pts = [PyContourPoint(0, i, float(a), float(b), 0.0, False) for i, (a, b) in enumerate(xy)]
+        for centroid in ((0.1, -0.2, 0.0), None):
+            c = PyContour(0, 0, pts, centroid)
+            cx, cy = (centroid[0], centroid[1]) if centroid else (sum(q[0] for q in xy.tolist()) / n, sum(q[1] for q in xy.tolist()) / n)
+            (a, b), d = c.find_closest_opposite()
+            (i, j), md = loops(xy.tolist(), cx, cy)
+            assert (a.point_index, b.point_index, d) == (i, j, md), (t, n, centroid)
