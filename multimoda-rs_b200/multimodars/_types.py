@@ -133,13 +133,7 @@ class PyContour:
     def compute_centroid(self):
         r = self._sync()
         if len(r):
-            sx = sy = sz = 0.0
-            for row in r:  # sequential fold, contour.rs:213-224
-                sx += row[2]
-                sy += row[3]
-                sz += row[4]
-            n = float(len(r))
-            self.centroid = (sx / n, sy / n, sz / n)
+            self.centroid = _centroid_rows(r)
 
     def points_as_tuples(self):
         return [(float(r[2]), float(r[3]), float(r[4])) for r in self._sync()]
@@ -301,12 +295,10 @@ def _sort_rows(rows):
 
 
 def _centroid_rows(rows):
-    sx = sy = sz = 0.0
-    for r in rows:
-        sx += r[2]
-        sy += r[3]
-        sz += r[4]
+    """Sequential left fold of the coordinates (contour.rs:213-224): cumsum adds left to right, so its last row is that
+    fold bit for bit — unlike np.sum / np.mean, which add pairwise."""
     n = float(len(rows))
+    sx, sy, sz = np.cumsum(rows[:, 2:5], axis=0)[-1].tolist()
     return (sx / n, sy / n, sz / n)
 
 
