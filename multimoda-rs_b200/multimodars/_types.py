@@ -106,7 +106,7 @@ class PyContour:
     @property
     def points(self):
         if self._pts is None:
-            self._pts = [PyContourPoint(*r) for r in self._rows]
+            self._pts = [PyContourPoint(*r) for r in self._rows.tolist()]
         return self._pts
 
     @points.setter
@@ -136,7 +136,7 @@ class PyContour:
             self.centroid = _centroid_rows(r)
 
     def points_as_tuples(self):
-        return [(float(r[2]), float(r[3]), float(r[4])) for r in self._sync()]
+        return [tuple(r) for r in self._sync()[:, 2:5].tolist()]
 
     def _clone(self, rows=None, **kw):
         c = PyContour(self.id, self.original_frame, (self._sync() if rows is None else rows).copy(), self.centroid,
