@@ -475,12 +475,20 @@ class PyGeometry:
 
     def get_summary(self):
         """(mla, max_stenosis, stenosis_length_mm) — py_geometry.rs:190-254."""
+        return self._summary([f.lumen.get_area() for f in self.frames], None)
+
+    def _summary(self, areas, ellips):
+        """`ellips` = the per-frame elliptic ratios when the caller already has them (PyGeometryPair.get_summary needs
+        them for its table; each costs an all-pairs farthest-point search)."""
         if not self.frames:
             return (0.0, 0.0, 0.0)
-        areas = [f.lumen.get_area() for f in self.frames]
         biggest, mla = max(areas), min(areas)
         max_sten = 1.0 - (mla / biggest) if biggest > 0.0 else 0.0
-        thr = (0.70 if all(f.lumen.get_elliptic_ratio() < 1.3 for f in self.frames) else 0.50) * biggest
+        if ellips is None:
+            round_enough = all(f.lumen.get_elliptic_ratio() < 1.3 for f in self.frames)
+        else:
+            round_enough = all(e < 1.3 for e in ellips)
+        thr = (0.70 if round_enough else 0.50) * biggest
         cen = [f.centroid for f in self.frames]
         longest, i = 0.0, 0
         while i < len(areas):
@@ -595,13 +603,14 @@ class PyGeometryPair:
     def get_summary(self):
         """py_geometry_pair.rs:70-201 -> (((dia_mla, dia_max_stenosis, dia_len_mm), (sys ...)), table); table rows are
         [id, area_dia, ellip_dia, area_sys, ellip_sys, z]; the table is also printed like the reference does."""
-        dia, sys_ = self.geom_a.get_summary(), self.geom_b.get_summary()
         a, b = self.geom_a.get_lumen_contours(), self.geom_b.get_lumen_contours()
+        area_a, area_b = [c.get_area() for c in a], [c.get_area() for c in b]
+        ell_a, ell_b = [c.get_elliptic_ratio() for c in a], [c.get_elliptic_ratio() for c in b]   # once per contour
+        dia, sys_ = self.geom_a._summary(area_a, ell_a), self.geom_b._summary(area_b, ell_b)
         n = len(a)
         if len(b) != n:
             print("ERROR: mismatched lengths between contour vectors")
-        mat = [[float(a[i].id), a[i].get_area(), a[i].get_elliptic_ratio(), b[i].get_area(), b[i].get_elliptic_ratio(),
-                a[i].centroid[2]] for i in range(n)]
+        mat = [[float(a[i].id), area_a[i], ell_a[i], area_b[i], ell_b[i], a[i].centroid[2]] for i in range(n)]
         headers = ["id", "area_dia", "ellip_dia", "area_sys", "ellip_sys", "z"]
         rows = [[str(a[i].id)] + [f"{v:.2f}" for v in mat[i][1:]] for i in range(n)]
         widths = [max([len(h)] + [len(r[k]) for r in rows]) for k, h in enumerate(headers)]
