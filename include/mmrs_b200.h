@@ -279,6 +279,16 @@ int mmrs_export_pair(mmrs_ctx* ctx, const double* blob_a, int64_t len_a, const d
 int mmrs_export_single(mmrs_ctx* ctx, const double* blob, int64_t len, const char* name, const char* output_dir,
                        int32_t watertight, const int32_t* kinds, int32_t n_kinds, int32_t naming);
 
+/* ---- value-type helpers (host only, no context) --------------------------------------------------
+ * Contour::area, find_farthest_points, find_closest_opposite, find_closest_opposite_3d
+ * (src/types/native/contour.rs:227-363; behind PyContour.get_area / find_farthest_points / find_closest_opposite /
+ * get_elliptic_ratio, src/types/binding/py_contour.rs:144-213) on n packed (x, y, z) points. `centroid` = the
+ * contour's stored centroid (has_centroid != 0) — otherwise the mean of the points, like the reference.
+ * out[8] = { area, farthest_i, farthest_j, farthest_dist, opposite_i, opposite_j, opposite_dist_2d,
+ * opposite_dist_3d }; entries that the reference refuses for this n (n <= 2 for the opposite searches, n == 0 for
+ * the farthest pair) are NaN.                                                                        */
+int mmrs_contour_metrics(const double* xyz, int64_t n, int32_t has_centroid, const double* centroid, double out[8]);
+
 /* ---- centerline alignment ----------------------------------------------------------------------
  * Replaces align_three_point_rs / align_manual_rs / align_combined_rs
  * (src/intravascular/centerline_align/align.rs:61-121, :123-164, :166-283; PyO3 wrappers in

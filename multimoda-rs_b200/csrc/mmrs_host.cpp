@@ -1978,6 +1978,92 @@ extern "C" int mmrs_export_pair(mmrs_ctx* ctx, const double* blob_a, int64_t len
     });
 }
 
+// Contour::{area, find_farthest_points, find_closest_opposite, find_closest_opposite_3d} of the reference's value types
+// (types/native/contour.rs:227-363), the loops as they stand there, on a packed (n, 3) f64 array: what the Python
+// value types call instead of n x n numpy temporaries.
+extern "C" int mmrs_contour_metrics(const double* xyz, int64_t n, int32_t has_centroid, const double* centroid,
+                                    double out[8]) {
+    if (!xyz || !out || n < 0 || (has_centroid && !centroid))
+        return mmrs::set_err(nullptr, MMRS_ERR_ARG, "mmrs_contour_metrics: bad arguments");
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int k = 0; k < 8; ++k) out[k] = nan;
+    auto X = [&](int64_t i) { return xyz[3 * i]; };
+    auto Y = [&](int64_t i) { return xyz[3 * i + 1]; };
+    auto Z = [&](int64_t i) { return xyz[3 * i + 2]; };
+    // area (contour.rs:345-363): half the norm of the summed cross products of consecutive points
+    if (n < 3) {
+        out[0] = 0.0;
+    } else {
+        double cx = 0.0, cy = 0.0, cz = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t j = (i + 1) % n;
+            cx = cx + (Y(i) * Z(j) - Z(i) * Y(j));
+            cy = cy + (Z(i) * X(j) - X(i) * Z(j));
+            cz = cz + (X(i) * Y(j) - Y(i) * X(j));
+        }
+        out[0] = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+    }
+    if (n == 0) return 0;
+    // farthest pair (contour.rs:227-243): strict `>` from ((p0, p0), 0.0)
+    {
+        int64_t bi = 0, bj = 0;
+        double best = 0.0;
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t j = i + 1; j < n; ++j) {
+                const double dx = X(i) - X(j), dy = Y(i) - Y(j), dz = Z(i) - Z(j);
+                const double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+                if (d > best) best = d, bi = i, bj = j;
+            }
+        out[1] = (double)bi, out[2] = (double)bj, out[3] = best;
+    }
+    if (n <= 2) return 0;  // the two "closest opposite" searches assert n > 2
+    {  // find_closest_opposite (contour.rs:247-296)
+        double cx, cy;
+        if (has_centroid) {
+            cx = centroid[0], cy = centroid[1];
+        } else {
+            double sx = 0.0, sy = 0.0;
+            for (int64_t i = 0; i < n; ++i) sx = sx + X(i), sy = sy + Y(i);
+            cx = sx / (double)n, cy = sy / (double)n;
+        }
+        std::vector<double> th((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            double t = std::atan2(Y(i) - cy, X(i) - cx);
+            if (t < 0.0) t += 2.0 * kPi;
+            th[(size_t)i] = t;
+        }
+        double min_dist = std::numeric_limits<double>::max();
+        int64_t pi = 0, pj = 1;
+        for (int64_t i = 0; i < n; ++i) {
+            double best_diff = std::numeric_limits<double>::max();
+            int64_t bj = i;
+            for (int64_t j = 0; j < n; ++j) {
+                if (j == i) continue;
+                double delta = std::fabs(th[(size_t)j] - th[(size_t)i]);
+                if (delta > kPi) delta = 2.0 * kPi - delta;
+                const double diff = std::fabs(delta - kPi);
+                if (diff < best_diff) best_diff = diff, bj = j;
+            }
+            const double dx = X(i) - X(bj), dy = Y(i) - Y(bj);
+            const double d = std::sqrt(dx * dx + dy * dy);
+            if (d < min_dist) min_dist = d, pi = i, pj = bj;
+        }
+        out[4] = (double)pi, out[5] = (double)pj, out[6] = min_dist;
+    }
+    {  // find_closest_opposite_3d (contour.rs:298-320): the minor axis of elliptic_ratio
+        const int64_t half = n / 2;
+        double min_dist = std::numeric_limits<double>::max();
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t j = (i + half) % n;
+            const double dx = X(i) - X(j), dy = Y(i) - Y(j), dz = Z(i) - Z(j);
+            const double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+            if (d < min_dist) min_dist = d;
+        }
+        out[7] = min_dist;
+    }
+    return 0;
+}
+
 extern "C" int mmrs_export_single(mmrs_ctx* ctx, const double* blob, int64_t len, const char* name,
                                   const char* output_dir, int32_t watertight, const int32_t* kinds, int32_t n_kinds,
                                   int32_t naming) {

@@ -75,7 +75,7 @@ EXPORTS = [
     "mmrs_sweep_download", "mmrs_sweep_plan", "mmrs_sweep_get_dist32", "mmrs_sweep_get_shortlist", "mmrs_last_timings",
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
     "mmrs_process_cases", "mmrs_process_stats", "mmrs_ctx_set_shard", "mmrs_export_pair", "mmrs_export_single",
-    "mmrs_align_centerline", "mmrs_sweep_prefilter_info", "mmrs_ctx_set_prune",
+    "mmrs_align_centerline", "mmrs_sweep_prefilter_info", "mmrs_ctx_set_prune", "mmrs_contour_metrics",
 ]
 
 _lib = None
@@ -302,6 +302,21 @@ class Context:
         s = (C.c_int64 * 5)()
         self._check(lib().mmrs_process_stats(self._p, s))
         return dict(units=s[0], evals=s[1], rechecks=s[2], chain_resolved=s[3], launches=s[4])
+
+
+def contour_metrics(xyz, centroid=None):
+    """mmrs_contour_metrics: (area, (far_i, far_j, far_dist), (opp_i, opp_j, opp_dist_2d), opp_dist_3d) of n packed
+    (x, y, z) points by the reference's own loops (types/native/contour.rs:227-363); host only, no context."""
+    a = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+    out = (C.c_double * 8)()
+    c = None if centroid is None else (C.c_double * 3)(float(centroid[0]), float(centroid[1]), float(centroid[2]))
+    L = lib()
+    L.mmrs_contour_metrics.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_double * 8]
+    rc = L.mmrs_contour_metrics(a.ctypes.data_as(C.c_void_p), len(a), 0 if c is None else 1, c, out)
+    if rc:
+        raise MmrsError(_err(None))
+    return out[0], (int(out[1]) if out[1] == out[1] else -1, int(out[2]) if out[2] == out[2] else -1, out[3]), \
+        (int(out[4]) if out[4] == out[4] else -1, int(out[5]) if out[5] == out[5] else -1, out[6]), out[7]
 
 
 # ---- geometry-level entry points ---------------------------------------------------

@@ -149,7 +149,7 @@ class PyContour:
     def _point(self, i):
         return PyContourPoint(*self._sync()[i])
 
-    def find_farthest_points(self):
+    def _farthest_numpy(self):
         """contour.rs:227-243 — first pair with the largest 3-D distance."""
         r = self._sync()
         if len(r) == 0:
@@ -186,7 +186,7 @@ class PyContour:
         i, j = divmod(best_k, n)
         return (self._point(i), self._point(j)), best
 
-    def find_closest_opposite(self):
+    def _opposite_numpy(self):
         """contour.rs:247-309 — the pair closest to opposite (by angle about the centroid) with the shortest chord."""
         r = self._sync()
         n = len(r)
@@ -213,18 +213,62 @@ class PyContour:
         i = int(np.argmin(chord))                           # first minimum == the strict `<` scan over i
         return (self._point(i), self._point(int(partner[i]))), float(chord[i])
 
-    def get_elliptic_ratio(self):
-        """contour.rs:313-343."""
+    def _minor_numpy(self):
         r = self._sync()
         n = len(r)
-        if n <= 2:
-            raise ValueError("Need at least 3 points")
-        major = self.find_farthest_points()[1]
         j = (np.arange(n) + n // 2) % n
-        minor = float(np.sqrt(((r[:, 2:5] - r[j, 2:5]) ** 2).sum(axis=1)).min())
-        return minor / major if major < minor else major / minor
+        d = r[:, 2:5] - r[j, 2:5]
+        return float(np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).min())
+
+    # The four measurements below run the reference's own loops in the library (mmrs_contour_metrics, host only);
+    # the numpy versions above give the same values bit for bit (tests/test_type_kats_cpu.py) and serve where the
+    # library has not been built.
+    def _metrics(self):
+        from . import _native as nat
+        r = self._sync()
+        try:
+            return nat.contour_metrics(r[:, 2:5], self.centroid if getattr(self, "_has_centroid", True) else None)
+        except (OSError, AttributeError):
+            return None
+
+    def find_farthest_points(self):
+        """contour.rs:227-243 — first pair with the largest 3-D distance."""
+        if len(self._sync()) == 0:
+            raise ValueError("contour has no points")
+        m = self._metrics()
+        if m is None:
+            return self._farthest_numpy()
+        _, (i, j, d), _, _ = m
+        return (self._point(i), self._point(j)), d
+
+    def find_closest_opposite(self):
+        """contour.rs:247-296 — the pair closest to opposite (by angle about the centroid) with the shortest chord."""
+        if len(self._sync()) <= 2:
+            raise ValueError("Need at least 3 points")
+        m = self._metrics()
+        if m is None:
+            return self._opposite_numpy()
+        _, _, (i, j, d), _ = m
+        return (self._point(i), self._point(j)), d
+
+    def get_elliptic_ratio(self):
+        """contour.rs:313-343: farthest pair over the shortest (i, i + n/2) chord, whichever way round is >= 1
+        (0 / 0 is NaN, like the reference's f64 division)."""
+        if len(self._sync()) <= 2:
+            raise ValueError("Need at least 3 points")
+        m = self._metrics()
+        major, minor = (self._farthest_numpy()[1], self._minor_numpy()) if m is None else (m[1][2], m[3])
+        num, den = (minor, major) if major < minor else (major, minor)
+        if den == 0.0:
+            return math.nan if num == 0.0 or num != num else math.copysign(math.inf, num)
+        return num / den
 
     def get_area(self):
+        """contour.rs:345-363 — half the norm of the summed cross products."""
+        m = self._metrics()
+        return self._area_numpy() if m is None else m[0]
+
+    def _area_numpy(self):
         """contour.rs:345-363 — half the norm of the summed cross products."""
         r = self._sync()
         n = len(r)

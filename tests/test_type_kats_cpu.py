@@ -112,7 +112,8 @@ def test_geometry_rotate_is_per_frame_and_a_copy():
 
 
 def test_farthest_points_and_area_equal_the_reference_loops():
-    """find_farthest_points / get_area are vectorised here; they must return exactly what the reference's loops do
+    """find_farthest_points / get_area / get_elliptic_ratio run in the library (mmrs_contour_metrics) with vectorised
+    numpy twins; both must return exactly what the reference's loops do
     (contour.rs:227-243: strict `>` on the rooted distances in (i, j > i) order, starting from (p0, p0), 0.0;
     contour.rs:345-363: sequential sums of the cross-product terms) — including exact ties and degenerate sets."""
     import numpy as np
@@ -145,10 +146,17 @@ def test_farthest_points_and_area_equal_the_reference_loops():
         else:
             xyz = rng.normal(0, 2, (n, 3))
         c = PyContour(0, 0, [PyContourPoint(0, i, *map(float, p), False) for i, p in enumerate(xyz)], (0.0, 0.0, 0.0))
-        (a, b), d = c.find_farthest_points()
         (i, j), md, area = loops(xyz.tolist())
-        assert (a.point_index, b.point_index, d) == (i, j, md), (trial, n)
-        assert c.get_area() == area, (trial, n)
+        for far, ar in ((c.find_farthest_points, c.get_area), (c._farthest_numpy, c._area_numpy)):   # library, numpy twin
+            (a, b), d = far()
+            assert (a.point_index, b.point_index, d) == (i, j, md), (trial, n, far.__name__)
+            assert ar() == area, (trial, n)
+        if n > 2:                                        # elliptic ratio: farthest over the shortest (i, i + n/2) chord
+            minor = min(math.sqrt(sum((xyz[k][q] - xyz[(k + n // 2) % n][q]) ** 2 for q in range(3))) for k in range(n))
+            assert c._minor_numpy() == minor
+            want = math.nan if (md == 0.0 and minor == 0.0) else (minor / md if md < minor else (md / minor if minor else math.inf))
+            got = c.get_elliptic_ratio()
+            assert got == want or (math.isnan(got) and math.isnan(want)), (trial, n, got, want)
 
 
 def test_closest_opposite_equals_the_reference_loops():
@@ -190,6 +198,7 @@ def test_closest_opposite_equals_the_reference_loops():
         for centroid in ((0.1, -0.2, 0.0), None):
             c = PyContour(0, 0, pts, centroid)
             cx, cy = (centroid[0], centroid[1]) if centroid else (sum(q[0] for q in xy.tolist()) / n, sum(q[1] for q in xy.tolist()) / n)
-            (a, b), d = c.find_closest_opposite()
             (i, j), md = loops(xy.tolist(), cx, cy)
-            assert (a.point_index, b.point_index, d) == (i, j, md), (t, n, centroid)
+            for opp in (c.find_closest_opposite, c._opposite_numpy):                          # library, numpy twin
+                (a, b), d = opp()
+                assert (a.point_index, b.point_index, d) == (i, j, md), (t, n, centroid, opp.__name__)
