@@ -151,6 +151,8 @@ def test_farthest_points_and_area_equal_the_reference_loops():
             (a, b), d = far()
             assert (a.point_index, b.point_index, d) == (i, j, md), (trial, n, far.__name__)
             assert ar() == area, (trial, n)
+        from multimodars import _native as nat
+        assert nat.contour_metrics(xyz)[0] == area       # the library's area, the third implementation
         if n > 2:                                        # elliptic ratio: farthest over the shortest (i, i + n/2) chord
             minor = min(math.sqrt(sum((xyz[k][q] - xyz[(k + n // 2) % n][q]) ** 2 for q in range(3))) for k in range(n))
             assert c._minor_numpy() == minor
