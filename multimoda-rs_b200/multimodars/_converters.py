@@ -7,7 +7,7 @@ from __future__ import annotations
 import numpy as np
 
 from ._types import (PyCenterline, PyContour, PyContourPoint, PyFrame, PyGeometry, PyGeometryPair, PyInputData,
-                     PyRecord, _records_from_array,
+                     PyRecord,
                      numpy_to_inputdata)  # noqa: F401  (the reference exports numpy_to_inputdata from this module)
 
 _LAYERS = ("lumen", "eem", "calcification", "sidebranch", "catheter", "wall")

@@ -5,7 +5,7 @@ import subprocess
 import sys
 from pathlib import Path
 
-import numpy as np
+import numpy as np  # noqa: F401
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))

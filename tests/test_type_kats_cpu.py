@@ -3,8 +3,6 @@ package (multimodars/_types.py): types/native/contour.rs:606-1040, types/native/
 PyFrame surface: degrees, about the frame centroid — py_frame.rs:90-116)."""
 import math
 
-import pytest
-
 from multimodars import PyContour, PyContourPoint, PyFrame, PyGeometry
 
 

@@ -6,7 +6,6 @@ import numpy as np
 import pytest
 
 from multimodars import PyContour, PyContourPoint, PyFrame, PyGeometry
-from oracle import oracle_py as ora
 
 
 def _centroid(points):
