@@ -124,3 +124,59 @@ def test_contour_file_dialects_match_oracle(tmp_path, variant):
     assert np.array_equal(got, want)
     g = mm.PyGeometry.from_blob(got, "x")
     assert len(g.frames) == 3 and all(len(f.lumen) == n for f in g.frames)
+
+
+def test_contour_reader_fuzz_matches_oracle(tmp_path):
+    """Seeded fuzz of the in-place contour-file reader against the oracle's line-by-line reader: a clean 3-frame file
+    with a few rows corrupted (odd number tokens, extra / missing fields, stray CRs and blanks, inserted junk rows, a
+    header). Both must build the same geometry blob or fail with the same message."""
+    import math
+    import random
+    rnd = random.Random(12345)
+    tok = ["1", "0", "12", "007", "+3", "-1", "1.5", "-2.25e0", "3E0", ".5", "5.", "1e+0", "1e-0", "inf", "nan", "NaN",
+           "-inf", "0x10", "1_0", "abc", "", " 2 ", "2 ", "\t2", "1,5", "true", "false", "TRUE", "4294967295",
+           "4294967296", "99999999999999999999", "1e400", "1e-400", "-0", "-0.0", "١"]
+    parsed = 0
+    for trial in range(150):
+        d = tmp_path / f"t{trial}"
+        d.mkdir()
+        delim, eol, n = rnd.choice(["\t", ","]), rnd.choice(["\n", "\r\n"]), 8
+        rows = [[str(f), repr(3 + 2 * math.cos(2 * math.pi * k / n)), repr(3 + 1.5 * math.sin(2 * math.pi * k / n)),
+                 repr(0.5 * f)] for f in range(3) for k in range(n)]
+        for _ in range(rnd.randint(0, 3)):
+            i = rnd.randrange(len(rows))
+            r = list(rows[i])
+            mode = rnd.randrange(5)
+            if len(r) < 4:
+                continue
+            if mode == 0:
+                r[rnd.randrange(4)] = rnd.choice(tok)
+            elif mode == 1:
+                r.append(rnd.choice(tok))
+            elif mode == 2:
+                r = r[:rnd.randint(0, 3)]
+            elif mode == 3:
+                r[rnd.randrange(4)] = " " + r[rnd.randrange(4)] + rnd.choice([" ", "\r", ""])
+            else:
+                rows.insert(i, [rnd.choice(tok) for _ in range(rnd.randint(1, 6))])
+                continue
+            rows[i] = r
+        if rnd.random() < 0.3:
+            rows.insert(rnd.randrange(len(rows)), [rnd.choice(["", " ", "\r"])])
+        if rnd.random() < 0.2:
+            rows.insert(0, ["frame", "x", "y", "z"])
+        for ph in ("diastolic", "systolic"):
+            with open(d / f"{ph}_contours.csv", "w", newline="") as f:
+                f.write(eol.join(delim.join(r) for r in rows) + (eol if rnd.random() < 0.8 else ""))
+            (d / f"{ph}_reference_points.csv").write_text(delim.join(["1", "3.5", "2.0", "0.5"]) + "\n")
+        got = []
+        for fn in (nat.geometry_from_dir, ora.build_geometry_from_dir):
+            try:
+                got.append(("ok", fn(d, "x", True)))
+            except (nat.MmrsError, ora.OracleError) as e:
+                got.append(("err", str(e)))
+        (ka, a), (kb, b) = got
+        assert ka == kb, (trial, a if ka == "err" else "blob", b if kb == "err" else "blob")
+        assert np.array_equal(a, b, equal_nan=True) if ka == "ok" else a == b, trial
+        parsed += ka == "ok"
+    assert 30 < parsed < 140          # the fuzz exercises both outcomes
