@@ -180,3 +180,39 @@ def test_contour_reader_fuzz_matches_oracle(tmp_path):
         assert np.array_equal(a, b, equal_nan=True) if ka == "ok" else a == b, trial
         parsed += ka == "ok"
     assert 30 < parsed < 140          # the fuzz exercises both outcomes
+
+
+def test_array_ingest_row_orders_and_parallel_paths_match_oracle():
+    """mmrs_geometry_from_arrays borrows the caller's rows, groups them by runs of equal frame ids and, for big inputs,
+    fills / sorts / encodes frame-parallel. Against the oracle's plain restatement: rows in frame order, fully shuffled,
+    interleaved in three passes and reversed; with and without the optional layers and records; small inputs (serial
+    paths) and two that cross the thresholds of the parallel paths (>= 32 768 points, >= 131 072 blob doubles)."""
+    rng = np.random.default_rng(99)
+
+    def layers(nf, npnt):
+        out = {}
+        for name, scale in (("lumen", 1.0), ("eem", 1.4), ("calc", 0.5), ("side", 0.3)):
+            rows = []
+            for f in range(nf):
+                ang = np.sort(rng.uniform(0, 2 * np.pi, npnt))
+                r = scale * (2 + 0.3 * np.cos(2 * ang))
+                rows.append(np.column_stack([np.full(npnt, 10 + f), 4.5 + r * np.cos(ang) + rng.normal(0, 0.01, npnt),
+                                             4.5 + r * np.sin(ang) + rng.normal(0, 0.01, npnt),
+                                             np.full(npnt, 0.5 * (nf - 1 - f))]))
+            out[name] = np.concatenate(rows)
+        return out
+
+    for nf, npnt in ((3, 12), (7, 33), (4, 64), (80, 500), (9, 17), (300, 150)):
+        base = layers(nf, npnt)
+        for variant in range(4):
+            arrs = {}
+            for k, a in base.items():
+                arrs[k] = (a, a[rng.permutation(len(a))], np.concatenate([a[i::3] for i in range(3)]), a[::-1].copy())[variant]
+            ref = np.array([10 + nf - 1, 6.5, 4.5, 0.0])
+            rec = np.array([[10 + f, 1.0, 1.0 + f, np.nan] for f in rng.permutation(nf)]) if variant % 2 else None
+            args = (arrs["lumen"], ref, arrs["eem"] if variant != 3 else None, arrs["calc"] if variant in (0, 2) else None,
+                    arrs["side"] if variant == 0 else None, rec, True, "x")
+            got = nat.geometry_from_arrays(*args)
+            want = ora.build_geometry_from_arrays(*args)
+            assert np.array_equal(got, want), (nf, npnt, variant)
+            assert np.array_equal(mm.PyGeometry.from_blob(got, "x").to_blob(), got)      # Python codec round trip
