@@ -219,3 +219,17 @@ def test_malformed_blobs_are_refused(tmp_path):
     assert len(big) > (1 << 17)                                # large enough for the frame-parallel decoder
     with pytest.raises(nat.MmrsError, match="truncated"):     # ... whose header walk notices the missing tail
         nat.export_single(big[:-100], "x", tmp_path, True, [0], 0)
+
+
+def test_large_geometry_takes_the_frame_parallel_decoder(tmp_path):
+    """A blob above the threshold of the frame-parallel decoder (csrc/mmrs_host.cpp decode: >= 131 072 doubles and
+    >= 16 frames) exports exactly what the Python restatement of the format expects — frame order, contours and points
+    intact."""
+    g = geometry("big", n_frames=48, n=500, with_catheter=True)
+    blob = g.to_blob()
+    assert len(blob) >= (1 << 17) and len(g.frames) >= 16
+    nat.export_single(blob, "big", str(tmp_path), True, [0, 4], 0)
+    for kind, name in (("Lumen", "lumen"), ("Catheter", "catheter")):
+        cs = [f.lumen if kind == "Lumen" else f.extras[kind] for f in g.frames]
+        want = expected_obj(cs, [(0.0, 0.0)] * sum(len(c) for c in cs), str(tmp_path / f"{name}_big.mtl"), True)
+        assert open(tmp_path / f"{name}_big.obj").read() == want
