@@ -312,8 +312,17 @@ def main():
                         "each pair distance once for both directed passes, so it executes about half of that"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on a bounded sample ---------------------------
+    def optional(what, leg):
+        """The reported-beside legs must never cost the headline line: a failure becomes {"error": ...} in its place."""
+        try:
+            return leg()
+        except Exception as e:  # noqa: BLE001
+            print(f"bench.py: {what} leg failed: {type(e).__name__}: {e}", file=sys.stderr)
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+
+    def cpu_leg():
         from oracle import oracle_py as ora
 
         ora.build()
@@ -322,12 +331,16 @@ def main():
         bi, _ = ora.sweep_batch(txy[:n], toff[:2], rxy[:n], roff[:2], cen[:1], 0, STEP_DEG, RANGE_DEG, RANGE_DEG, threads=cores)
         dt = time.perf_counter() - t0
         assert int(bi[0]) == int(res["best_idx"][0]), "GPU and CPU oracle disagree on unit 0"
-        cpu = {"value": ncand / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 of {U} frame pairs x {ncand} candidates (N=M={n}), {cores} threads over candidates, {dt:.1f} s"}
+        return {"value": ncand / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"1 of {U} frame pairs x {ncand} candidates (N=M={n}), {cores} threads over candidates, {dt:.1f} s"}
+
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = optional("cpu_baseline", cpu_leg)
 
     # ---- wall time of the public API call on the same workload ---------------------------------------------------
     api = None
-    if world == 1 and not args.no_api:
+
+    def api_leg():
         import multimodars as mm
 
         def inp(seed, dia):
@@ -345,13 +358,17 @@ def main():
                                  write_obj=False, bruteforce=True, smooth=True, postprocessing=False)
         wall = time.perf_counter() - t0
         st = mm.get_context().process_stats()
-        api = {"call": "from_array_singlepair(bruteforce=True, step 0.01, range 180)", "align_wall_s": wall,
-               "evals": st["evals"], "evals_per_s": st["evals"] / wall, "units": st["units"],
-               "chain_resolved_units": st["chain_resolved"], "f64_rechecks": st["rechecks"]}
+        return {"call": "from_array_singlepair(bruteforce=True, step 0.01, range 180)", "align_wall_s": wall,
+                "evals": st["evals"], "evals_per_s": st["evals"] / wall, "units": st["units"],
+                "chain_resolved_units": st["chain_resolved"], "f64_rechecks": st["rechecks"]}
+
+    if world == 1 and not args.no_api:
+        api = optional("api", api_leg)
 
     # ---- the opt-in tensor-core prefilter tier on a 40-unit slice of the same batch (reported, not the headline) -----
     tcp = None
-    if world == 1 and not args.no_tc:
+
+    def tc_leg():
         Us = 40
         sl = slice(0, Us * n)
         out = {}
@@ -365,20 +382,24 @@ def main():
                 best = t if best is None or t < best else best
             out[name] = (best, r, ctx.prefilter_info())
         info = out["tc"][2]
-        tcp = {"kernel": "k_tc_sweep (tcgen05 kind::f16, bf16x3 split operands, FP32 accumulators in TMEM)",
-               "units": Us, "evals_per_s": Us * ncand / (out["tc"][0] * 1e-3),
-               "dense_evals_per_s": Us * ncand / (out["dense"][0] * 1e-3),
-               "speedup_vs_dense": out["dense"][0] / out["tc"][0], "k1t_ms": info["tc_ms"],
-               "rescored_fraction": info["rescored"] / (Us * ncand), "max_err_over_rmax2": info["max_err"],
-               "window_over_rmax2": info["window"],
-               "identical_selection": bool((out["tc"][1]["best_idx"] == out["dense"][1]["best_idx"]).all()
-                                           and (out["tc"][1]["best_dist"] == out["dense"][1]["best_dist"]).all()),
-               "default": "off (auto resolves to the dense FP32 sweep)"}
+        return {"kernel": "k_tc_sweep (tcgen05 kind::f16, bf16x3 split operands, FP32 accumulators in TMEM)",
+                "units": Us, "evals_per_s": Us * ncand / (out["tc"][0] * 1e-3),
+                "dense_evals_per_s": Us * ncand / (out["dense"][0] * 1e-3),
+                "speedup_vs_dense": out["dense"][0] / out["tc"][0], "k1t_ms": info["tc_ms"],
+                "rescored_fraction": info["rescored"] / (Us * ncand), "max_err_over_rmax2": info["max_err"],
+                "window_over_rmax2": info["window"],
+                "identical_selection": bool((out["tc"][1]["best_idx"] == out["dense"][1]["best_idx"]).all()
+                                            and (out["tc"][1]["best_dist"] == out["dense"][1]["best_dist"]).all()),
+                "default": "off (auto resolves to the dense FP32 sweep)"}
+
+    if world == 1 and not args.no_tc:
+        tcp = optional("tc_prefilter", tc_leg)
 
     # ---- the opt-in EXACT lower-bound pruning tier on the whole batch (reported, not the headline: it does not score
     # every candidate, it proves most of them cannot win; selections identical to the dense sweep) -----------------------
     pruned = None
-    if world == 1 and not args.no_tc:
+
+    def pruned_leg():
         dense_idx, dense_dist = res["best_idx"].copy(), res["best_dist"].copy()
         ctx.sweep_upload(txy, toff, rxy, roff, cen, [grid], mode=0, prefilter=1, prune=1)
         ms = []
@@ -389,12 +410,15 @@ def main():
             ms.append(ctx.timings()["total_ms"])
         info = ctx.prefilter_info()
         pm = float(np.mean(ms[1:]))
-        pruned = {"kernels": "k_lb<1,8> (rows-only bounds over 32 sampled points of each set, 8 candidates per warp) + k_sweep<..,LIST> on the survivors",
-                  "ms_per_step": pm, "candidates_decided_per_s": evals_rank / (pm * 1e-3),
-                  "speedup_vs_dense": float(np.mean(dev_ms)) / pm, "scored_fraction": info["rescored"] / evals_rank,
-                  "bounds_ms": info["tc_ms"], "survivors_ms": info["rescore_ms"],
-                  "identical_selection": bool((r["best_idx"] == dense_idx).all() and (r["best_dist"] == dense_dist).all()),
-                  "default": "off (mmrs_sweep_opts.prune / mmrs_ctx_set_prune / MMRS_PRUNE=1)"}
+        return {"kernels": "k_lb<1,8> (rows-only bounds over 32 sampled points of each set, 8 candidates per warp) + k_sweep<..,LIST> on the survivors",
+                "ms_per_step": pm, "candidates_decided_per_s": evals_rank / (pm * 1e-3),
+                "speedup_vs_dense": float(np.mean(dev_ms)) / pm, "scored_fraction": info["rescored"] / evals_rank,
+                "bounds_ms": info["tc_ms"], "survivors_ms": info["rescore_ms"],
+                "identical_selection": bool((r["best_idx"] == dense_idx).all() and (r["best_dist"] == dense_dist).all()),
+                "default": "off (mmrs_sweep_opts.prune / mmrs_ctx_set_prune / MMRS_PRUNE=1)"}
+
+    if world == 1 and not args.no_tc:
+        pruned = optional("pruned", pruned_leg)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
