@@ -136,6 +136,10 @@ typedef struct mmrs_sweep_opts {
      * candidates. > 0 on, < 0 off, 0 = the context default (mmrs_ctx_set_prune; off unless set). Applies when
      * every unit has >= 128 points per set and the batch averages >= 256 candidates per unit.        */
     int32_t prune;
+    /* Partition of this batch across the ranks of the context (mmrs_ctx_comm_init / mmrs_ctx_set_shard):
+     * 0 = the context's axis (mmrs_ctx_set_partition; whole units unless set), -1 = not partitioned (every rank
+     * sweeps the whole batch by itself: no collective is issued for it), 1 = whole units, 2 = candidate angles. */
+    int32_t partition;
 } mmrs_sweep_opts;
 
 #define MMRS_FLAG_DEGENERATE 1 /* grid degenerate: best_angle = fallback, nothing evaluated */
@@ -169,10 +173,12 @@ int mmrs_sweep_regrid(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, co
 int mmrs_sweep_run(mmrs_ctx* ctx);
 int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out);
 
-/* Launch plan of the uploaded batch: [0] register tile TA (test points per lane of the sweep
- * kernel), [1] 1 if the test set is walked in several register chunks, [2] CTAs of the sweep
- * launch, [3] dynamic shared memory per CTA in bytes.                                      */
-int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[4]);
+/* Launch plan of the uploaded batch. The units are grouped into size classes (register tile, chunked or not, exact
+ * tiling or not) and the sweep kernel is launched once per class. For the class that carries most of the work:
+ * [0] register tile TA (test points per lane of the sweep kernel), [1] bit 0: the test set is walked in several
+ * register chunks, bit 1: exact tiling (32 TA points in register slots + a tail pass over the remaining n mod 32),
+ * [3] dynamic shared memory per CTA in bytes; [2] CTAs of all sweep launches, [4] number of size classes.   */
+int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[5]);
 
 /* Diagnostics on the last run (valid until the next upload).                 */
 /* FP32 distance of every candidate of `unit` (needs opts.keep_dist32).       */
@@ -322,14 +328,37 @@ int mmrs_align_centerline(mmrs_ctx* ctx, int32_t method, const double* centerlin
                           double** out_blobs, int64_t* out_lens, double* spacing_out, double* rotation_rad_out,
                           double* refine_out);
 
-/* ---- multi-GPU: sharding the units of every batched sweep across ranks -------------------------
- * One process per GPU. Every rank calls mmrs_process_cases with IDENTICAL inputs; inside, each batched
- * sweep stage evaluates only this rank's contiguous block of units on its GPU and the per-unit results
- * (40 B each) are combined with `exchange`, an in-place all-reduce(SUM) over int64 words across ranks
- * (non-owned entries are zero, so the sum is an exact merge; the host binds it to ncclAllReduce /
- * torch.distributed.all_reduce). The frame chain, post steps and inter-pullback bookkeeping are then
- * replayed identically on every rank (cheap, O(points)). There is no other collective.
- * world <= 1 or fn == NULL switches sharding off.                                                */
+/* ---- multi-GPU: one process per GPU, every batched sweep partitioned across the ranks ------------------------
+ * The path shards on independent work (the reference runs candidates, and whole pullbacks, concurrently:
+ * process_utils.rs:69-74, binding/entry.rs:140-277). Every rank issues the same sweep calls with the same batch;
+ * each rank's GPU evaluates only its part and the per-unit results are merged so that every rank downloads the
+ * complete, identical result array:
+ *   axis 1 (default) whole UNITS: cost-balanced contiguous blocks of the units; merged with ONE all-reduce(SUM) over the
+ *          32-byte device results per run (entries of other ranks are zero, so the sum is an exact merge);
+ *   axis 2 CANDIDATE ANGLES: every unit's grid is cut into `world` contiguous sub-ranges (global candidate indices
+ *          kept). After the FP32 sweep the packed (distance, index) keys are merged with all-reduce(MIN, uint64) —
+ *          the reduction of process_utils.rs:69-74: lowest distance, ties -> lowest index — so every rank shortlists
+ *          its sub-range against the GLOBAL FP32 minimum; the local f64 winners are all-gathered (32 B per unit and
+ *          rank), the global leftmost f64 arg-min is taken and the tie counts are summed. For single-frame sweeps.
+ * With a communicator bound (mmrs_ctx_comm_init) the collectives are NCCL calls on device buffers on the context's
+ * stream, between the kernels of a run. mmrs_ctx_set_shard binds a host callback instead (axis 1 only).
+ *
+ * mmrs_comm_unique_id: rank 0 creates the rendezvous token (ncclGetUniqueId) and hands it to the other ranks by any
+ * means (MPI, torch.distributed, a file); mmrs_ctx_comm_init is collective (ncclCommInitRank on the context's device).
+ * NCCL is bound at run time (dlopen); both calls fail with MMRS_ERR_STATE where libnccl.so.2 is absent.          */
+#define MMRS_COMM_ID_BYTES 128
+int mmrs_comm_unique_id(uint8_t id_out[MMRS_COMM_ID_BYTES]);
+int mmrs_ctx_comm_init(mmrs_ctx* ctx, const uint8_t id[MMRS_COMM_ID_BYTES], int32_t rank, int32_t world);
+/* Axis used by batches whose opts leave `partition` 0: 1 whole units (default), 2 candidate angles, 0 none. */
+int mmrs_ctx_set_partition(mmrs_ctx* ctx, int32_t axis);
+/* rank / world / axis of the context: out[0..2]; out[3] = 1 when an NCCL communicator is bound. */
+int mmrs_ctx_comm_info(const mmrs_ctx* ctx, int32_t out[4]);
+
+/* ---- the same with a host callback as the transport (e.g. gloo, MPI) ---------------------------------------------
+ * Axis 1 only. The per-unit results (32 B each, 4 int64 words) are combined at download with `exchange`, an in-place
+ * all-reduce(SUM) over int64 words across ranks (non-owned entries are zero, so the sum is an exact merge; the host
+ * binds it to MPI_Allreduce / torch.distributed.all_reduce over gloo, ...). world <= 1 or fn == NULL switches it off.
+ * A communicator bound with mmrs_ctx_comm_init takes precedence.                                            */
 typedef int (*mmrs_exchange_fn)(void* user, int64_t* buf, int64_t n_words);
 int mmrs_ctx_set_shard(mmrs_ctx* ctx, int32_t rank, int32_t world, mmrs_exchange_fn fn, void* user);
 

@@ -999,21 +999,10 @@ struct Searcher {
                 check(mmrs_grid_from_reference_params(step_deg, window_deg, 1, centres[i], limes_deg, &grids[i]));
         }
     }
-    // Unit sharding (mmrs_ctx_set_shard): rank r owns the r-th contiguous balanced block of the U units.
-    bool sharded(size_t U) const { return ctx->shard_world > 1 && ctx->exchange && U > 1; }
-    bool owns(size_t U, size_t u) const {
-        const size_t w = (size_t)ctx->shard_world, r = (size_t)ctx->shard_rank;
-        const size_t base = U / w, extra = U % w;
-        const size_t lo = r * base + std::min(r, extra), hi = lo + base + (r < extra ? 1 : 0);
-        return u >= lo && u < hi;
-    }
-    // Merges `skip` (may be null) with the units other ranks own.
-    const std::vector<char>* shard_skip(size_t U, const std::vector<char>* skip, std::vector<char>& store) const {
-        if (!sharded(U)) return skip;
-        store.assign(U, 0);
-        for (size_t u = 0; u < U; ++u) store[u] = ((skip && (*skip)[u]) || !owns(U, u)) ? 1 : 0;
-        return &store;
-    }
+    // Multi-GPU: the sweep layer partitions every batch of more than one unit across the ranks of the context and
+    // merges the results (mmrs_ctx_comm_init / mmrs_ctx_set_shard); every rank must therefore issue the same batched
+    // sweeps in the same order. A one-unit batch (the chain's own re-search of a tie set) is never partitioned, so it
+    // may be issued by one rank alone.
     std::vector<mmrs_unit_result> finish(size_t U, const std::vector<mmrs_grid>& grids,
                                          const std::vector<int32_t>& which) {
         std::vector<mmrs_unit_result> out(U);
@@ -1027,13 +1016,6 @@ struct Searcher {
             stats[2] += out[i].n_shortlist > 0 ? out[i].n_shortlist : 0;
         }
         stats[4] += ctx->launches + ctx->upload_launches;
-        if (sharded(U)) {  // keep only what this rank evaluated, then sum across ranks (zeros elsewhere)
-            static_assert(sizeof(mmrs_unit_result) == 40, "exchange works on 5 int64 words per unit");
-            for (size_t u = 0; u < U; ++u)
-                if (!owns(U, u)) std::memset(&out[u], 0, sizeof(mmrs_unit_result));
-            if (ctx->exchange(ctx->exchange_user, reinterpret_cast<int64_t*>(out.data()), (int64_t)U * 5) != 0)
-                throw std::runtime_error("mmrs: the exchange callback (all-reduce of per-unit results) failed");
-        }
         return out;
     }
     // Uploads the point sets of `u` and runs the first stage of their search.
@@ -1043,8 +1025,7 @@ struct Searcher {
         if (U == 0) return {};
         std::vector<mmrs_grid> grids;
         std::vector<int32_t> which;
-        std::vector<char> store;
-        make_grids(U, step_deg, window_deg, limes_deg, centres, shard_skip(U, nullptr, store), grids, which);
+        make_grids(U, step_deg, window_deg, limes_deg, centres, nullptr, grids, which);
         mmrs_sweep_batch b{};
         b.n_units = (int64_t)U;
         b.test_xy = u.test.data();
@@ -1058,6 +1039,7 @@ struct Searcher {
         b.mode = mode;
         mmrs_sweep_opts o{};
         o.tie_margin = tie_margin;
+        o.partition = U > 1 ? 0 : -1;
         check(mmrs_sweep_upload(ctx, &b, &o));
         return finish(U, grids, which);
     }
@@ -1068,8 +1050,7 @@ struct Searcher {
         if (U == 0) return {};
         std::vector<mmrs_grid> grids;
         std::vector<int32_t> which;
-        std::vector<char> store;
-        make_grids(U, step_deg, window_deg, limes_deg, centres, shard_skip(U, skip, store), grids, which);
+        make_grids(U, step_deg, window_deg, limes_deg, centres, skip, grids, which);
         check(mmrs_sweep_regrid(ctx, grids.data(), (int64_t)grids.size(), which.empty() ? nullptr : which.data(), tie_margin));
         return finish(U, grids, which);
     }

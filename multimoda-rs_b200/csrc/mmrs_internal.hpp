@@ -21,7 +21,13 @@ struct UnitDesc {
     int n_cand;
     int flags;
     long long dist_off;           // offset of this unit's first candidate in dist32
+    int ta;                       // register tile of this unit's size class (test points per lane of K1)
+    int n_tail;                   // exact tiling: the last n_tail (< 32) test points live in the tail block, not in a slot
+    int c_lo, c_hi;               // candidates [c_lo, c_hi) are swept by THIS rank (all of them unless the batch is
+                                  // partitioned across ranks: whole units -> empty range on the other ranks, candidate
+                                  // axis -> one contiguous sub-range per rank, global indices kept)
 };
+constexpr int kFlagRemote = 0x400;  // internal UnitDesc.flags bit: another rank owns this unit (never leaves the library)
 
 struct WorkItem {
     int unit;
@@ -44,6 +50,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 int set_err(mmrs_ctx* ctx, int code, const std::string& msg);
+int comm_broadcast(mmrs_ctx* ctx, void* host, size_t bytes, int root);
 }  // namespace mmrs
 
 struct mmrs_ctx {
@@ -60,10 +67,17 @@ struct mmrs_ctx {
     bool ready = false, ran = false;
     int64_t n_units = 0;
     int mode = 0;
-    int TA = 2;
-    bool multi = false;
+    // size classes of the uploaded units: K1 is launched once per class (register tile, chunked?, exact tiling?)
+    struct SweepClass {
+        int ta = 2;
+        bool multi = false, tailp = false;
+        size_t smem = 0;
+        size_t work_begin = 0, work_count = 0;  // range of h_work / d_work
+        long long cost = 0;                     // padded pair evaluations per candidate, summed over the class
+    };
+    std::vector<SweepClass> classes;
+    std::vector<int> class_of_unit;
     int max_pts = 1;
-    size_t smem_sweep = 0;
     long long total_cands = 0;
     double opt_rel = 2e-6, opt_abs = 2e-6, tie_margin = 0.0;
     int cap = 64;
@@ -77,6 +91,8 @@ struct mmrs_ctx {
     std::vector<double> h_cs;
     std::vector<unsigned char> h_zero;
     std::vector<float> h_rmax;
+    std::vector<double> f_test, f_ref;        // the batch without its non-finite points (only when one was found)
+    std::vector<int64_t> f_toff, f_roff;
     std::map<int64_t, std::vector<double>> overflow_dist;
     void* h_res = nullptr;  // pinned
     size_t h_res_cap = 0;
@@ -106,10 +122,17 @@ struct mmrs_ctx {
     std::vector<mmrs::WorkItem> h_work_lb;
     mmrs::DevBuf d_units_lb, d_lay_lb, d_work_lb;
 
-    // unit sharding across ranks (mmrs_ctx_set_shard)
+    // partition of every batched sweep across ranks (mmrs_ctx_comm_init / mmrs_ctx_set_shard / mmrs_ctx_set_partition)
     int shard_rank = 0, shard_world = 1;
-    mmrs_exchange_fn exchange = nullptr;
+    mmrs_exchange_fn exchange = nullptr;   // host callback (any transport); used when no NCCL communicator is bound
     void* exchange_user = nullptr;
+    void* comm = nullptr;                  // ncclComm_t (mmrs_comm.hpp): collectives on device buffers, on `stream`
+    int part_axis = 1;                     // 1 = whole units, 2 = candidate sub-ranges of every unit
+    int part_active = 0;                   // axis in force for the uploaded batch (0 = not partitioned)
+    int opt_partition = 0;                 // mmrs_sweep_opts.partition of the uploaded batch
+    long long collectives = 0;             // collectives issued since the context was created
+    mmrs::DevBuf d_bcast;                  // staging of comm_broadcast
+    mmrs::DevBuf d_res_all, d_cnt;         // candidate axis: the ranks' local results [world][U]; (n_shortlist, ties, overflow) sums
 
     // counters of the last mmrs_process_cases call
     int64_t stats[5] = {0, 0, 0, 0, 0};

@@ -4,6 +4,7 @@
 // point needs a CUDA device that can run the sm_100a image.
 // =============================================================================
 #include "mmrs_internal.hpp"
+#include "mmrs_comm.hpp"
 #include "sweep_kernels.cuh"
 #include "tc_kernels.cuh"
 
@@ -11,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -162,6 +164,8 @@ extern "C" void mmrs_ctx_destroy(mmrs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
     ctx->free_all();
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_tc) cudaEventDestroy(ev);
@@ -173,7 +177,7 @@ void mmrs_ctx::free_all() {
     for (DevBuf* b : {&d_test, &d_ref, &d_units, &d_work, &d_lay, &d_cs64, &d_cs32, &d_zero, &d_dist32, &d_key,
                       &d_rmax, &d_sl_base, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp, &d_work_tc,
                       &d_work_list, &d_key_tc, &d_l1_items, &d_l1_count, &d_l1_base, &d_l1_n, &d_units_lb, &d_lay_lb,
-                      &d_work_lb}) {
+                      &d_work_lb, &d_res_all, &d_cnt, &d_bcast}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr;
         b->cap = 0;
@@ -211,33 +215,58 @@ struct ListArgs {  // LIST arguments of k_sweep; all null for the dense sweep
     const unsigned* rmax = nullptr;
     unsigned* diag = nullptr;
 };
-template <int TA, bool MULTI, bool LIST>
+// The dynamic shared-memory limit is per-FUNCTION state shared by every host thread and context on the device, so it is
+// raised ONCE per instantiation to the 227 KB opt-in maximum and never lowered (several contexts may launch the same
+// instantiation with different sizes from different threads: process_cases_pipelined).
+constexpr int kMaxDynSmem = 227 * 1024;
+template <class K>
+static cudaError_t raise_smem_once(K kernel, std::once_flag& once, cudaError_t& result) {
+    std::call_once(once, [&] { result = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem); });
+    return result;
+}
+#define RAISE_SMEM(kernel)                                       \
+    ([&]() -> cudaError_t {                                      \
+        static std::once_flag once;                              \
+        static cudaError_t result = cudaSuccess;                 \
+        return raise_smem_once(kernel, once, result);            \
+    }())
+
+template <int TA, bool MULTI, bool LIST, bool TAILP>
 static void launch_sweep_k(int grid, size_t smem, cudaStream_t s, const UnitDesc* units, const WorkItem* work,
                            const float4* lay, const float2* cs32, float* dist32, unsigned long long* key,
                            const ListArgs& l) {
-    cudaFuncSetAttribute(k_sweep<TA, MULTI, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sweep<TA, MULTI, LIST><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key, l.items, l.n_items, l.cap,
-                                                          l.chunk, l.rmax, l.diag);
+    RAISE_SMEM((k_sweep<TA, MULTI, LIST, TAILP>));
+    k_sweep<TA, MULTI, LIST, TAILP><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key, l.items, l.n_items,
+                                                                 l.cap, l.chunk, l.rmax, l.diag);
 }
 template <int TA>
-static void launch_sweep_ta(bool multi, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
+static void launch_sweep_ta(bool multi, bool tailp, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
                             const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
                             unsigned long long* key, const ListArgs* l) {
+    const ListArgs none{};
+    const ListArgs& la = l ? *l : none;
+    if constexpr (TA % 2 == 0 && TA >= 4) {   // exact tiling is instantiated for even register tiles
+        if (tailp) {
+            if (l) launch_sweep_k<TA, false, true, true>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
+            else launch_sweep_k<TA, false, false, true>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
+            return;
+        }
+    }
     if (l) {
-        if (multi) launch_sweep_k<TA, true, true>(grid, smem, s, units, work, lay, cs32, dist32, key, *l);
-        else launch_sweep_k<TA, false, true>(grid, smem, s, units, work, lay, cs32, dist32, key, *l);
+        if (multi) launch_sweep_k<TA, true, true, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
+        else launch_sweep_k<TA, false, true, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
     } else {
-        if (multi) launch_sweep_k<TA, true, false>(grid, smem, s, units, work, lay, cs32, dist32, key, ListArgs{});
-        else launch_sweep_k<TA, false, false>(grid, smem, s, units, work, lay, cs32, dist32, key, ListArgs{});
+        if (multi) launch_sweep_k<TA, true, false, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
+        else launch_sweep_k<TA, false, false, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
     }
 }
-static bool launch_sweep(int TA, bool multi, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
+static bool launch_sweep(int TA, bool multi, bool tailp, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
                          const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
                          unsigned long long* key, const ListArgs* l = nullptr) {
     switch (TA) {
-#define CASE(T)                                                                        \
-    case T:                                                                            \
-        launch_sweep_ta<T>(multi, grid, smem, s, units, work, lay, cs32, dist32, key, l); \
+#define CASE(T)                                                                               \
+    case T:                                                                                   \
+        launch_sweep_ta<T>(multi, tailp, grid, smem, s, units, work, lay, cs32, dist32, key, l); \
         return true;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
             CASE(15) CASE(16) CASE(17) CASE(18)
@@ -246,69 +275,137 @@ static bool launch_sweep(int TA, bool multi, int grid, size_t smem, cudaStream_t
     return false;
 }
 
-// Choose the register tile: TA in [2,18] minimising the padded work
-// sum_u ceil(n_u / (32 TA)) * 32 TA, ties -> larger TA (fewer chunks).
-static int choose_ta(const std::vector<int>& ns) {
-    int best_ta = 2;
+// Size class of one unit: the register tile TA in [2,18] (test points per lane) minimising the padded work
+// ceil(n / (32 TA)) * 32 TA (a chunk loop adds ~5 % per extra chunk: column minima go through shared memory;
+// ties -> larger TA), against exact tiling: TA = floor(n / 32) full slots plus a tail pass over the remaining
+// R = n mod 32 points, which costs R * ceil(m / 32) pair evaluations per lane at about 1.5x the main loop's price.
+struct ClassChoice {
+    int ta;
+    bool tailp;
+    int n_chunks;
+};
+static ClassChoice choose_class(int n, int m) {
+    ClassChoice best{2, false, 1};
     double best_cost = 1e300;
+    if (n <= 0) return best;
     for (int ta = 2; ta <= 18; ++ta) {
-        double cost = 0;
-        for (int n : ns) {
-            if (n <= 0) continue;
-            const int per = 32 * ta;
-            const int chunks = (n + per - 1) / per;
-            // a chunk loop adds ~5% per extra chunk (column minima go through shared memory)
-            cost += (double)chunks * per * (chunks > 1 ? 1.05 : 1.0);
-        }
-        if (cost <= best_cost) {
-            best_cost = cost;
-            best_ta = ta;
-        }
+        const int per = 32 * ta;
+        const int chunks = (n + per - 1) / per;
+        const double cost = (double)chunks * per * (chunks > 1 ? 1.05 : 1.0);
+        if (cost <= best_cost) best_cost = cost, best = ClassChoice{ta, false, chunks};
     }
-    return best_ta;
+    const int tf = n / 32, R = n - 32 * tf;
+    const bool allow = !(std::getenv("MMRS_NO_TAILPASS") && std::getenv("MMRS_NO_TAILPASS")[0] == '1');
+    if (allow && tf >= 4 && tf <= 18 && tf % 2 == 0 && R > 0 && 2 * ((m + 1) / 2) <= 32 * (tf + 1)) {
+        const double cost = 32.0 * tf + 1.5 * ((R + 1) / 2 * 2) * (double)(tf + 1) * 32.0 / std::max(m, 1);
+        if (cost < best_cost) best = ClassChoice{tf, true, 1};
+    }
+    return best;
 }
 
 // ---- upload ----------------------------------------------------------------------------
 // Points part of an upload: validates the offsets, chooses the register tile, lays every unit out in the
 // staging image (k_prep) and keeps the f64 points on the device. Grid-independent.
-static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
+// Non-finite points. directed_hausdorff (process_utils.rs:84-121) keeps a row minimum only if it is finite (:112) and a
+// NaN distance never passes `d2 < min_sq` (:108): a point with a NaN or infinite coordinate therefore takes part in
+// neither directed pass, in either role, at any angle (rotating it keeps it non-finite) — exactly as if it were not in
+// its set; only the emptiness test (:86-88) sees it, and a set whose points are all non-finite yields 0.0 like an empty
+// one. The sweep kernels order distances by the bit patterns of non-negative finite floats, so such points are dropped
+// HERE (rare: the batch is copied only when one is found). Returns true when a filtered copy was made.
+static bool drop_non_finite(mmrs_ctx* ctx, const mmrs_sweep_batch* b, mmrs_sweep_batch* fb) {
     const int64_t U = b->n_units;
-    std::vector<int> ns(U);
+    const size_t n_test = (size_t)b->test_off[U], n_ref = (size_t)b->ref_off[U];
+    bool finite = true;
+    for (size_t i = 0; i < 2 * n_test && finite; ++i) finite = std::isfinite(b->test_xy[i]);
+    for (size_t i = 0; i < 2 * n_ref && finite; ++i) finite = std::isfinite(b->ref_xy[i]);
+    if (finite) return false;
+    auto filter = [U](const double* xy, const int64_t* off, std::vector<double>& oxy, std::vector<int64_t>& ooff) {
+        oxy.clear();
+        ooff.assign(1, 0);
+        for (int64_t u = 0; u < U; ++u) {
+            for (int64_t i = off[u]; i < off[u + 1]; ++i)
+                if (std::isfinite(xy[2 * i]) && std::isfinite(xy[2 * i + 1])) oxy.push_back(xy[2 * i]), oxy.push_back(xy[2 * i + 1]);
+            ooff.push_back((int64_t)oxy.size() / 2);
+        }
+    };
+    filter(b->test_xy, b->test_off, ctx->f_test, ctx->f_toff);
+    filter(b->ref_xy, b->ref_off, ctx->f_ref, ctx->f_roff);
+    *fb = *b;
+    fb->test_xy = ctx->f_test.data(), fb->test_off = ctx->f_toff.data();
+    fb->ref_xy = ctx->f_ref.data(), fb->ref_off = ctx->f_roff.data();
+    return true;
+}
+
+static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
+    const mmrs_sweep_batch* b = b_in;
+    mmrs_sweep_batch filtered;
+    {
+        const int64_t U0 = b->n_units;
+        for (int64_t u = 0; u < U0; ++u)
+            if (b->test_off[u + 1] < b->test_off[u] || b->ref_off[u + 1] < b->ref_off[u] || b->test_off[0] < 0 || b->ref_off[0] < 0)
+                return set_err(ctx, MMRS_ERR_ARG, "bad point offsets");
+        if ((b->test_off[U0] && !b->test_xy) || (b->ref_off[U0] && !b->ref_xy))
+            return set_err(ctx, MMRS_ERR_ARG, "point arrays are NULL");
+        if (drop_non_finite(ctx, b, &filtered)) b = &filtered;
+    }
+    const int64_t U = b->n_units;
     int max_n = 1, max_m = 1;
     for (int64_t u = 0; u < U; ++u) {
         const int64_t n = b->test_off[u + 1] - b->test_off[u], m = b->ref_off[u + 1] - b->ref_off[u];
         if (n < 0 || m < 0 || n > (1 << 24) || m > (1 << 24)) return set_err(ctx, MMRS_ERR_ARG, "bad point offsets");
-        ns[u] = (int)n;
         max_n = std::max(max_n, (int)n);
         max_m = std::max(max_m, (int)m);
     }
-    const int TA = choose_ta(ns);
-    ctx->TA = TA;
     ctx->max_pts = std::max(max_n, max_m);
     std::vector<UnitDesc>& units = ctx->h_units;
     units.assign(U, UnitDesc{});
+    ctx->classes.clear();
+    ctx->class_of_unit.assign(U, -1);
     long long lay_off = 0;
-    bool multi = false;
-    size_t smem_max = 0;
     for (int64_t u = 0; u < U; ++u) {
         UnitDesc& d = units[u];
         d.test_off = b->test_off[u];
         d.ref_off = b->ref_off[u];
-        d.n = ns[u];
+        d.n = (int)(b->test_off[u + 1] - b->test_off[u]);
         d.m = (int)(b->ref_off[u + 1] - b->ref_off[u]);
         d.cx = b->centre_xy[2 * u];
         d.cy = b->centre_xy[2 * u + 1];
         d.lay_off = lay_off;
+        d.ta = 2;
         if (d.n > 0 && d.m > 0) {
-            d.n_chunks = (d.n + 32 * TA - 1) / (32 * TA);
+            const ClassChoice cc = choose_class(d.n, d.m);
+            d.ta = cc.ta;
+            d.n_chunks = cc.n_chunks;
+            d.n_tail = cc.tailp ? d.n - 32 * cc.ta : 0;
             d.m_pairs = (d.m + 1) / 2;
-            const long long a_elems = (long long)d.n_chunks * ((TA + 1) / 2) * 32, b_elems = d.m_pairs;
-            lay_off += a_elems + b_elems;
-            if (d.n_chunks > 1) multi = true;
-            smem_max = std::max(smem_max, (size_t)(a_elems + b_elems) * 16);
+            const long long a_elems = (long long)d.n_chunks * ((cc.ta + 1) / 2) * 32,
+                            b_elems = cc.tailp ? 16 * (cc.ta + 1) : d.m_pairs,   // exact tiling pads the B block (k_prep)
+                            t_elems = (d.n_tail + 1) / 2;
+            lay_off += a_elems + b_elems + t_elems;
+            // shared memory of a CTA of this unit: mbarrier + key, the staging image, then per warp either the chunked
+            // column minima (MULTI) or the tail pass's column seeds (exact tiling)
+            size_t smem = 16 + (size_t)(a_elems + b_elems + t_elems) * 16;
+            if (d.n_chunks > 1) smem += (size_t)kWarpsPerCta * 2 * d.m_pairs * 4;
+            if (cc.tailp) smem += (size_t)kWarpsPerCta * 32 * (cc.ta + 1) * 4;
+            if (smem > (size_t)kMaxDynSmem)
+                return set_err(ctx, MMRS_ERR_ARG,
+                               "unit too large for the shared-memory staging of the sweep kernel (" +
+                                   std::to_string(smem) + " B > 227 KB)");
+            int k = 0;
+            for (; k < (int)ctx->classes.size(); ++k) {
+                const auto& c = ctx->classes[k];
+                if (c.ta == cc.ta && c.multi == (d.n_chunks > 1) && c.tailp == cc.tailp) break;
+            }
+            if (k == (int)ctx->classes.size()) {
+                mmrs_ctx::SweepClass c;
+                c.ta = cc.ta, c.multi = d.n_chunks > 1, c.tailp = cc.tailp;
+                ctx->classes.push_back(c);
+            }
+            ctx->classes[k].smem = std::max(ctx->classes[k].smem, smem);
+            ctx->classes[k].cost += (long long)d.n_chunks * 32 * cc.ta * d.m;
+            ctx->class_of_unit[u] = k;
         }
     }
-    ctx->multi = multi;
     {   // tensor-core prefilter: every non-empty unit must fit its operand layout
         bool ok = true;
         size_t smem_tc = 0;
@@ -359,27 +456,8 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
             ENSURE(ctx->d_lay_lb, (size_t)off * 16);
         }
     }
-    size_t col_bytes = 0;
-    if (multi) {
-        int max_pairs = 0;
-        for (auto& d : units) max_pairs = std::max(max_pairs, d.m_pairs);
-        col_bytes = (size_t)kWarpsPerCta * 2 * max_pairs * 4;
-    }
-    ctx->smem_sweep = 16 + smem_max + col_bytes;
-    if (ctx->smem_sweep > 227 * 1024)
-        return set_err(ctx, MMRS_ERR_ARG,
-                       "unit too large for the shared-memory staging of the sweep kernel (" +
-                           std::to_string(ctx->smem_sweep) + " B > 227 KB)");
     const size_t n_test = (size_t)b->test_off[U], n_ref = (size_t)b->ref_off[U];
     if ((n_test && !b->test_xy) || (n_ref && !b->ref_xy)) return set_err(ctx, MMRS_ERR_ARG, "point arrays are NULL");
-    if (ctx->lb_shape_ok || ctx->tc_shape_ok) {
-        // The optional tiers order candidates by the bit patterns of non-negative finite floats; a non-finite
-        // coordinate (the reference skips non-finite minima, process_utils.rs:112) sends the batch down the dense path.
-        bool finite = true;
-        for (size_t i = 0; i < 2 * n_test && finite; ++i) finite = std::isfinite(b->test_xy[i]);
-        for (size_t i = 0; i < 2 * n_ref && finite; ++i) finite = std::isfinite(b->ref_xy[i]);
-        if (!finite) ctx->lb_shape_ok = ctx->tc_shape_ok = false;
-    }
     ENSURE(ctx->d_test, n_test * 16);
     ENSURE(ctx->d_ref, n_ref * 16);
     ENSURE(ctx->d_units, U * sizeof(UnitDesc));
@@ -402,8 +480,7 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, units.data(), U * sizeof(UnitDesc), cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_rmax.p, 0, U * 4, s));
     k_prep<<<(unsigned)U, 256, 0, s>>>((const UnitDesc*)ctx->d_units.p, (const double*)ctx->d_test.p,
-                                       (const double*)ctx->d_ref.p, (float4*)ctx->d_lay.p, (unsigned*)ctx->d_rmax.p,
-                                       TA);
+                                       (const double*)ctx->d_ref.p, (float4*)ctx->d_lay.p, (unsigned*)ctx->d_rmax.p);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->upload_launches = 1;
     if (ctx->lb_shape_ok) {
@@ -462,21 +539,64 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
         if (d.n == 0 || d.m == 0) d.flags |= MMRS_FLAG_EMPTY;
         d.dist_off = dist_off;
         dist_off += d.n_cand;
-        if (!d.flags) live += d.n_cand;
+        d.c_lo = 0;
+        d.c_hi = d.n_cand;
     }
     ctx->total_cands = dist_off;
+    // Partition across ranks (mmrs_ctx_comm_init / mmrs_ctx_set_shard): which candidates of which units THIS rank sweeps.
+    {
+        const int world = ctx->shard_world, rank = ctx->shard_rank;
+        int axis = ctx->opt_partition == 0 ? ctx->part_axis : ctx->opt_partition;
+        if (world <= 1 || (!ctx->comm && !ctx->exchange) || axis < 1 || axis > 2) axis = 0;
+        if (axis == 2 && !ctx->comm)
+            return set_err(ctx, MMRS_ERR_STATE, "the candidate-axis partition needs a communicator (mmrs_ctx_comm_init)");
+        ctx->part_active = axis;
+        if (axis == 1) {
+            // whole units in contiguous blocks balanced by cost (pair evaluations), identical on every rank
+            std::vector<double> pre(U + 1, 0.0);
+            for (int64_t u = 0; u < U; ++u) {
+                const UnitDesc& d = units[u];
+                pre[u + 1] = pre[u] + 1.0 + (d.flags ? 0.0 : (double)d.n * d.m * d.n_cand);
+            }
+            const double total = pre[U];
+            for (int64_t u = 0; u < U; ++u) {
+                // owner = the block the unit's cost midpoint falls into
+                const double mid = 0.5 * (pre[u] + pre[u + 1]);
+                int owner = (int)(mid * world / total);
+                owner = std::min(std::max(owner, 0), world - 1);
+                if (owner != rank) units[u].flags |= kFlagRemote, units[u].c_hi = 0;
+            }
+        } else if (axis == 2) {
+            for (int64_t u = 0; u < U; ++u) {
+                UnitDesc& d = units[u];
+                const long long base = d.n_cand / world, extra = d.n_cand % world;
+                d.c_lo = (int)(rank * base + std::min<long long>(rank, extra));
+                d.c_hi = d.c_lo + (int)(base + (rank < extra ? 1 : 0));
+            }
+        }
+    }
+    for (int64_t u = 0; u < U; ++u)
+        if (!units[u].flags) live += units[u].c_hi - units[u].c_lo;
     // work list: one CTA = one unit x one tile of candidates (8 warps, one candidate per warp per pass)
     {
         const long long slots = (long long)ctx->n_sm * 2 * 4;  // CTAs for ~4 waves at 2 CTAs/SM
         long long per_warp = (live + slots * kWarpsPerCta - 1) / (slots * kWarpsPerCta);
-        per_warp = std::max<long long>(1, std::min<long long>(per_warp, 8));
+        // a CTA stages its unit once (one TMA bulk copy) and every warp walks `per_warp` candidates; measured on B200
+        // (profiles/r02_tile_per_warp.txt): 8, 32 and 64 per warp are within 0.5 % of each other, 8 keeps the tail short
+        static const long long cap = std::getenv("MMRS_TILE_PER_WARP") ? std::atoll(std::getenv("MMRS_TILE_PER_WARP")) : 8;
+        per_warp = std::max<long long>(1, std::min<long long>(per_warp, std::max<long long>(cap, 1)));
         const int tile = (int)per_warp * kWarpsPerCta;
         ctx->h_work.clear();
-        for (int64_t u = 0; u < U; ++u) {
-            const UnitDesc& d = units[u];
-            if (d.flags) continue;
-            for (int c0 = 0; c0 < d.n_cand; c0 += tile)
-                ctx->h_work.push_back(WorkItem{(int)u, c0, std::min(tile, d.n_cand - c0), 0});
+        for (size_t k = 0; k < ctx->classes.size(); ++k) {   // one contiguous range of the work list per size class
+            auto& cl = ctx->classes[k];
+            cl.work_begin = ctx->h_work.size();
+            for (int64_t u = 0; u < U; ++u) {
+                const UnitDesc& d = units[u];
+                if (d.flags || ctx->class_of_unit[u] != (int)k) continue;
+                for (int c0 = d.c_lo; c0 < d.c_hi; c0 += tile)
+                    ctx->h_work.push_back(WorkItem{(int)u, c0, std::min(tile, d.c_hi - c0), 0});
+            }
+            cl.work_count = ctx->h_work.size() - cl.work_begin;
         }
     }
     // Tensor-core prefilter: worth it when the units carry enough candidates to amortise the per-CTA operand set-up.
@@ -489,7 +609,7 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
         if (env && *env) mode = (*env == '0') ? 1 : 2;
         // auto (0) currently resolves to the dense FP32 sweep: on B200 the prefilter's per-tile TMEM hand-shakes and
         // the FMNMX-bound epilogue make K1t slower than K1 (17 vs 24 M evaluations/s).
-        ctx->use_tc = mode == 2 && ctx->tc_shape_ok && live_units > 0;
+        ctx->use_tc = mode == 2 && ctx->tc_shape_ok && live_units > 0 && ctx->part_active != 2;
         if (mode == 2 && !ctx->use_tc && ctx->opt_prefilter == 2)
             return set_err(ctx, MMRS_ERR_ARG,
                            "prefilter required but the batch does not fit the tensor-core operand layout (64 <= points "
@@ -525,7 +645,8 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
         const char* env = std::getenv("MMRS_PRUNE");
         int mode = ctx->opt_prune;
         if (env && *env) mode = (*env == '0') ? 0 : 1;
-        ctx->use_prune = mode == 1 && !ctx->use_tc && ctx->lb_shape_ok && live_units > 0 && live >= 256 * live_units;
+        ctx->use_prune = mode == 1 && !ctx->use_tc && ctx->lb_shape_ok && live_units > 0 && live >= 256 * live_units &&
+                         ctx->part_active != 2;
         ctx->h_work_lb.clear();
         if (ctx->use_prune) {
             for (int pass = 0; pass < 2; ++pass)
@@ -606,6 +727,9 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
     ctx->cap = (o && o->shortlist_cap > 0) ? o->shortlist_cap : 64;
     ctx->tie_margin = (o && o->tie_margin > 0) ? o->tie_margin : 0.0;
     ctx->opt_prune = (o && o->prune != 0) ? (o->prune > 0 ? 1 : 0) : ctx->ctx_prune;
+    ctx->opt_partition = o ? o->partition : 0;
+    if (ctx->opt_partition < -1 || ctx->opt_partition > 2)
+        return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: partition must be -1 (off), 0 (context default), 1 (units) or 2 (angles)");
     ctx->opt_prefilter = o ? o->prefilter : 0;
     if (o && o->keep_dist32 && ctx->opt_prefilter == 0) ctx->opt_prefilter = 1;  // exact FP32 for EVERY candidate
     if (o && o->keep_dist32) ctx->opt_prune = 0;
@@ -658,7 +782,7 @@ static int full_f64_unit(mmrs_ctx* ctx, int64_t u, UnitResultDev& r) {
     const UnitDesc& d = ctx->h_units[u];
     ENSURE(ctx->d_tmp, (size_t)d.n_cand * 8);
     const int smem = exact_smem(ctx);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_exact_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(ctx, RAISE_SMEM(k_exact_dense));
     const int grid = std::min(d.n_cand, ctx->n_sm * 8);
     k_exact_dense<<<grid, 256, smem, ctx->stream>>>((const UnitDesc*)ctx->d_units.p, (int)u,
                                                     (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
@@ -711,12 +835,12 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[0], s));
         if (ctx->lb_R == 128) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k_lb<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_lb));
+            CUDA_TRY(ctx, RAISE_SMEM((k_lb<4, 2>)));
             k_lb<4, 2><<<(unsigned)ctx->h_work_lb.size(), kThreads, ctx->smem_lb, s>>>(
                 lbu, (const WorkItem*)ctx->d_work_lb.p, (const float4*)ctx->d_lay_lb.p, (const float2*)ctx->d_cs32.p,
                 (float*)ctx->d_dist32.p);
         } else {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k_lb<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_lb));
+            CUDA_TRY(ctx, RAISE_SMEM((k_lb<1, 8>)));
             k_lb<1, 8><<<(unsigned)ctx->h_work_lb.size(), kThreads, ctx->smem_lb, s>>>(
                 lbu, (const WorkItem*)ctx->d_work_lb.p, (const float4*)ctx->d_lay_lb.p, (const float2*)ctx->d_cs32.p,
                 (float*)ctx->d_dist32.p);
@@ -733,13 +857,18 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         la.chunk = 1;
         la.rmax = (const unsigned*)ctx->d_rmax.p;
         la.diag = (unsigned*)ctx->d_l1_n.p + 2;
-        auto rescore = [&]() {
+        auto rescore = [&]() {   // one launch per size class; each scores the list items of its own units
             const long long grid = ((long long)la.cap + la.chunk - 1) / la.chunk;
-            return launch_sweep(ctx->TA, ctx->multi, (int)grid, ctx->smem_sweep, s, units, nullptr,
-                                (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p,
-                                (unsigned long long*)ctx->d_key.p, &la);
+            for (const auto& cl : ctx->classes) {
+                if (!launch_sweep(cl.ta, cl.multi, cl.tailp, (int)grid, cl.smem, s, units, nullptr,
+                                  (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p,
+                                  (unsigned long long*)ctx->d_key.p, &la))
+                    return false;
+                ctx->launches += 1;
+            }
+            return true;
         };
-        if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
+        if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for this register tile");
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[1], s));
         // survivors: bound <= that distance + twice the FP32 window; everything else cannot be the arg-min
@@ -752,15 +881,15 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         la.n_items = (const unsigned*)ctx->d_l1_n.p;
         la.cap = ctx->l1_cap;
         la.chunk = 32;
-        if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
+        if (!rescore()) return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for this register tile");
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[2], s));
-        ctx->launches += 5;
+        ctx->launches += 3;
     } else if (tc) {
         // tier 0: every candidate on the tensor cores (bf16x3, FP32 accumulate) -> approximate dist32 + per-unit minimum
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_key_tc.p, 0xff, U * 8, s));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_tc));
+        CUDA_TRY(ctx, RAISE_SMEM(k_tc_sweep));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[0], s));
         const char* trace_path = std::getenv("MMRS_TC_TRACE");  // experiments: per-tile clock stamps of CTA 0
         long long* d_trace = nullptr;
@@ -809,20 +938,33 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         la.chunk = 8;
         la.rmax = (const unsigned*)ctx->d_rmax.p;
         la.diag = (unsigned*)ctx->d_l1_n.p + 1;
-        if (!launch_sweep(ctx->TA, ctx->multi, (int)(((long long)ctx->l1_cap + la.chunk - 1) / la.chunk), ctx->smem_sweep, s,
-                          units, nullptr, (const float4*)ctx->d_lay.p,
-                          (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p, &la))
-            return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
+        for (const auto& cl : ctx->classes) {
+            if (!launch_sweep(cl.ta, cl.multi, cl.tailp, (int)(((long long)ctx->l1_cap + la.chunk - 1) / la.chunk), cl.smem, s,
+                              units, nullptr, (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p,
+                              (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p, &la))
+                return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for this register tile");
+            ctx->launches += 1;
+        }
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[2], s));
-        ctx->launches += 3;
+        ctx->launches += 2;
     } else if (!ctx->h_work.empty()) {
-        if (!launch_sweep(ctx->TA, ctx->multi, (int)ctx->h_work.size(), ctx->smem_sweep, s, units,
-                          (const WorkItem*)ctx->d_work.p, (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p,
-                          (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p))
-            return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for TA=" + std::to_string(ctx->TA));
-        CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches += 1;
+        for (const auto& cl : ctx->classes) {   // one launch per size class (register tile / chunked / exact tiling)
+            if (!cl.work_count) continue;
+            if (!launch_sweep(cl.ta, cl.multi, cl.tailp, (int)cl.work_count, cl.smem, s, units,
+                              (const WorkItem*)ctx->d_work.p + cl.work_begin, (const float4*)ctx->d_lay.p,
+                              (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p))
+                return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for this register tile");
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+    }
+    if (ctx->part_active == 2) {
+        // candidate axis: the global FP32 minimum of every unit = min over ranks of the packed (distance, index) keys
+        NcclApi& nc = nccl_api();
+        const int rc = nc.AllReduce(ctx->d_key.p, ctx->d_key.p, (size_t)U, kNcclUint64, kNcclMin, ctx->comm, s);
+        if (rc != kNcclSuccess) return set_err(ctx, MMRS_ERR_CUDA, nccl_err(rc));
+        ctx->collectives += 1;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
     k_shortlist<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p,
@@ -834,7 +976,7 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     {
         const int smem = exact_smem(ctx);
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(ctx, RAISE_SMEM(k_exact));
         const int grid = ctx->n_sm * 8;
         k_exact<<<grid, 256, smem, s>>>(units, (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
                                         (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
@@ -850,8 +992,37 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
                                                          (UnitResultDev*)ctx->d_res.p);
         CUDA_TRY(ctx, cudaGetLastError());
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
     ctx->launches += 3;
+    if (ctx->part_active && ctx->comm) {
+        NcclApi& nc = nccl_api();
+        if (ctx->part_active == 1) {
+            // whole units: entries of the other ranks are zero, so ONE sum over the 32-byte results is an exact merge
+            static_assert(sizeof(UnitResultDev) == 32, "the merge works on 4 int64 words per unit");
+            const int rc = nc.AllReduce(ctx->d_res.p, ctx->d_res.p, (size_t)U * 4, kNcclInt64, kNcclSum, ctx->comm, s);
+            if (rc != kNcclSuccess) return set_err(ctx, MMRS_ERR_CUDA, nccl_err(rc));
+            ctx->collectives += 1;
+        } else {
+            const int W = ctx->shard_world;
+            ENSURE(ctx->d_res_all, (size_t)W * U * sizeof(UnitResultDev));
+            ENSURE(ctx->d_cnt, (size_t)U * 16);
+            int rc = nc.AllGather(ctx->d_res.p, ctx->d_res_all.p, (size_t)U * 4, kNcclInt64, ctx->comm, s);
+            if (rc != kNcclSuccess) return set_err(ctx, MMRS_ERR_CUDA, nccl_err(rc));
+            k_merge_angle<<<(unsigned)((U + 7) / 8), 256, 0, s>>>(
+                units, (int)U, W, (const UnitResultDev*)ctx->d_res_all.p, (const double2*)ctx->d_cs64.p,
+                (const int2*)ctx->d_items.p, (const double*)ctx->d_sl_dist.p, (const int*)ctx->d_sl_count.p,
+                (const unsigned*)ctx->d_sl_base.p, (const unsigned long long*)ctx->d_key.p,
+                (const unsigned*)ctx->d_rmax.p, ctx->tie_margin, (UnitResultDev*)ctx->d_res.p, (int4*)ctx->d_cnt.p);
+            CUDA_TRY(ctx, cudaGetLastError());
+            rc = nc.AllReduce(ctx->d_cnt.p, ctx->d_cnt.p, (size_t)U * 4, kNcclInt32, kNcclSum, ctx->comm, s);
+            if (rc != kNcclSuccess) return set_err(ctx, MMRS_ERR_CUDA, nccl_err(rc));
+            k_finish_angle<<<(unsigned)((U + 255) / 256), 256, 0, s>>>((int)U, (const int4*)ctx->d_cnt.p,
+                                                                       (UnitResultDev*)ctx->d_res.p);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches += 2;
+            ctx->collectives += 2;
+        }
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
     return MMRS_OK;
 }
 
@@ -886,6 +1057,12 @@ extern "C" int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out) {
                      "largest unit list %d), shortlist %.2f, recheck %.2f\n",
                      (long long)U, ctx->total_cands, t[0], ctx->prune_ran ? "pruned:" : ctx->tc_ran ? "tc:" : "dense;", a, b, scored,
                      worst, t[1], t[2]);
+    }
+    if (ctx->part_active == 1 && !ctx->comm && ctx->exchange) {
+        // host transport: the same exact sum-merge through the caller's all-reduce
+        if (ctx->exchange(ctx->exchange_user, reinterpret_cast<int64_t*>(ctx->h_res), (int64_t)U * 4) != 0)
+            return set_err(ctx, MMRS_ERR_CUDA, "mmrs: the exchange callback (all-reduce of per-unit results) failed");
+        ctx->collectives += 1;
     }
     const UnitResultDev* hr = (const UnitResultDev*)ctx->h_res;
     bool need_rmax = false;
@@ -977,13 +1154,18 @@ extern "C" int mmrs_sweep_get_shortlist(mmrs_ctx* ctx, int64_t unit, int64_t* id
     return MMRS_OK;
 }
 
-extern "C" int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[4]) {
+extern "C" int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[5]) {
     if (!ctx || !plan_out) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_plan: NULL argument");
     if (!ctx->ready) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_plan: no batch uploaded");
-    plan_out[0] = ctx->TA;
-    plan_out[1] = ctx->multi ? 1 : 0;
+    // the size class that carries most of the work
+    const mmrs_ctx::SweepClass* top = nullptr;
+    for (const auto& cl : ctx->classes)
+        if (!top || cl.cost > top->cost) top = &cl;
+    plan_out[0] = top ? top->ta : 0;
+    plan_out[1] = top ? (top->multi ? 1 : 0) | (top->tailp ? 2 : 0) : 0;
     plan_out[2] = (int64_t)ctx->h_work.size();
-    plan_out[3] = (int64_t)ctx->smem_sweep;
+    plan_out[3] = top ? (int64_t)top->smem : 0;
+    plan_out[4] = (int64_t)ctx->classes.size();
     return MMRS_OK;
 }
 
@@ -1044,7 +1226,7 @@ extern "C" int mmrs_eval_exact(mmrs_ctx* ctx, const double* test_xy, int64_t n_t
     const int max_n = (int)std::max(n_test, n_ref);
     const int smem = 64 + 2 * max_n * 16;
     if (smem > 227 * 1024) return set_err(ctx, MMRS_ERR_ARG, "mmrs_eval_exact: point sets too large for shared memory");
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_exact_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(ctx, RAISE_SMEM(k_exact_dense));
     const int grid = (int)std::min<int64_t>(n_angles, (int64_t)ctx->n_sm * 8);
     k_exact_dense<<<grid, 256, smem, s>>>((const UnitDesc*)(base + o_unit), 0, (const double*)base,
                                           (const double*)(base + (size_t)n_test * 16), (const double2*)(base + o_cs),
@@ -1102,6 +1284,72 @@ extern "C" int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]) {
     out[2] = b;
     out[3] = (double)h[0];
     out[4] = (double)err;
+    return MMRS_OK;
+}
+
+// ---- communicator ---------------------------------------------------------------------------------------------
+extern "C" int mmrs_comm_unique_id(uint8_t id_out[MMRS_COMM_ID_BYTES]) {
+    if (!id_out) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_comm_unique_id: id_out is NULL");
+    NcclApi& nc = nccl_api();
+    if (!nc.ok()) return set_err(nullptr, MMRS_ERR_STATE, nc.error);
+    static_assert(sizeof(nccl_unique_id) == MMRS_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    nccl_unique_id id;
+    const int rc = nc.GetUniqueId(&id);
+    if (rc != kNcclSuccess) return set_err(nullptr, MMRS_ERR_CUDA, nccl_err(rc));
+    std::memcpy(id_out, &id, sizeof id);
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_ctx_comm_init(mmrs_ctx* ctx, const uint8_t id[MMRS_COMM_ID_BYTES], int32_t rank, int32_t world) {
+    if (!ctx || !id) return set_err(ctx, MMRS_ERR_ARG, "mmrs_ctx_comm_init: NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, MMRS_ERR_ARG, "mmrs_ctx_comm_init: bad rank / world");
+    NcclApi& nc = nccl_api();
+    if (!nc.ok()) return set_err(ctx, MMRS_ERR_STATE, nc.error);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->comm) {
+        nc.CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    nccl_unique_id uid;
+    std::memcpy(&uid, id, sizeof uid);
+    nccl_comm_t comm = nullptr;
+    const int rc = nc.CommInitRank(&comm, world, uid, rank);
+    if (rc != kNcclSuccess) return set_err(ctx, MMRS_ERR_CUDA, nccl_err(rc));
+    ctx->comm = comm;
+    ctx->shard_rank = rank;
+    ctx->shard_world = world;
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_ctx_set_partition(mmrs_ctx* ctx, int32_t axis) {
+    if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_ctx_set_partition: ctx is NULL");
+    if (axis < 0 || axis > 2) return set_err(ctx, MMRS_ERR_ARG, "mmrs_ctx_set_partition: axis must be 0, 1 or 2");
+    ctx->part_axis = axis;
+    return MMRS_OK;
+}
+
+extern "C" int mmrs_ctx_comm_info(const mmrs_ctx* ctx, int32_t out[4]) {
+    if (!ctx || !out) return MMRS_ERR_ARG;
+    out[0] = ctx->shard_rank, out[1] = ctx->shard_world, out[2] = ctx->part_axis, out[3] = ctx->comm ? 1 : 0;
+    return MMRS_OK;
+}
+
+// Broadcast of a host buffer from `root` to every rank through the communicator (device staging, NCCL broadcast on the
+// context's stream). Used by mmrs_process_cases to hand the aligned pullbacks of one rank to the others.
+int mmrs::comm_broadcast(mmrs_ctx* ctx, void* host, size_t bytes, int root) {
+    if (!ctx->comm) return set_err(ctx, MMRS_ERR_STATE, "no communicator bound");
+    if (bytes == 0) return MMRS_OK;
+    NcclApi& nc = nccl_api();
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENSURE(ctx->d_bcast, bytes);
+    if (ctx->shard_rank == root)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_bcast.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = nc.Broadcast(ctx->d_bcast.p, ctx->d_bcast.p, bytes, /*ncclInt8*/ 0, root, ctx->comm, ctx->stream);
+    if (rc != kNcclSuccess) return set_err(ctx, MMRS_ERR_CUDA, nccl_err(rc));
+    if (ctx->shard_rank != root)
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, ctx->d_bcast.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->collectives += 1;
     return MMRS_OK;
 }
 

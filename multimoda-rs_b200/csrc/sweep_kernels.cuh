@@ -29,6 +29,12 @@ namespace mmrs {
 #ifndef MMRS_J_UNROLL
 #define MMRS_J_UNROLL 0  // 0 = default (2)
 #endif
+#ifndef MMRS_EXP_NOTAIL   // timing experiments only (wrong results): skip the tail pass / the seed loads of exact tiling
+#define MMRS_EXP_NOTAIL 0
+#endif
+#ifndef MMRS_EXP_NOSEED
+#define MMRS_EXP_NOSEED 0
+#endif
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 
@@ -102,23 +108,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 //   read instead of a 64-bit pair: the sweep is register-file-bandwidth bound).
 // Indices past the end repeat the last point (a duplicate never changes a
 // min-over-points or a max-over-points).
+// Tail block (exact tiling, UnitDesc.n_tail > 0; after the B block): the n mod 32 test points that do not fill a
+// register slot, two per float4 (x0, y0, x1, y1). K1 scores them in a short pass of its own instead of a padded slot.
 // =============================================================================
 __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restrict__ test_xy,
-                       const double* __restrict__ ref_xy, float4* __restrict__ lay, unsigned* __restrict__ rmax_bits,
-                       int TA) {
+                       const double* __restrict__ ref_xy, float4* __restrict__ lay, unsigned* __restrict__ rmax_bits) {
     const UnitDesc ud = units[blockIdx.x];
     if (ud.n <= 0 || ud.m <= 0) return;
+    const int TA = ud.ta;
     const int half = (TA + 1) / 2, pairs = TA / 2;
     const int a_elems = ud.n_chunks * half * 32;
+    // exact tiling (n_tail > 0): the register slots hold the first 32 TA points only, the rest is the tail block
+    const int n_main = ud.n - ud.n_tail;
+    // exact tiling: the B block is padded to 16 (TA + 1) float4 so that the tail pass can address its reference points
+    // lane + 32 q without clamping (indices past the end repeat the last point)
+    const int b_elems = ud.n_tail > 0 ? 16 * (TA + 1) : ud.m_pairs;
     float4* A = lay + ud.lay_off;
     float4* B = A + a_elems;
+    float4* T = B + b_elems;
     float rmax = 0.f;
     for (int e = threadIdx.x; e < a_elems; e += blockDim.x) {
         int l = e & 31, ck = e >> 5;
         int c = ck / half, k = ck - c * half;
         int i0 = c * 32 * TA + 2 * k * 32 + l, i1 = (k < pairs) ? i0 + 32 : i0;
-        i0 = min(i0, ud.n - 1);
-        i1 = min(i1, ud.n - 1);
+        i0 = min(i0, n_main - 1);
+        i1 = min(i1, n_main - 1);
         const double* p0 = test_xy + 2 * (ud.test_off + i0);
         const double* p1 = test_xy + 2 * (ud.test_off + i1);
         float4 v;
@@ -129,13 +143,23 @@ __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restr
         A[e] = v;
         rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    for (int j = threadIdx.x; j < ud.m_pairs; j += blockDim.x) {
+    for (int j = threadIdx.x; j < b_elems; j += blockDim.x) {
         const int j0 = min(2 * j, ud.m - 1), j1 = min(2 * j + 1, ud.m - 1);
         const double* p0 = ref_xy + 2 * (ud.ref_off + j0);
         const double* p1 = ref_xy + 2 * (ud.ref_off + j1);
         const float4 v = make_float4((float)(p0[0] - ud.cx), (float)(p0[1] - ud.cy), (float)(p1[0] - ud.cx),
                                      (float)(p1[1] - ud.cy));
         B[j] = v;
+        rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    // tail block: float4 t = tail points 2t and 2t+1 as (x0, y0, x1, y1) (an odd count repeats the last point)
+    for (int t = threadIdx.x; t < (ud.n_tail + 1) / 2; t += blockDim.x) {
+        const int i0 = n_main + min(2 * t, ud.n_tail - 1), i1 = n_main + min(2 * t + 1, ud.n_tail - 1);
+        const double* p0 = test_xy + 2 * (ud.test_off + i0);
+        const double* p1 = test_xy + 2 * (ud.test_off + i1);
+        const float4 v = make_float4((float)(p0[0] - ud.cx), (float)(p0[1] - ud.cy), (float)(p1[0] - ud.cx),
+                                     (float)(p1[1] - ud.cy));
+        T[t] = v;
         rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
     unsigned rb = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
@@ -158,13 +182,22 @@ __global__ void k_cs32(const double2* __restrict__ cs64, float2* __restrict__ cs
 //               units), so the SMs stay busy however unevenly the survivors are spread over the units. Same arithmetic;
 //               overwrites the dist32 entries and records the largest |d_old^2 - d_fp32^2| / Rmax^2 (the tensor-core
 //               prefilter's error, checked against its window).
-template <int TA, bool MULTI, bool LIST>
+// TAILP = true : exact tiling for a test set of 32 TA + R points (0 < R < 32, single chunk). The R tail points would
+//               waste most of a padded register slot (520 points: slot 17 carries 8 points and 24 duplicates, 4.4 % of
+//               the launch), so per candidate the warp first runs a short pass with the roles swapped: every lane
+//               holds ceil(M / 32) reference points in registers, the rotated tail points are broadcast two at a time;
+//               the tail's row minima are finished with one REDUX each and its column minima — lane-local, no REDUX —
+//               go to a per-warp shared-memory array from which the main loop seeds its column accumulators (one
+//               broadcast LDS.64 per two reference points; the seed takes the free slot of the first 3-input minimum).
+template <int TA, bool MULTI, bool LIST, bool TAILP>
 __global__ void __launch_bounds__(kThreads, 2)
     k_sweep(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
             const float2* __restrict__ cs32, float* __restrict__ dist32, unsigned long long* __restrict__ key,
             const int2* __restrict__ l_items, const unsigned* __restrict__ l_nitems, unsigned l_cap, int l_chunk,
             const unsigned* __restrict__ rmax_bits, unsigned* __restrict__ diag) {
     static_assert(TA >= 2 && TA <= 18, "register tile out of range");
+    static_assert(!(TAILP && MULTI), "the tail pass is for single-chunk units");
+    constexpr int SB = TA + 1;         // TAILP: reference points per lane of the tail pass (M <= 32 SB)
     constexpr int H = TA / 2;          // packed pairs of test points per lane
     constexpr bool TAIL = (TA & 1);    // plus one unpaired point when TA is odd
     constexpr int S = H + (TAIL ? 1 : 0);
@@ -205,15 +238,23 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
     }
     const UnitDesc ud = units[unit];
+    if (LIST && (ud.ta != TA || (ud.n_chunks > 1) != MULTI || (ud.n_tail > 0) != TAILP)) {
+        // a run of another size class: the launch of that class scores it (uniform per CTA: before any barrier use)
+        g_pos = run_end;
+        if (g_pos >= g_hi) break;
+        continue;
+    }
     const int a_elems = ud.n_chunks * S * 32;
-    const int b_elems = ud.m_pairs;          // float4 per PAIR of reference points
+    const int b_elems = TAILP ? 16 * SB : ud.m_pairs;   // float4 per PAIR of reference points (exact tiling: padded)
     const int b_pts = 2 * ud.m_pairs;
+    const int t_elems = TAILP ? (ud.n_tail + 1) / 2 : 0;   // float4 per PAIR of tail points
     float4* sB = sA + a_elems;
-    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems);  // MULTI only: [warp][b_pts]
+    const float4* sT = sB + b_elems;
+    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems + t_elems);  // MULTI: [warp][b_pts]; TAILP: [warp][32 SB]
 
     if (threadIdx.x == 0) {
         *s_key = ~0ull;
-        const uint32_t bytes = (uint32_t)(a_elems + b_elems) * 16u;
+        const uint32_t bytes = (uint32_t)(a_elems + b_elems + t_elems) * 16u;
         mbar_expect_tx(bar, bytes);
         tma_bulk_g2s(sA, lay + ud.lay_off, bytes, bar);
     }
@@ -222,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     phase ^= 1u;
 
     unsigned long long best = ~0ull;
-    unsigned* my_col = s_col + wid * b_pts;
+    unsigned* my_col = s_col + wid * (TAILP ? 32 * SB : b_pts);
     // LIST: squared give-up threshold from the unit's best exact distance so far (bits; 0xffffffff = none yet)
     unsigned give_up = 0xffffffffu;
     if (LIST) {
@@ -239,6 +280,58 @@ __global__ void __launch_bounds__(kThreads, 2)
         const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
         unsigned rowmax = 0u, colmax = 0u;  // bit patterns of non-negative floats order like unsigned ints
         bool gave_up = false;
+
+        if (TAILP) {
+            // Tail pass, roles swapped: this lane's reference points lane, lane + 32, ... in registers (indices past the
+            // end repeat the last stored point), the rotated tail points broadcast two at a time.
+            const float2* sBp = reinterpret_cast<const float2*>(sB) + lane;
+            float bx[SB], by[SB], tc[SB];
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                const float2 b = sBp[32 * q];   // one base register, immediate offsets (the B block is padded to 32 SB points)
+                bx[q] = b.x;
+                by[q] = b.y;
+                tc[q] = INF;
+            }
+#if MMRS_EXP_NOTAIL
+            for (int t = 0; t < 0; ++t) {
+#else
+#pragma unroll 1
+            for (int t = 0; t < t_elems; ++t) {
+#endif
+                const float4 a = sT[t];  // (x0, y0, x1, y1): broadcast
+                const uint64_t X2 = pk(a.x, a.z), Y2 = pk(a.y, a.w);
+                const uint64_t PX = fma2(Y2, NS2, mul2(X2, C2)), PY = fma2(X2, S2, mul2(Y2, C2));
+                float r0 = INF, r1 = INF;   // row minima of the two tail points over this lane's reference points
+#pragma unroll
+                for (int q = 0; q < SB; q += 2) {
+                    const uint64_t dxa = sub2(PX, pk(bx[q], bx[q])), dya = sub2(PY, pk(by[q], by[q]));
+                    const uint64_t da = fma2(dxa, dxa, mul2(dya, dya));   // (|t0 - b_q|^2, |t1 - b_q|^2)
+                    float a0, a1;
+                    upk(da, a0, a1);
+                    tc[q] = min3(tc[q], a0, a1);
+                    if (q + 1 < SB) {
+                        const uint64_t dxb = sub2(PX, pk(bx[q + 1], bx[q + 1])), dyb = sub2(PY, pk(by[q + 1], by[q + 1]));
+                        const uint64_t db = fma2(dxb, dxb, mul2(dyb, dyb));
+                        float b0, b1;
+                        upk(db, b0, b1);
+                        tc[q + 1] = min3(tc[q + 1], b0, b1);
+                        r0 = min3(r0, a0, b0);
+                        r1 = min3(r1, a1, b1);
+                    } else {
+                        r0 = fminf(r0, a0);
+                        r1 = fminf(r1, a1);
+                    }
+                }
+                const unsigned m0 = __reduce_min_sync(0xffffffffu, __float_as_uint(r0));
+                const unsigned m1 = __reduce_min_sync(0xffffffffu, __float_as_uint(r1));
+                rowmax = max(rowmax, max(m0, m1));
+            }
+            __syncwarp();  // the previous candidate's main loop is done reading the seeds
+#pragma unroll
+            for (int q = 0; q < SB; ++q) my_col[lane + 32 * q] = __float_as_uint(tc[q]);
+            __syncwarp();
+        }
 
         for (int ch = 0; ch < ud.n_chunks; ++ch) {
             uint64_t AX[H], AY[H];
@@ -265,6 +358,11 @@ __global__ void __launch_bounds__(kThreads, 2)
                 const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y);
                 const uint64_t bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
                 float c0 = INF, c1 = INF;
+                if (TAILP && !MMRS_EXP_NOSEED) {  // the tail's column minima seed the accumulators (every lane: a minimum is idempotent)
+                    const uint2 seed = *reinterpret_cast<const uint2*>(&my_col[2 * j]);
+                    c0 = __uint_as_float(seed.x);
+                    c1 = __uint_as_float(seed.y);
+                }
                 if (MULTI && ch > 0 && lane == 0) {
                     // Column minima of the previous chunks enter lane 0's accumulators up front: the load is
                     // issued a whole iteration before its use and the warp REDUX below does the merge for free.
@@ -276,8 +374,8 @@ __global__ void __launch_bounds__(kThreads, 2)
                     const float ex0 = tx - B.x, ey0 = ty - B.y, ex1 = tx - B.z, ey1 = ty - B.w;
                     const float t0 = fmaf(ex0, ex0, ey0 * ey0), t1 = fmaf(ex1, ex1, ey1 * ey1);
                     row[TA - 1] = min3(row[TA - 1], t0, t1);
-                    c0 = MULTI ? fminf(c0, t0) : t0;  // single-chunk: the tail's distances seed the column minima
-                    c1 = MULTI ? fminf(c1, t1) : t1;
+                    c0 = (MULTI || TAILP) ? fminf(c0, t0) : t0;  // plain single-chunk: these distances seed the column minima
+                    c1 = (MULTI || TAILP) ? fminf(c1, t1) : t1;
                 }
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
@@ -548,7 +646,7 @@ __global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __r
     __shared__ unsigned s_base;
     const int u = blockIdx.x;
     const UnitDesc ud = units[u];
-    if (ud.n_cand <= 0 || ud.n <= 0 || ud.m <= 0) {
+    if (ud.n_cand <= 0 || ud.n <= 0 || ud.m <= 0 || ud.c_hi <= ud.c_lo) {   // nothing of this unit is swept here
         if (threadIdx.x == 0) {
             sl_count[u] = 0;
             sl_base[u] = 0;
@@ -570,7 +668,7 @@ __global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __r
                                 : dmin * (1.0f + rel) + abs_scale * rmax;
     const float* d = dist32 + ud.dist_off;
     int mine = 0;
-    for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x) mine += (d[c] <= thr) ? 1 : 0;
+    for (int c = ud.c_lo + threadIdx.x; c < ud.c_hi; c += blockDim.x) mine += (d[c] <= thr) ? 1 : 0;
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_n, mine);
     __syncthreads();
@@ -588,7 +686,7 @@ __global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __r
             items[k] = make_int2(-1, 0);
         return;
     }
-    for (int c = threadIdx.x; c < ud.n_cand; c += blockDim.x)
+    for (int c = ud.c_lo + threadIdx.x; c < ud.c_hi; c += blockDim.x)
         if (d[c] <= thr) items[base + atomicAdd(&s_pos, 1)] = make_int2(u, c);
 }
 
@@ -719,6 +817,13 @@ __global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const 
     if (u >= n_units) return;
     const int n = sl_count[u];
     UnitResultDev r;
+    if (units[u].flags & kFlagRemote) {   // another rank owns this unit: all-zero entry, the merge is a sum
+        if (lane == 0) {
+            r.best_idx = 0, r.best_dist = 0.0, r.best_d32 = 0.f, r.n_shortlist = 0, r.n_ties = 0, r.flags = 0;
+            res[u] = r;
+        }
+        return;
+    }
     r.best_idx = -1;
     r.best_dist = 0.0;
     r.best_d32 = __uint_as_float((unsigned)(key[u] >> 32));
@@ -764,6 +869,70 @@ __global__ void k_select(const UnitDesc* __restrict__ units, int n_units, const 
         r.n_ties = ties + 1;
     }
     if (lane == 0) res[u] = r;
+}
+
+// =============================================================================
+// Candidate-axis partition (mmrs_ctx_set_partition 2): every rank swept one contiguous candidate sub-range of every
+// unit and holds its LOCAL leftmost f64 arg-min (k_select over its own shortlist, which was cut against the GLOBAL
+// FP32 minimum: the packed keys were merged with all-reduce(MIN, uint64) before k_shortlist). res_all = the ranks'
+// local results after the all-gather, [world][n_units].
+//   k_merge_angle   global leftmost f64 arg-min (lowest distance, ties -> lowest candidate index: process_utils.rs:69-74)
+//                   and THIS rank's share of the counts: its shortlist size, its candidates within tie_margin of the
+//                   global winner whose angle differs from the winner's, and whether its pool overflowed.
+//   k_finish_angle  after the all-reduce(SUM) of those counts.
+// One warp per unit.
+// =============================================================================
+__global__ void k_merge_angle(const UnitDesc* __restrict__ units, int n_units, int world,
+                              const UnitResultDev* __restrict__ res_all, const double2* __restrict__ cs64,
+                              const int2* __restrict__ items, const double* __restrict__ sl_dist,
+                              const int* __restrict__ sl_count, const unsigned* __restrict__ sl_base,
+                              const unsigned long long* __restrict__ key, const unsigned* __restrict__ rmax_bits,
+                              double tie_margin, UnitResultDev* __restrict__ res, int4* __restrict__ cnt) {
+    const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (u >= n_units) return;
+    long long bi = -1;
+    double bd = 0.0;
+    for (int r = 0; r < world; ++r) {   // rank order = candidate order, but compare explicitly
+        const UnitResultDev x = res_all[(size_t)r * n_units + u];
+        if (x.best_idx < 0) continue;
+        if (bi < 0 || x.best_dist < bd || (x.best_dist == bd && x.best_idx < bi)) bi = x.best_idx, bd = x.best_dist;
+    }
+    const int n = sl_count[u];
+    int ties = 0;
+    if (bi >= 0 && n > 0) {
+        const unsigned base = sl_base[u];
+        const double lim = bd + tie_margin * fmax(1.0, (double)__uint_as_float(rmax_bits[u]));
+        const long long co = units[u].cand_off;
+        const double2 wcs = cs64[co + bi];
+        for (int k = lane; k < n; k += 32) {
+            const int i = items[base + k].y;
+            if (i == bi || sl_dist[base + k] > lim) continue;
+            const double2 c = cs64[co + i];
+            ties += (c.x != wcs.x || c.y != wcs.y) ? 1 : 0;
+        }
+        for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
+    }
+    if (lane == 0) {
+        UnitResultDev r;
+        r.best_idx = bi;
+        r.best_dist = bd;
+        r.best_d32 = __uint_as_float((unsigned)(key[u] >> 32));
+        r.n_shortlist = 0;
+        r.n_ties = 0;
+        r.flags = units[u].flags;
+        res[u] = r;
+        cnt[u] = make_int4(n > 0 ? n : 0, ties, n < 0 ? 1 : 0, 0);
+    }
+}
+
+__global__ void k_finish_angle(int n_units, const int4* __restrict__ cnt, UnitResultDev* __restrict__ res) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const int4 c = cnt[u];
+    // a pool overflow on any rank: every rank rechecks ALL candidates of the unit in f64 at download (negative count)
+    res[u].n_shortlist = c.z ? -1 : c.x;
+    res[u].n_ties = res[u].best_idx >= 0 ? c.y + 1 : 0;
 }
 
 // =============================================================================

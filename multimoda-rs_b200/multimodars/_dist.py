@@ -180,6 +180,22 @@ def make_exchange(group=None):
     return allreduce_sum_int64
 
 
+def init_comm(ctx, group=None, axis: int = 1):
+    """Binds an NCCL communicator of its own to `ctx` (mmrs_ctx_comm_init): rank 0 creates the rendezvous token, the
+    process group carries it to the other ranks. From then on every batched sweep of `ctx` is partitioned across the
+    ranks (axis 1: whole units, 2: candidate angles) and merged by NCCL collectives on device buffers, on the
+    context's own stream — no host staging (mmrs_b200.h, "multi-GPU")."""
+    import torch.distributed as dist
+
+    from . import _native as nat
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [nat.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(box[0], rank, world)
+    ctx.set_partition(axis)
+
+
 def enable_unit_sharding(ctx, group=None):
     """Shard the units of every batched sweep of `ctx` (one frame pair = one unit) across the ranks of `group`:
     each rank sweeps its block on its own GPU; only 40 B per unit cross NVLink (one all-reduce per search stage)."""

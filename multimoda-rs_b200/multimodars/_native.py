@@ -39,7 +39,7 @@ class SweepBatch(C.Structure):
 class SweepOpts(C.Structure):
     _fields_ = [("shortlist_rel", C.c_double), ("shortlist_abs", C.c_double), ("shortlist_cap", C.c_int32),
                 ("tie_margin", C.c_double), ("keep_dist32", C.c_int32), ("prefilter", C.c_int32),
-                ("prefilter_abs", C.c_double), ("prune", C.c_int32)]
+                ("prefilter_abs", C.c_double), ("prune", C.c_int32), ("partition", C.c_int32)]
 
 
 class UnitResult(C.Structure):
@@ -76,6 +76,7 @@ EXPORTS = [
     "mmrs_eval_exact", "mmrs_fp32_probe", "mmrs_free", "mmrs_geometry_from_dir", "mmrs_geometry_from_arrays",
     "mmrs_process_cases", "mmrs_process_stats", "mmrs_ctx_set_shard", "mmrs_export_pair", "mmrs_export_single",
     "mmrs_align_centerline", "mmrs_sweep_prefilter_info", "mmrs_ctx_set_prune", "mmrs_contour_metrics",
+    "mmrs_comm_unique_id", "mmrs_ctx_comm_init", "mmrs_ctx_set_partition", "mmrs_ctx_comm_info",
 ]
 
 _lib = None
@@ -191,11 +192,12 @@ class Context:
 
     @staticmethod
     def _opts(shortlist_rel=0.0, shortlist_abs=0.0, shortlist_cap=0, tie_margin=0.0, keep_dist32=False, prefilter=0,
-              prefilter_abs=0.0, prune=0):
+              prefilter_abs=0.0, prune=0, partition=0):
         """prefilter: 0 auto, 1 off (dense FP32 sweep), 2 required (tensor-core tier, mmrs_b200.h).
-        prune: > 0 exact lower-bound pruning on, < 0 off, 0 the context default (set_prune)."""
+        prune: > 0 exact lower-bound pruning on, < 0 off, 0 the context default (set_prune).
+        partition: 0 the context's axis, -1 not partitioned, 1 whole units, 2 candidate angles (comm_init)."""
         return SweepOpts(shortlist_rel, shortlist_abs, shortlist_cap, tie_margin, int(keep_dist32), int(prefilter),
-                         float(prefilter_abs), int(prune))
+                         float(prefilter_abs), int(prune), int(partition))
 
     def set_prune(self, on: bool):
         """mmrs_ctx_set_prune: context-wide default for exact lower-bound pruning (mmrs_process_cases uses it)."""
@@ -232,9 +234,10 @@ class Context:
         return out
 
     def plan(self):
-        p = (C.c_int64 * 4)()
+        p = (C.c_int64 * 5)()
         self._check(lib().mmrs_sweep_plan(self._p, p))
-        return dict(TA=p[0], multi=bool(p[1]), ctas=p[2], smem_bytes=p[3])
+        return dict(TA=p[0], multi=bool(p[1] & 1), exact_tiling=bool(p[1] & 2), ctas=p[2], smem_bytes=p[3],
+                    size_classes=p[4])
 
     def dist32(self, unit, n_cand):
         out = np.empty(n_cand, dtype=np.float32)
@@ -298,10 +301,42 @@ class Context:
         self._exchange_cb = EXCHANGE_FN(_cb)   # keep the trampoline alive
         self._check(lib().mmrs_ctx_set_shard(self._p, int(rank), int(world), self._exchange_cb, None))
 
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        """mmrs_ctx_comm_init: binds an NCCL communicator (collective over all `world` ranks). `uid` is the 128-byte
+        token rank 0 obtained from comm_unique_id() and handed to the others (multimodars._dist.init_comm)."""
+        if len(uid) != COMM_ID_BYTES:
+            raise ValueError("uid must be 128 bytes")
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(uid)
+        lib().mmrs_ctx_comm_init.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
+        self._check(lib().mmrs_ctx_comm_init(self._p, buf, int(rank), int(world)))
+
+    def set_partition(self, axis: int):
+        """mmrs_ctx_set_partition: 1 whole units (default), 2 candidate angles, 0 none."""
+        lib().mmrs_ctx_set_partition.argtypes = [C.c_void_p, C.c_int32]
+        self._check(lib().mmrs_ctx_set_partition(self._p, int(axis)))
+
+    def comm_info(self):
+        out = (C.c_int32 * 4)()
+        lib().mmrs_ctx_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        lib().mmrs_ctx_comm_info(self._p, out)
+        return dict(rank=out[0], world=out[1], axis=out[2], nccl=bool(out[3]))
+
     def process_stats(self):
         s = (C.c_int64 * 5)()
         self._check(lib().mmrs_process_stats(self._p, s))
         return dict(units=s[0], evals=s[1], rechecks=s[2], chain_resolved=s[3], launches=s[4])
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """mmrs_comm_unique_id (ncclGetUniqueId): called on rank 0, the token goes to every rank's comm_init."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    lib().mmrs_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    if lib().mmrs_comm_unique_id(buf):
+        raise MmrsError(_err(None))
+    return bytes(buf)
 
 
 def contour_metrics(xyz, centroid=None):

@@ -13,8 +13,9 @@ import bench  # noqa: E402
 
 
 def test_workload_shape_is_baseline_config_2():
-    txy, toff, rxy, roff, cen, U, n = bench.make_units(20261018)
+    txy, toff, rxy, roff, cen, U, n = bench.make_units(20261018, n_pairs=1)
     assert U == 398 and n == 520                       # 2 pullbacks x 199 frame pairs, 500 lumen + 20 catheter points
+    assert bench.N_PAIRS == 8                          # the bench batch: the same 8 pullback pairs at every --gpus N
     assert txy.shape == (U * n, 2) and rxy.shape == (U * n, 2) and toff[-1] == U * n
     # units are centred on the frame (lumen) centroid, like align_within_many builds them
     assert abs(txy[:500].mean(axis=0)).max() < 1e-12
@@ -32,4 +33,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "36000" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"] == bench.WORKLOAD
+    assert d["config"]["workload"] == bench.WORKLOAD and d["scaling"] == "strong"
+    # the reference arm's config is the GPU arm's (the driver compares them): the bounded sample lives in cpu_baseline
+    assert d["config"]["units"] == 398 * bench.N_PAIRS and d["config"]["candidates_per_unit"] == 36000
+    assert "sample" not in d["config"] and "1 of the 3184" in d["cpu_baseline"]["sample"]

@@ -299,3 +299,79 @@ def test_fp32_error_stays_inside_half_the_shortlist_window(ctx):
 def test_fp32_probe_reports_plausible_peak(ctx):
     tf = ctx.fp32_probe(2048)
     assert 20.0 < tf < 90.0, tf
+
+
+# ---- exact tiling (tail pass) and size classes -----------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+def test_exact_tiling_tail_pass(ctx, mode):
+    """Test sets of 32 TA + R points (R = 1 ... 31) take the exact-tiling kernel: 32 TA points in register slots and
+    a tail pass over the rest. Odd and even reference counts, reference sets at the edge of the tail pass's
+    register budget (M <= 32 (TA + 1)), and the same sizes one point past it (padded slot instead)."""
+    rng = np.random.default_rng(21 + mode)
+    sizes = [(520, 520), (521, 519), (513, 544), (543, 512), (520, 545), (130, 128), (159, 160), (200, 193), (577, 600)]
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, sizes)
+    g = nat.make_grid(0.25, 45.0)
+    res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=mode, keep_dist32=True)
+    assert ctx.plan()["size_classes"] >= 3
+    check_against_oracle(ctx, tests, refs, cents, res, 0.25, 45.0, mode)
+
+
+def test_exact_tiling_is_the_plan_for_520_points(ctx):
+    rng = np.random.default_rng(23)
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, [(520, 520)] * 3)
+    ctx.sweep_upload(txy, toff, rxy, roff, cents, [nat.make_grid(1.0, 20.0)], mode=0)
+    p = ctx.plan()
+    assert (p["TA"], p["multi"], p["exact_tiling"], p["size_classes"]) == (16, False, True, 1)
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, [(510, 510)] * 3)
+    ctx.sweep_upload(txy, toff, rxy, roff, cents, [nat.make_grid(1.0, 20.0)], mode=0)
+    p = ctx.plan()
+    assert (p["TA"], p["multi"], p["exact_tiling"]) == (16, False, False)
+
+
+def test_mixed_size_classes_in_one_batch(ctx):
+    """520-point frame pairs next to OCT-resolution (2 020, four register chunks) and small units: one launch per
+    size class instead of one register tile for the whole batch; pruned list re-scoring goes through the classes too."""
+    rng = np.random.default_rng(29)
+    sizes = [(520, 520), (2020, 2020), (300, 310), (520, 520), (1000, 1000), (2020, 2000)]
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, sizes)
+    g = nat.make_grid(0.1, 30.0)
+    res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=0, keep_dist32=True)
+    assert ctx.plan()["size_classes"] >= 3
+    check_against_oracle(ctx, tests, refs, cents, res, 0.1, 30.0, 0)
+    pr = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=0, prune=1)
+    assert ctx.prefilter_info()["kind"] == "lower-bound pruning"
+    for k in ("best_idx", "best_angle", "best_dist", "n_ties"):
+        assert (pr[k] == res[k]).all(), k
+
+
+# ---- non-finite coordinates (process_utils.rs:108, :112) -------------------------------------------------
+def test_non_finite_points_take_no_part(ctx):
+    """A NaN distance never passes `d2 < min_sq` and a non-finite row minimum is skipped (process_utils.rs:104-114), so
+    a point with a NaN / infinite coordinate takes part in neither directed pass, in either role. Units with such
+    points in the test set, in the reference set, in both, and a set made ONLY of them (every candidate costs 0.0, the
+    leftmost wins) must select what the oracle's literal loops select, with bit-equal f64 distances."""
+    rng = np.random.default_rng(31)
+    sizes = [(200, 200), (520, 520), (130, 140), (64, 64), (300, 300)]
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, sizes)
+    nan, inf = float("nan"), float("inf")
+    tests[0][7] = (nan, 1.0)
+    tests[0][100] = (inf, -inf)
+    refs[1][0] = (nan, nan)
+    refs[1][519] = (2.0, inf)
+    tests[2][5] = (nan, nan)
+    refs[2][9] = (-inf, 0.5)
+    tests[3][:] = nan                      # all rows non-finite: both directed distances are 0.0 at every angle
+    txy, rxy = np.concatenate(tests), np.concatenate(refs)
+    g = nat.make_grid(0.5, 60.0)
+    for mode in (0, 1):
+        res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=mode)
+        for u, (t, r, c) in enumerate(zip(tests, refs, cents)):
+            o = ora.sweep(t, r, c, mode, 0.5, 60.0)
+            assert res["best_idx"][u] == o["index"] and res["best_angle"][u] == o["angle"], (mode, u)
+            assert res["best_dist"][u] == o["cost"], (mode, u)
+        assert res["best_idx"][3] == 0 and res["best_dist"][3] == 0.0
+    # the literal cost closure on the device (no filtering in front of it) agrees with the oracle's loops too
+    angles = np.array([0.0, 0.3, -1.2])
+    for u in (0, 1, 2, 3):
+        got = ctx.eval_exact(tests[u], refs[u], cents[u], 0, angles)
+        assert np.array_equal(got, ora.costs(tests[u], refs[u], cents[u], 0, angles)), u
