@@ -105,6 +105,8 @@ struct mmrs_ctx {
     bool tc_shape_ok = false;   // every live unit has kTcMinPts <= n, m <= kTcMaxPts (decided at upload)
     bool use_tc = false;        // decided per grid set (apply_grids)
     bool tc_ran = false;
+    bool use_xf = false, xf_ran = false;   // expanded-form tier K1x (k_sweep<.., XF>)
+    double xf_abs = 8e-6;       // its tier-1 window: d^2 <= dmin^2 + xf_abs * Rmax^2 (>= 4.8x the proven error bound)
     double tc_abs = 4e-6;       // tier-1 window: d^2 <= dmin^2 + tc_abs * Rmax^2
     unsigned l1_cap = 0;
     size_t smem_tc = 0;

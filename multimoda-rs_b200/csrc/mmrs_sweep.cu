@@ -206,6 +206,8 @@ static int ensure(mmrs_ctx* ctx, DevBuf& b, size_t bytes) {
         if (_r != MMRS_OK) return _r;                      \
     } while (0)
 
+constexpr bool kXfDefault = false;   // what mmrs_sweep_opts.prefilter = 0 (auto) resolves to for large batches
+
 // ---- kernel dispatch over TA ----------------------------------------------------------
 struct ListArgs {  // LIST arguments of k_sweep; all null for the dense sweep
     const int2* items = nullptr;
@@ -231,42 +233,49 @@ static cudaError_t raise_smem_once(K kernel, std::once_flag& once, cudaError_t& 
         return raise_smem_once(kernel, once, result);            \
     }())
 
-template <int TA, bool MULTI, bool LIST, bool TAILP>
+template <int TA, bool MULTI, bool LIST, bool TAILP, bool XF>
 static void launch_sweep_k(int grid, size_t smem, cudaStream_t s, const UnitDesc* units, const WorkItem* work,
                            const float4* lay, const float2* cs32, float* dist32, unsigned long long* key,
                            const ListArgs& l) {
-    RAISE_SMEM((k_sweep<TA, MULTI, LIST, TAILP>));
-    k_sweep<TA, MULTI, LIST, TAILP><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key, l.items, l.n_items,
-                                                                 l.cap, l.chunk, l.rmax, l.diag);
+    RAISE_SMEM((k_sweep<TA, MULTI, LIST, TAILP, XF>));
+    k_sweep<TA, MULTI, LIST, TAILP, XF><<<grid, kThreads, smem, s>>>(units, work, lay, cs32, dist32, key, l.items,
+                                                                     l.n_items, l.cap, l.chunk, l.rmax, l.diag);
 }
+// xf: the expanded-form tier K1x (dense launches only; a list is always re-scored in direct form)
 template <int TA>
-static void launch_sweep_ta(bool multi, bool tailp, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
+static void launch_sweep_ta(bool multi, bool tailp, bool xf, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
                             const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
                             unsigned long long* key, const ListArgs* l) {
     const ListArgs none{};
     const ListArgs& la = l ? *l : none;
+#define GO(M, L, T, X) launch_sweep_k<TA, M, L, T, X>(grid, smem, s, units, work, lay, cs32, dist32, key, la)
     if constexpr (TA % 2 == 0 && TA >= 4) {   // exact tiling is instantiated for even register tiles
         if (tailp) {
-            if (l) launch_sweep_k<TA, false, true, true>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
-            else launch_sweep_k<TA, false, false, true>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
+            if (l) GO(false, true, true, false);
+            else if (xf) GO(false, false, true, true);
+            else GO(false, false, true, false);
             return;
         }
     }
     if (l) {
-        if (multi) launch_sweep_k<TA, true, true, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
-        else launch_sweep_k<TA, false, true, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
+        if (multi) GO(true, true, false, false);
+        else GO(false, true, false, false);
+    } else if (xf) {
+        if (multi) GO(true, false, false, true);
+        else GO(false, false, false, true);
     } else {
-        if (multi) launch_sweep_k<TA, true, false, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
-        else launch_sweep_k<TA, false, false, false>(grid, smem, s, units, work, lay, cs32, dist32, key, la);
+        if (multi) GO(true, false, false, false);
+        else GO(false, false, false, false);
     }
+#undef GO
 }
 static bool launch_sweep(int TA, bool multi, bool tailp, int grid, size_t smem, cudaStream_t s, const UnitDesc* units,
                          const WorkItem* work, const float4* lay, const float2* cs32, float* dist32,
-                         unsigned long long* key, const ListArgs* l = nullptr) {
+                         unsigned long long* key, const ListArgs* l = nullptr, bool xf = false) {
     switch (TA) {
-#define CASE(T)                                                                               \
-    case T:                                                                                   \
-        launch_sweep_ta<T>(multi, tailp, grid, smem, s, units, work, lay, cs32, dist32, key, l); \
+#define CASE(T)                                                                                   \
+    case T:                                                                                       \
+        launch_sweep_ta<T>(multi, tailp, xf, grid, smem, s, units, work, lay, cs32, dist32, key, l); \
         return true;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
             CASE(15) CASE(16) CASE(17) CASE(18)
@@ -380,11 +389,12 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
             d.m_pairs = (d.m + 1) / 2;
             const long long a_elems = (long long)d.n_chunks * ((cc.ta + 1) / 2) * 32,
                             b_elems = cc.tailp ? 16 * (cc.ta + 1) : d.m_pairs,   // exact tiling pads the B block (k_prep)
+                            nb_elems = (b_elems + 1) / 2,                        // squared norms of the reference points
                             t_elems = (d.n_tail + 1) / 2;
-            lay_off += a_elems + b_elems + t_elems;
+            lay_off += a_elems + b_elems + nb_elems + t_elems;
             // shared memory of a CTA of this unit: mbarrier + key, the staging image, then per warp either the chunked
             // column minima (MULTI) or the tail pass's column seeds (exact tiling)
-            size_t smem = 16 + (size_t)(a_elems + b_elems + t_elems) * 16;
+            size_t smem = 16 + (size_t)(a_elems + b_elems + nb_elems + t_elems) * 16;
             if (d.n_chunks > 1) smem += (size_t)kWarpsPerCta * 2 * d.m_pairs * 4;
             if (cc.tailp) smem += (size_t)kWarpsPerCta * 32 * (cc.ta + 1) * 4;
             if (smem > (size_t)kMaxDynSmem)
@@ -637,6 +647,25 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
             ENSURE(ctx->d_l1_n, 16);
         }
     }
+    // Expanded-form tier K1x (k_sweep<.., XF>): the same work list and size classes as the dense sweep, 6 instead of 8
+    // packed FP32 instructions per 2 x 2 block; candidates inside its error window are re-scored in direct form.
+    {
+        const char* env = std::getenv("MMRS_XF");   // experiments: 1 = on for every batch that qualifies, 0 = off
+        int mode = ctx->opt_prefilter;
+        if (env && *env && mode == 0) mode = (*env == '0') ? 1 : 3;
+        if (mode == 0) mode = kXfDefault ? 3 : 1;
+        // worth it when the sweep is long enough to pay for two extra launches (window + re-scoring)
+        ctx->use_xf = mode == 3 && !ctx->use_tc && ctx->part_active != 2 && live >= (ctx->opt_prefilter == 3 ? 1 : (1 << 20));
+        if (ctx->use_xf) {
+            ctx->l1_cap = (unsigned)std::min<long long>(std::max<long long>({(long long)U * 64, 65536LL, live / 32}),
+                                                        std::max<long long>(live, 1));
+            ENSURE(ctx->d_key_tc, U * 8);
+            ENSURE(ctx->d_l1_items, (size_t)ctx->l1_cap * 8);
+            ENSURE(ctx->d_l1_count, U * 4);
+            ENSURE(ctx->d_l1_base, U * 4);
+            ENSURE(ctx->d_l1_n, 16);
+        }
+    }
     // Lower-bound pruning: worth it when a unit carries enough candidates for the two extra passes to pay off.
     {
         long long live_units = 0;
@@ -645,7 +674,7 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
         const char* env = std::getenv("MMRS_PRUNE");
         int mode = ctx->opt_prune;
         if (env && *env) mode = (*env == '0') ? 0 : 1;
-        ctx->use_prune = mode == 1 && !ctx->use_tc && ctx->lb_shape_ok && live_units > 0 && live >= 256 * live_units &&
+        ctx->use_prune = mode == 1 && !ctx->use_tc && !ctx->use_xf && ctx->lb_shape_ok && live_units > 0 && live >= 256 * live_units &&
                          ctx->part_active != 2;
         ctx->h_work_lb.clear();
         if (ctx->use_prune) {
@@ -734,8 +763,10 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
     if (o && o->keep_dist32 && ctx->opt_prefilter == 0) ctx->opt_prefilter = 1;  // exact FP32 for EVERY candidate
     if (o && o->keep_dist32) ctx->opt_prune = 0;
     ctx->tc_abs = (o && o->prefilter_abs > 0) ? o->prefilter_abs : 4e-6;
-    if (ctx->opt_prefilter < 0 || ctx->opt_prefilter > 2)
-        return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: prefilter must be 0 (auto), 1 (off) or 2 (required)");
+    ctx->xf_abs = (o && o->prefilter_abs > 0) ? o->prefilter_abs : 8e-6;
+    if (ctx->opt_prefilter < 0 || ctx->opt_prefilter > 3)
+        return set_err(ctx, MMRS_ERR_ARG,
+                       "mmrs_sweep_upload: prefilter must be 0 (auto), 1 (off), 2 (tensor-core tier) or 3 (expanded-form tier)");
     if (b->n_units == 0) {
         ctx->grids.clear();
         ctx->grid_of_unit.clear();
@@ -825,8 +856,10 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_nitems.p, 0, 16, s));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
     const bool tc = ctx->use_tc && !ctx->h_work_tc.empty();
-    const bool prune = !tc && ctx->use_prune && !ctx->h_work_lb.empty();
-    ctx->tc_ran = tc;
+    const bool xf = !tc && ctx->use_xf && !ctx->h_work.empty();
+    const bool prune = !tc && !xf && ctx->use_prune && !ctx->h_work_lb.empty();
+    ctx->xf_ran = xf;
+    ctx->tc_ran = tc || xf;
     ctx->prune_ran = prune;
     if (prune) {
         // tier 0: lower bounds of every candidate (rows-only passes over R strided points of each set)
@@ -948,6 +981,47 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[2], s));
         ctx->launches += 2;
+    } else if (xf) {
+        // tier 0: every candidate in the expanded form (K1x) -> FP32 distances with a bounded ABSOLUTE error on d^2
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_key_tc.p, 0xff, U * 8, s));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_l1_n.p, 0, 16, s));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[0], s));
+        for (const auto& cl : ctx->classes) {
+            if (!cl.work_count) continue;
+            if (!launch_sweep(cl.ta, cl.multi, cl.tailp, (int)cl.work_count, cl.smem, s, units,
+                              (const WorkItem*)ctx->d_work.p + cl.work_begin, (const float4*)ctx->d_lay.p,
+                              (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key_tc.p,
+                              nullptr, true))
+                return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for this register tile");
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[1], s));
+        // tier 1: the candidates inside the tier's error window of the unit's minimum ...
+        k_shortlist<<<(unsigned)U, 256, 0, s>>>(units, (const float*)ctx->d_dist32.p,
+                                                (const unsigned long long*)ctx->d_key_tc.p,
+                                                (const unsigned*)ctx->d_rmax.p, 4e-6f, (float)ctx->xf_abs, ctx->l1_cap,
+                                                (int*)ctx->d_l1_count.p, (unsigned*)ctx->d_l1_base.p,
+                                                (int2*)ctx->d_l1_items.p, (unsigned*)ctx->d_l1_n.p, 2, nullptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        // ... are re-scored in direct form (tier 2): from here on the run works on exact FP32 values
+        ListArgs la;
+        la.items = (const int2*)ctx->d_l1_items.p;
+        la.n_items = (const unsigned*)ctx->d_l1_n.p;
+        la.cap = ctx->l1_cap;
+        la.chunk = 16;
+        la.rmax = (const unsigned*)ctx->d_rmax.p;
+        la.diag = (unsigned*)ctx->d_l1_n.p + 1;
+        for (const auto& cl : ctx->classes) {
+            if (!launch_sweep(cl.ta, cl.multi, cl.tailp, (int)(((long long)ctx->l1_cap + la.chunk - 1) / la.chunk), cl.smem, s,
+                              units, nullptr, (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p,
+                              (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p, &la))
+                return set_err(ctx, MMRS_ERR_ARG, "no sweep kernel for this register tile");
+            ctx->launches += 1;
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tc[2], s));
+        ctx->launches += 1;
     } else if (!ctx->h_work.empty()) {
         for (const auto& cl : ctx->classes) {   // one launch per size class (register tile / chunked / exact tiling)
             if (!cl.work_count) continue;
@@ -971,7 +1045,7 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
                                             (const unsigned long long*)ctx->d_key.p, (const unsigned*)ctx->d_rmax.p,
                                             (float)ctx->opt_rel, (float)ctx->opt_abs, ctx->pool_cap,
                                             (int*)ctx->d_sl_count.p, (unsigned*)ctx->d_sl_base.p, (int2*)ctx->d_items.p,
-                                            (unsigned*)ctx->d_nitems.p, 0, tc ? (const int*)ctx->d_l1_count.p : nullptr);
+                                            (unsigned*)ctx->d_nitems.p, 0, (tc || xf) ? (const int*)ctx->d_l1_count.p : nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     {
@@ -1055,7 +1129,7 @@ extern "C" int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out) {
         }
         std::fprintf(stderr, "[mmrs]   run: %lld units, %lld candidates, sweep %.2f ms (%s tier0 %.2f + tier1 %.2f; %lld scored exactly, "
                      "largest unit list %d), shortlist %.2f, recheck %.2f\n",
-                     (long long)U, ctx->total_cands, t[0], ctx->prune_ran ? "pruned:" : ctx->tc_ran ? "tc:" : "dense;", a, b, scored,
+                     (long long)U, ctx->total_cands, t[0], ctx->prune_ran ? "pruned:" : ctx->xf_ran ? "expanded:" : ctx->tc_ran ? "tc:" : "dense;", a, b, scored,
                      worst, t[1], t[2]);
     }
     if (ctx->part_active == 1 && !ctx->comm && ctx->exchange) {
@@ -1279,7 +1353,8 @@ extern "C" int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]) {
     CUDA_TRY(ctx, cudaMemcpy(h, ctx->d_l1_n.p, 8, cudaMemcpyDeviceToHost));
     float err;
     std::memcpy(&err, &h[1], 4);
-    out[0] = ctx->prune_ran ? 2.0 : 1.0;
+    out[0] = ctx->prune_ran ? 2.0 : ctx->xf_ran ? 3.0 : 1.0;
+    if (ctx->xf_ran) out[5] = ctx->xf_abs;
     out[1] = a;
     out[2] = b;
     out[3] = (double)h[0];

@@ -47,6 +47,11 @@ __device__ __forceinline__ uint64_t pk(float lo, float hi) {
 __device__ __forceinline__ void upk(uint64_t v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
     uint64_t r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -108,7 +113,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 //   read instead of a 64-bit pair: the sweep is register-file-bandwidth bound).
 // Indices past the end repeat the last point (a duplicate never changes a
 // min-over-points or a max-over-points).
-// Tail block (exact tiling, UnitDesc.n_tail > 0; after the B block): the n mod 32 test points that do not fill a
+// NB block (after the B block): float2 j = (|b_2j|^2, |b_2j+1|^2), the squared norms the expanded-form tier adds.
+// Tail block (exact tiling, UnitDesc.n_tail > 0; after the NB block): the n mod 32 test points that do not fill a
 // register slot, two per float4 (x0, y0, x1, y1). K1 scores them in a short pass of its own instead of a padded slot.
 // =============================================================================
 __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restrict__ test_xy,
@@ -123,9 +129,11 @@ __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restr
     // exact tiling: the B block is padded to 16 (TA + 1) float4 so that the tail pass can address its reference points
     // lane + 32 q without clamping (indices past the end repeat the last point)
     const int b_elems = ud.n_tail > 0 ? 16 * (TA + 1) : ud.m_pairs;
+    const int nb_elems = (b_elems + 1) / 2;   // NB block: |b|^2 of the FP32 reference points, float2 per pair of points
     float4* A = lay + ud.lay_off;
     float4* B = A + a_elems;
-    float4* T = B + b_elems;
+    float2* NB = reinterpret_cast<float2*>(B + b_elems);
+    float4* T = B + b_elems + nb_elems;
     float rmax = 0.f;
     for (int e = threadIdx.x; e < a_elems; e += blockDim.x) {
         int l = e & 31, ck = e >> 5;
@@ -150,8 +158,11 @@ __global__ void k_prep(const UnitDesc* __restrict__ units, const double* __restr
         const float4 v = make_float4((float)(p0[0] - ud.cx), (float)(p0[1] - ud.cy), (float)(p1[0] - ud.cx),
                                      (float)(p1[1] - ud.cy));
         B[j] = v;
+        // squared norms of the ROUNDED coordinates, formed in f64 and rounded once (expanded-form tier, K1x)
+        NB[j] = make_float2((float)((double)v.x * v.x + (double)v.y * v.y), (float)((double)v.z * v.z + (double)v.w * v.w));
         rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
+    if (threadIdx.x == 0 && (b_elems & 1)) NB[b_elems] = make_float2(0.f, 0.f);   // padding of the odd float4
     // tail block: float4 t = tail points 2t and 2t+1 as (x0, y0, x1, y1) (an odd count repeats the last point)
     for (int t = threadIdx.x; t < (ud.n_tail + 1) / 2; t += blockDim.x) {
         const int i0 = n_main + min(2 * t, ud.n_tail - 1), i1 = n_main + min(2 * t + 1, ud.n_tail - 1);
@@ -189,7 +200,19 @@ __global__ void k_cs32(const double2* __restrict__ cs64, float2* __restrict__ cs
 //               the tail's row minima are finished with one REDUX each and its column minima — lane-local, no REDUX —
 //               go to a per-warp shared-memory array from which the main loop seeds its column accumulators (one
 //               broadcast LDS.64 per two reference points; the seed takes the free slot of the first 3-input minimum).
-template <int TA, bool MULTI, bool LIST, bool TAILP>
+// XF = true    : K1x, the EXPANDED-FORM tier (dense launches only). |a - b|^2 = |b|^2 - 2 a.b + |a|^2: per packed pair of
+//               test points and reference point two FFMA2 give r = |b|^2 - 2 a.b (what the row minima need: |a|^2 is
+//               constant along a row and is added after the minimum) and one FADD2 gives r + |a|^2 (what the column
+//               minima need) — 6 packed FP32 instructions per 2 x 2 block instead of 8 (-7 % per block measured,
+//               profiles/r02_microbench_expanded_forms.txt). The price is cancellation: with Rn the largest point norm
+//               the result carries an ABSOLUTE error of at most 13 u Rn^2 (u = 2^-24; one rounding each for |b|^2
+//               (u), the two FMAs (3 u + 3 u: the partial sums stay below 3 Rn^2), the final add (4 u) and two for
+//               |a|^2) <= 1.6e-6 Rmax^2, instead of the direct form's relative 3e-7. So K1x is a FILTER tier exactly like
+//               K1 is a filter for the f64 recheck: every candidate is scored, the candidates within the error window
+//               of the minimum are re-scored by the direct-form kernel (LIST), and K2/K3/K4 run unchanged on exact
+//               FP32 values — the selection is bit-identical to the dense direct path. The tail pass and the odd
+//               scalar slot stay in direct form (their values are exact, the seeds and minima mix freely).
+template <int TA, bool MULTI, bool LIST, bool TAILP, bool XF>
 __global__ void __launch_bounds__(kThreads, 2)
     k_sweep(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, const float4* __restrict__ lay,
             const float2* __restrict__ cs32, float* __restrict__ dist32, unsigned long long* __restrict__ key,
@@ -197,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             const unsigned* __restrict__ rmax_bits, unsigned* __restrict__ diag) {
     static_assert(TA >= 2 && TA <= 18, "register tile out of range");
     static_assert(!(TAILP && MULTI), "the tail pass is for single-chunk units");
+    static_assert(!(XF && LIST), "the expanded form is a dense tier; lists are re-scored in direct form");
     constexpr int SB = TA + 1;         // TAILP: reference points per lane of the tail pass (M <= 32 SB)
     constexpr int H = TA / 2;          // packed pairs of test points per lane
     constexpr bool TAIL = (TA & 1);    // plus one unpaired point when TA is odd
@@ -247,14 +271,16 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int a_elems = ud.n_chunks * S * 32;
     const int b_elems = TAILP ? 16 * SB : ud.m_pairs;   // float4 per PAIR of reference points (exact tiling: padded)
     const int b_pts = 2 * ud.m_pairs;
+    const int nb_elems = (b_elems + 1) / 2;                // float2 per PAIR of reference points: their squared norms
     const int t_elems = TAILP ? (ud.n_tail + 1) / 2 : 0;   // float4 per PAIR of tail points
     float4* sB = sA + a_elems;
-    const float4* sT = sB + b_elems;
-    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems + t_elems);  // MULTI: [warp][b_pts]; TAILP: [warp][32 SB]
+    const float2* sNB = reinterpret_cast<const float2*>(sB + b_elems);
+    const float4* sT = sB + b_elems + nb_elems;
+    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems + nb_elems + t_elems);  // MULTI: [warp][b_pts]; TAILP: [warp][32 SB]
 
     if (threadIdx.x == 0) {
         *s_key = ~0ull;
-        const uint32_t bytes = (uint32_t)(a_elems + b_elems + t_elems) * 16u;
+        const uint32_t bytes = (uint32_t)(a_elems + b_elems + nb_elems + t_elems) * 16u;
         mbar_expect_tx(bar, bytes);
         tma_bulk_g2s(sA, lay + ud.lay_off, bytes, bar);
     }
@@ -334,7 +360,8 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
 
         for (int ch = 0; ch < ud.n_chunks; ++ch) {
-            uint64_t AX[H], AY[H];
+            uint64_t AX[H], AY[H];           // XF: (-2 x', -2 y')
+            uint64_t NA[XF ? H : 1];         // XF: |a'|^2 of the rotated FP32 points
             float row[TA];
             float tx = 0.f, ty = 0.f;
             if (TAIL) {
@@ -349,6 +376,12 @@ __global__ void __launch_bounds__(kThreads, 2)
                 const uint64_t X2 = pk(a.x, a.y), Y2 = pk(a.z, a.w);
                 AX[k] = fma2(Y2, NS2, mul2(X2, C2));  // x' = x cos - y sin
                 AY[k] = fma2(X2, S2, mul2(Y2, C2));   // y' = x sin + y cos
+                if (XF) {
+                    NA[k] = fma2(AX[k], AX[k], mul2(AY[k], AY[k]));
+                    const uint64_t M2 = pk(-2.f, -2.f);
+                    AX[k] = mul2(AX[k], M2);          // exact scaling
+                    AY[k] = mul2(AY[k], M2);
+                }
                 row[2 * k] = INF;
                 row[2 * k + 1] = INF;
             }
@@ -377,19 +410,41 @@ __global__ void __launch_bounds__(kThreads, 2)
                     c0 = (MULTI || TAILP) ? fminf(c0, t0) : t0;  // plain single-chunk: these distances seed the column minima
                     c1 = (MULTI || TAILP) ? fminf(c1, t1) : t1;
                 }
+                if (XF) {
+                    const float2 nb = sNB[j];
+                    const uint64_t n0 = pk(nb.x, nb.x), n1 = pk(nb.y, nb.y);
 #pragma unroll
-                for (int k = 0; k < H; ++k) {
-                    const uint64_t dx0 = sub2(AX[k], bx0), dy0 = sub2(AY[k], by0);
-                    const uint64_t dx1 = sub2(AX[k], bx1), dy1 = sub2(AY[k], by1);
-                    const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));  // (|a0-b0|^2, |a1-b0|^2)
-                    const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));  // (|a0-b1|^2, |a1-b1|^2)
-                    float d00, d10, d01, d11;
-                    upk(d0, d00, d10);
-                    upk(d1, d01, d11);
-                    row[2 * k] = min3(row[2 * k], d00, d01);
-                    row[2 * k + 1] = min3(row[2 * k + 1], d10, d11);
-                    c0 = min3(c0, d00, d10);
-                    c1 = min3(c1, d01, d11);
+                    for (int k = 0; k < H; ++k) {
+                        const uint64_t r0 = fma2(AX[k], bx0, fma2(AY[k], by0, n0));  // |b0|^2 - 2 a.b0 for (a0, a1)
+                        const uint64_t r1 = fma2(AX[k], bx1, fma2(AY[k], by1, n1));
+                        const uint64_t d0 = add2(r0, NA[k]), d1 = add2(r1, NA[k]);   // + |a|^2: the squared distances
+                        float r00, r10, r01, r11, d00, d10, d01, d11;
+                        upk(r0, r00, r10);
+                        upk(r1, r01, r11);
+                        upk(d0, d00, d10);
+                        upk(d1, d01, d11);
+                        row[2 * k] = min3(row[2 * k], r00, r01);
+                        row[2 * k + 1] = min3(row[2 * k + 1], r10, r11);
+                        c0 = min3(c0, d00, d10);
+                        c1 = min3(c1, d01, d11);
+                    }
+                    c0 = fmaxf(c0, 0.f);   // cancellation can leave a tiny negative value: the bit-pattern order needs >= 0
+                    c1 = fmaxf(c1, 0.f);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < H; ++k) {
+                        const uint64_t dx0 = sub2(AX[k], bx0), dy0 = sub2(AY[k], by0);
+                        const uint64_t dx1 = sub2(AX[k], bx1), dy1 = sub2(AY[k], by1);
+                        const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));  // (|a0-b0|^2, |a1-b0|^2)
+                        const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));  // (|a0-b1|^2, |a1-b1|^2)
+                        float d00, d10, d01, d11;
+                        upk(d0, d00, d10);
+                        upk(d1, d01, d11);
+                        row[2 * k] = min3(row[2 * k], d00, d01);
+                        row[2 * k + 1] = min3(row[2 * k + 1], d10, d11);
+                        c0 = min3(c0, d00, d10);
+                        c1 = min3(c1, d01, d11);
+                    }
                 }
                 unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
                 unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
@@ -406,7 +461,16 @@ __global__ void __launch_bounds__(kThreads, 2)
                 }
             }
             if (LIST && gave_up) break;  // the row minima are incomplete: only the column bound counts
-            float rm = row[0];
+            if (XF) {   // row minima of r -> squared distances: + |a|^2 (the odd scalar slot is already a distance)
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    float n0, n1;
+                    upk(NA[k], n0, n1);
+                    row[2 * k] += n0;
+                    row[2 * k + 1] += n1;
+                }
+            }
+            float rm = XF ? fmaxf(row[0], 0.f) : row[0];
 #pragma unroll
             for (int k = 1; k < TA; ++k) rm = fmaxf(rm, row[k]);
             rowmax = max(rowmax, __float_as_uint(rm));
@@ -664,8 +728,12 @@ __global__ void k_shortlist(const UnitDesc* __restrict__ units, const float* __r
     __syncthreads();
     const float dmin = __uint_as_float((unsigned)(key[u] >> 32));
     const float rmax = __uint_as_float(rmax_bits[u]);
-    const float thr = mode == 1 ? sqrtf(fmaf(dmin, dmin, abs_scale * rmax * rmax)) * (1.0f + rel)
-                                : dmin * (1.0f + rel) + abs_scale * rmax;
+    // mode 2 (expanded-form tier): the window of the tier's own absolute error on d^2 (abs_scale Rmax^2), widened by the
+    // whole FP32 window of the stage behind it (4e-6 relative + 4e-6 Rmax: twice what k_shortlist mode 0 uses), so that
+    // every candidate the exact FP32 values would shortlist is among the re-scored ones whatever the distance is.
+    const float thr = mode == 2   ? sqrtf(fmaf(dmin, dmin, abs_scale * rmax * rmax)) * (1.0f + rel) + 4e-6f * rmax
+                      : mode == 1 ? sqrtf(fmaf(dmin, dmin, abs_scale * rmax * rmax)) * (1.0f + rel)
+                                  : dmin * (1.0f + rel) + abs_scale * rmax;
     const float* d = dist32 + ud.dist_off;
     int mine = 0;
     for (int c = ud.c_lo + threadIdx.x; c < ud.c_hi; c += blockDim.x) mine += (d[c] <= thr) ? 1 : 0;

@@ -264,7 +264,7 @@ class Context:
         o = (C.c_double * 6)()
         lib().mmrs_sweep_prefilter_info.argtypes = [C.c_void_p, c_dp]
         self._check(lib().mmrs_sweep_prefilter_info(self._p, o))
-        return dict(ran=bool(o[0]), kind={0: None, 1: "tensor-core prefilter", 2: "lower-bound pruning"}[int(o[0])],
+        return dict(ran=bool(o[0]), kind={0: None, 1: "tensor-core prefilter", 2: "lower-bound pruning", 3: "expanded-form tier"}[int(o[0])],
                     tc_ms=o[1], rescore_ms=o[2], rescored=int(o[3]), max_err=o[4], window=o[5])
 
     def eval_exact(self, test_xy, ref_xy, centre, mode, angles):

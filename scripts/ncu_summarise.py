@@ -21,7 +21,7 @@ all_ms = sum(v[1] for v in tot.values())
 out = ROOT / "profiles" / f"{tag}_launches_bench_py.csv"
 out.write_text("\n".join(lines) + "\n")
 summary = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv python bench.py --steps 2 --warmup 3 "
-                      "--no-cpu-baseline --no-api --no-tc", "total_device_ms": all_ms,
+                      "--no-cpu-baseline --no-api --no-tc  (the 3 184-unit strong-scaling batch)", "total_device_ms": all_ms,
            "kernels": {k: {"launches": v[0], "ms": v[1], "share": v[1] / all_ms} for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])}}
 (ROOT / "profiles" / f"{tag}_launches_bench_py_summary.json").write_text(json.dumps(summary, indent=1))
 print(json.dumps(summary, indent=1)[:1200])
@@ -47,16 +47,19 @@ if rep.exists():
         if k in head:
             i = head.index(k)
             d[k] = f"{vals[i]} {units[i]}".strip()
-    (ROOT / "profiles" / f"{tag}_ksweep_ta17_u398_ncu_full_summary.json").write_text(json.dumps(d, indent=1))
+    (ROOT / "profiles" / f"{tag}_ksweep_u398_ncu_full_summary.json").write_text(json.dumps(d, indent=1))
     def num(k):
         i = head.index(k)
         v = float(vals[i].replace(",", ""))
         u = units[i].lower()
         return v * (1e6 if u.startswith("mbyte") else 1e3 if u.startswith("kbyte") else 1e9 if u.startswith("gbyte") else 1.0)
     rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
-    tr = {"kernel": "k_sweep<17,false,false>", "workload": "config 2: 398 units x 36000 candidates, N=M=520",
+    kname = d.get("Kernel Name", "k_sweep").split("(")[0].replace("void ", "")
+    tr = {"kernel": kname, "workload": "config 2 (one pullback pair): 398 units x 36000 candidates, N=M=520",
           "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch_config2": rd + wr,
-          "source": f"ncu --set full, profiles/{tag}_ksweep_ta17_u398_ncu_full_summary.json",
-          "algorithmic_bytes_per_launch": 60699776}
+          "dram_bytes_per_unit": (rd + wr) / 398.0,
+          "source": f"ncu --set full --clock-control none, profiles/{tag}_ksweep_u398_ncu_full_summary.json",
+          "algorithmic_bytes_per_launch": 398 * (2 * 520 * 16 + 36000 * 4),
+          "algorithmic_bytes_note": "per unit: both point sets once (f64 x, y) + one FP32 distance per candidate"}
     (ROOT / "profiles" / "sweep_traffic.json").write_text(json.dumps(tr, indent=1))
     print(json.dumps(d, indent=1))

@@ -17,7 +17,10 @@ torch.cuda.set_device(local)
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = mm.get_context(local)
-_dist.enable_unit_sharding(ctx)
+if os.environ.get("MMRS_SHARD_TRANSPORT", "nccl") == "callback":
+    _dist.enable_unit_sharding(ctx)      # host callback transport (torch.distributed all-reduce), axis 1
+else:
+    _dist.init_comm(ctx)                 # the library's own NCCL communicator: collectives on device buffers
 
 # 1. config 1 (golden): full mode on the example pullbacks, default + brute force
 pack, gold = gio.inputs(), gio.oracle_outputs()

@@ -209,3 +209,61 @@ def test_wall_alignment_flag_only_touches_walls():
     assert aortic_dir(plain.frames[2]) @ aortic_dir(plain.frames[1]) < 0.9
     for k in (1, 2, 3):  # after the fix every wall's aortic direction is the parallel transport of frame 0's
         assert aortic_dir(fixed.frames[k]) @ aortic_dir(fixed.frames[0]) > 1 - 1e-9
+
+
+# ---- against the oracle restatement (oracle/centerline_py.py, pinned on the reference's Rust tests) --------------------
+def _oracle_frames(g):
+    from oracle import oracle_py as ora
+
+    return ora.decode_geometry(g.to_blob())
+
+
+def _assert_same_geometry(got_frames, want_frames, atol=1e-9):
+    assert len(got_frames) == len(want_frames)
+    for a, b in zip(got_frames, want_frames):
+        assert a["id"] == b["id"] and np.allclose(a["centroid"], b["centroid"], atol=atol, rtol=0)
+        assert (a["reference_point"] is None) == (b["reference_point"] is None)
+        if a["reference_point"] is not None:
+            assert np.allclose(a["reference_point"], b["reference_point"], atol=atol, rtol=0)
+        assert sorted(a["contours"]) == sorted(b["contours"])
+        for k in a["contours"]:
+            ca, cb = a["contours"][k], b["contours"][k]
+            assert np.array_equal(ca["points"][:, :2], cb["points"][:, :2])          # frame / point indices: exact
+            assert np.allclose(ca["points"][:, 2:5], cb["points"][:, 2:5], atol=atol, rtol=0)
+            assert (ca["centroid"] is None) == (cb["centroid"] is None)
+            if ca["centroid"] is not None:
+                assert np.allclose(ca["centroid"], cb["centroid"], atol=atol, rtol=0)
+
+
+@pytest.mark.parametrize("pair", [False, True])
+def test_manual_and_three_point_match_the_oracle(pair):
+    """The product's host-f64 methods against the independent pure-Python restatement: spacing and the selected
+    three-point angle EXACTLY, every coordinate within 1e-9 (nalgebra's association order cannot be confirmed from the
+    reference checkout, oracle/centerline_py.py header)."""
+    from oracle import centerline_py as oc
+
+    g = pullback(n_frames=6, n=48, dz=1.25, extras=True, ref_index=7, ry=1.6)
+    g2 = pullback(n_frames=6, n=48, dz=1.25, extras=True, ref_index=7, ry=1.3, label="h")
+    target = PyGeometryPair(g, g2, "pair") if pair else g
+    cl = centerline((10.0, -3.0, 40.0), (0.3, -0.2, -1.0), 60, 0.4)
+    ocl = oc.centerline_from_rows(cl._rows())
+    ogeoms = [_oracle_frames(g), _oracle_frames(g2)] if pair else [_oracle_frames(g)]
+    ref = (10.0, -3.0, 40.0)
+    # align_manual
+    res, spacing, rot = align_manual(cl, target, 25.0, ref)
+    want, wspacing, wrot = oc.align_manual(ocl, ogeoms, 25.0, ref)
+    assert spacing == wspacing and math.radians(rot) == pytest.approx(wrot, abs=1e-15)
+    got = [res.geom_a, res.geom_b] if pair else [res]
+    for gg, ww in zip(got, want):
+        _assert_same_geometry(_oracle_frames(gg), ww)
+    # align_three_point: landmarks taken from a planted 40-degree placement
+    planted, _, _ = oc.align_manual(ocl, ogeoms[:1], 40.0, ref)
+    lum = planted[0][0]["contours"][0]["points"]
+    main, ccw, cw = tuple(lum[7][2:5]), tuple(lum[0][2:5]), tuple(lum[24][2:5])
+    res, spacing, rot = align_three_point(cl, target, main, ccw, cw, angle_step_deg=1.0)
+    want, wspacing, wrot = oc.align_three_point(ocl, ogeoms, main, ccw, cw, math.radians(1.0))
+    assert spacing == wspacing
+    assert abs(math.radians(rot) - wrot) < 1e-12      # the same candidate of the serial `while angle < TAU` loop
+    got = [res.geom_a, res.geom_b] if pair else [res]
+    for gg, ww in zip(got, want):
+        _assert_same_geometry(_oracle_frames(gg), ww)

@@ -1,9 +1,8 @@
 """align_combined = three-point start + refine_alignment_hausdorff (align_algorithms.rs:339-451): every
 (centerline index, angle) candidate is scored by the symmetric Hausdorff distance on the GPU as one batch of
 sweep units. Checked (1) by recovering a planted (rotation, centerline index) whose cost is exactly 0 and
-(2) against a numpy brute force over the same candidate loop, each candidate re-placed with align_manual
-(the same rotate_by_best_rotation + apply_transformations the reference's loop calls) and scored with the
-oracle-style f64 max-min in (x, y) (process_utils.rs:78-121 ignores z)."""
+(2) against the ORACLE's align_combined (oracle/centerline_py.py: the pure-Python restatement of align.rs:166-283 and
+align_algorithms.rs:339-451, pinned on the reference's Rust tests by tests/test_oracle_centerline.py)."""
 import math
 
 import numpy as np
@@ -66,7 +65,16 @@ def test_combined_recovers_planted_rotation_and_index():
     assert st["units"] > 0 and st["launches"] > 0   # the candidates went through the sweep kernels
 
 
-def test_combined_matches_numpy_brute_force():
+def test_combined_matches_the_oracle():
+    """mmrs_align_centerline method 2 (three-point start + refine_alignment_hausdorff with every candidate scored on the
+    GPU) against oracle/centerline_py.py::align_combined, the pure-Python restatement of align.rs:166-283 /
+    align_algorithms.rs:339-451 pinned on the reference's Rust tests: the same number of candidates scored, the same
+    refined (angle, centerline index) — i.e. the same total rotation to 1e-12 — the same minimal Hausdorff distance and
+    the same final geometry to 1e-9 (float tolerance: oracle/centerline_py.py header)."""
+    from oracle import centerline_py as oc
+    from oracle import oracle_py as ora
+    from tests.test_centerline_cpu import _assert_same_geometry
+
     n, direction = 40, (0.0, 0.0, -1.0)
     g = pullback(n_frames=4, n=n, dz=1.0, ref_frame=0, ref_index=3, ry=1.4)
     p0 = np.array([-1.0, 4.0, 30.0])
@@ -84,35 +92,13 @@ def test_combined_matches_numpy_brute_force():
     blobs, spacing, rot_rad, (best_h, n_cand) = nat.align_centerline(
         ctx, 2, cl._rows(), [g.to_blob()], main_ref_pt=main, ccw_ref_pt=ccw, cw_ref_pt=cw,
         angle_step_rad=math.radians(step), points=cloud, angle_range_rad=math.radians(rng_deg), index_range=idx_range)
-    # numpy restatement of the candidate loop (align_algorithms.rs:373-441) on the three-point start
-    start, _, rot0 = align_three_point(cl, g, main, ccw, cw)
-    assert abs(rot0 - theta0) < 1e-9
-    best = (float("inf"), None, None)
-    count = 0
-    for delta in range(-idx_range, idx_range + 1):
-        cur = 3 + delta
-        ref_pt = p0 + cur * spacing * d
-        seg_end = p0 + (cur + 4 - 1) * spacing * d
-        lo, hi = np.minimum(ref_pt, seg_end) - 5.0, np.maximum(ref_pt, seg_end) + 5.0
-        filt = cloud[((cloud >= lo) & (cloud <= hi)).all(1)]
-        angle = -math.radians(rng_deg)
-        while angle <= math.radians(rng_deg):
-            cand, _, _ = align_manual(cl, start, math.degrees(angle), tuple(ref_pt))
-            ratio = len(filt) / (n * 4)
-            nd = min(max(math.ceil(ratio * n), 1), n)
-            pts = []
-            for f in cand.frames:
-                rows = f.lumen.points_array()[:, 2:5]
-                pick = range(n) if nd >= n else [int(i * (n / nd)) for i in range(nd)]
-                pts.append(rows[list(pick)])
-            h = hausdorff_xy(filt, np.concatenate(pts))
-            count += 1
-            if h < best[0]:
-                best = (h, angle, cur)
-            angle += math.radians(step)
-    assert n_cand == count
-    assert abs(best_h - best[0]) < 1e-9, (best_h, best)
-    assert abs(rot_rad - (math.radians(theta0) + best[1])) < 1e-9
-    res = PyGeometry.from_blob(blobs[0], "g")
-    want, _, _ = align_manual(cl, g, math.degrees(rot_rad), tuple(p0 + best[2] * spacing * d))
-    assert np.allclose(lumen_cloud(res), lumen_cloud(want), atol=1e-9)
+    want, wspacing, wtotal, info = oc.align_combined(oc.centerline_from_rows(cl._rows()), [ora.decode_geometry(g.to_blob())],
+                                                     main, ccw, cw, cloud, math.radians(step), math.radians(rng_deg), idx_range)
+    assert spacing == wspacing
+    assert n_cand == info["scored"] and info["scored"] == (2 * idx_range + 1) * 11
+    assert abs(best_h - info["min_hausdorff"]) < 1e-9, (best_h, info)
+    assert abs(rot_rad - wtotal) < 1e-12, (rot_rad, wtotal, info)
+    # the planted -3.3 degrees come back to the grid; the centerline runs along z and the cost reads (x, y) only, so the
+    # index candidates tie and the FIRST one (strict `<`, align_algorithms.rs:433) wins — the final geometry's z tells which
+    assert abs(info["delta"] - math.radians(-3.0)) < 1e-12 and info["refined_idx"] == 1
+    _assert_same_geometry(ora.decode_geometry(blobs[0]), want[0])

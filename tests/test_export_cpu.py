@@ -1,5 +1,6 @@
-"""OBJ / MTL / PNG export (mmrs_export_pair, mmrs_export_single) against the reference's writers restated
-from their format strings: io/output.rs:10-181 (write_obj_mesh), to_object/process.rs:9-121,
+"""OBJ / MTL / PNG export (mmrs_export_pair, mmrs_export_single) against the ORACLE's restatement of the reference's
+writers (oracle/export_py.py: io/output.rs:10-181 write_obj_mesh, texture.rs UV coordinates, write_mtl.rs bodies) and,
+restated here from their format strings, to_object/process.rs:9-121,
 to_object/interpolation.rs:9-157, to_object/write_mtl.rs:15-273, to_object/texture.rs:6-95,
 binding/entry.rs:741-818. Host-only: no GPU needed."""
 import math
@@ -12,21 +13,8 @@ import pytest
 
 from multimodars import PyContour, PyContourPoint, PyFrame, PyGeometry
 from multimodars import _native as nat
-
-
-def rust_f64(v):
-    """Rust's `{}` for f64: shortest round-trip digits, never scientific."""
-    if v != v:
-        return "NaN"
-    if math.isinf(v):
-        return "-inf" if v < 0 else "inf"
-    r = repr(float(v))
-    if "e" in r or "E" in r:
-        from decimal import Decimal
-        r = format(Decimal(r), "f")
-    if r.endswith(".0"):
-        r = r[:-2]
-    return r
+from oracle.export_py import obj_text as expected_obj
+from oracle.export_py import mtl_text, rust_f64, uv_coords  # noqa: F401
 
 
 def ring(fid, cz, r, n, cx=0.0, cy=0.0, kind="Lumen", phase=0.0):
@@ -44,44 +32,6 @@ def geometry(label, n_frames=3, n=8, r0=2.0, dz=0.5, grow=0.0, with_catheter=Tru
         ref = PyContourPoint(f, 1, 1.0, 2.0, f * dz, False) if f == n_frames - 1 else None
         frames.append(PyFrame(f, lum.centroid, lum, extras, ref))
     return PyGeometry(frames, label)
-
-
-def expected_obj(contours, uv, mtl, watertight):
-    """io/output.rs:10-155 as text."""
-    out = []
-    offs, cur = [], 1
-    for c in contours:
-        offs.append(cur)
-        for p in c.points:
-            out.append(f"v {rust_f64(p.x)} {rust_f64(p.y)} {rust_f64(p.z)}")
-            cur += 1
-    out.append(f"mtllib {mtl}")
-    out.append("usemtl displacement_material")
-    for u, v in uv:
-        out.append(f"vt {rust_f64(u)} {rust_f64(v)}")
-    for c in contours:
-        for p in c.points:
-            dx, dy = p.x - c.centroid[0], p.y - c.centroid[1]
-            ln = math.sqrt(dx * dx + dy * dy)
-            nx, ny = (dx / ln, dy / ln) if ln > 0.0 else (0.0, 0.0)
-            out.append(f"vn {rust_f64(-nx)} {rust_f64(-ny)} {rust_f64(-0.0)}")
-    ppc = len(contours[0].points)
-    tri = lambda a, b, c: f"f {a}/{a}/{a} {b}/{b}/{b} {c}/{c}/{c}"
-    for k in range(len(contours) - 1):
-        o1, o2 = offs[k], offs[k + 1]
-        for j in range(ppc):
-            jn = (j + 1) % ppc
-            out.append(tri(o1 + j, o1 + jn, o2 + j))
-            out.append(tri(o2 + j, o1 + jn, o2 + jn))
-    if watertight:
-        a, z = contours[0].centroid, contours[-1].centroid
-        out += [f"v {rust_f64(a[0])} {rust_f64(a[1])} {rust_f64(a[2])}", "vt 0.5 0.5", "vn 0.0 0.0 -1.0"]
-        out += [f"v {rust_f64(z[0])} {rust_f64(z[1])} {rust_f64(z[2])}", "vt 0.5 0.5", "vn 0.0 0.0 1.0"]
-        for i in range(ppc):
-            out.append(tri(offs[0] + i, offs[0] + (i + 1) % ppc, cur))
-        for i in range(ppc):
-            out.append(tri(cur + 1, offs[-1] + (i + 1) % ppc, offs[-1] + i))
-    return "\n".join(out) + "\n"
 
 
 def read_png(path):
@@ -121,8 +71,8 @@ def test_single_export_matches_reference_format(tmp_path):
     got = open(tmp_path / "lumen_rest.obj").read()
     assert got == want
     assert "v 1 " in got and "v 0.0000001 " in got and " -0 " in got and "v 1000000000000000000000 " in got
-    assert open(mtl).read() == "newmtl material\nKa 1.0 1.0 1.0\nKd 1.0 1.0 1.0\nKs 0.0 0.0 0.0\n"
-    assert open(tmp_path / "catheter_rest.mtl").read() == "newmtl material\nKa 0.0 0.0 0.0\nKd 0.0 0.0 0.0\nKs 0.0 0.0 0.0\n"
+    assert open(mtl).read() == mtl_text("lumen") == "newmtl material\nKa 1.0 1.0 1.0\nKd 1.0 1.0 1.0\nKs 0.0 0.0 0.0\n"
+    assert open(tmp_path / "catheter_rest.mtl").read() == mtl_text("catheter")
     # naming 1 = to_object::write_single_geometry ("{case}_{type}")
     nat.export_single(g.to_blob(), "case", str(tmp_path / "w"), False, [0], 1)
     assert sorted(os.listdir(tmp_path / "w")) == ["case_lumen.mtl", "case_lumen.obj"]
@@ -152,13 +102,11 @@ def test_pair_export_files_textures_and_interpolation(tmp_path):
                                       p.z * (1.0 - t) + q.z * t, p.aortic) for p, q in zip(fa.lumen.points, fb.lumen.points)]
                 c = tuple(u * (1.0 - t) + v * t for u, v in zip(fa.lumen.centroid, fb.lumen.centroid))
                 lum.append(PyContour(fa.lumen.id, fa.lumen.original_frame, pts, c, None, None, "Lumen"))
-        uv = [((pi + 0.5) / 8, (ci + 0.5) / 3) for ci in range(3) for pi in range(8)]  # texture.rs:6-28
+        uv = uv_coords(3, 8)
         got = open(tmp_path / f"lumen_{i:03d}_dia - sys.obj").read()
         assert got == expected_obj(lum, uv, f"lumen_{i:03d}_dia - sys.mtl", True)
-        assert open(tmp_path / f"lumen_{i:03d}_dia - sys.mtl").read() == (
-            f"newmtl displacement_material\nKa 1 1 1\nKd 1 1 1\nmap_Kd lumen_{i:03d}_dia - sys.png\n")
-        assert open(tmp_path / f"catheter_{i:03d}_dia - sys.mtl").read() == (
-            f"newmtl black_material\nKa 0 0 0\nKd 0 0 0\nmap_Kd catheter_{i:03d}_dia - sys.png\n")
+        assert open(tmp_path / f"lumen_{i:03d}_dia - sys.mtl").read() == mtl_text("lumen", f"lumen_{i:03d}_dia - sys.png")
+        assert open(tmp_path / f"catheter_{i:03d}_dia - sys.mtl").read() == mtl_text("catheter", f"catheter_{i:03d}_dia - sys.png")
         # displacement texture: texture.rs:51-74, normalised by the first-to-last max displacement
         img = read_png(tmp_path / f"lumen_{i:03d}_dia - sys.png")
         assert img.shape == (3, 8, 3)
