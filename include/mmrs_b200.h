@@ -177,6 +177,7 @@ int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out);
  * tiling or not) and the sweep kernel is launched once per class. For the class that carries most of the work:
  * [0] register tile TA (test points per lane of the sweep kernel), [1] bit 0: the test set is walked in several
  * register chunks, bit 1: exact tiling (32 TA points in register slots + a tail pass over the remaining n mod 32),
+ * bit 2: the blocked kernel for units beyond the shared-memory staging (more than ~4 000 points per set),
  * [3] dynamic shared memory per CTA in bytes; [2] CTAs of all sweep launches, [4] number of size classes.   */
 int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[5]);
 

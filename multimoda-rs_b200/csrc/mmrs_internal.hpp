@@ -71,12 +71,15 @@ struct mmrs_ctx {
     struct SweepClass {
         int ta = 2;
         bool multi = false, tailp = false;
+        bool big = false;                       // units beyond K1's shared-memory staging: K1b (k_sweep_big)
         size_t smem = 0;
         size_t work_begin = 0, work_count = 0;  // range of h_work / d_work
         long long cost = 0;                     // padded pair evaluations per candidate, summed over the class
     };
     std::vector<SweepClass> classes;
     std::vector<int> class_of_unit;
+    long long big_scratch_per_warp = 0;         // K1b: floats of row-minimum scratch per warp (largest padded test set)
+    mmrs::DevBuf d_big_rows, d_exact_scratch;   // K1b row minima across reference blocks; K3 rotated points of oversize sets
     int max_pts = 1;
     long long total_cands = 0;
     double opt_rel = 2e-6, opt_abs = 2e-6, tie_margin = 0.0;

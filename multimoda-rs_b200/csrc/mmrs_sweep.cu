@@ -177,7 +177,7 @@ void mmrs_ctx::free_all() {
     for (DevBuf* b : {&d_test, &d_ref, &d_units, &d_work, &d_lay, &d_cs64, &d_cs32, &d_zero, &d_dist32, &d_key,
                       &d_rmax, &d_sl_base, &d_sl_dist, &d_sl_count, &d_items, &d_nitems, &d_res, &d_tmp, &d_work_tc,
                       &d_work_list, &d_key_tc, &d_l1_items, &d_l1_count, &d_l1_base, &d_l1_n, &d_units_lb, &d_lay_lb,
-                      &d_work_lb, &d_res_all, &d_cnt, &d_bcast}) {
+                      &d_work_lb, &d_res_all, &d_cnt, &d_bcast, &d_big_rows, &d_exact_scratch}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr;
         b->cap = 0;
@@ -370,6 +370,7 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
     units.assign(U, UnitDesc{});
     ctx->classes.clear();
     ctx->class_of_unit.assign(U, -1);
+    ctx->big_scratch_per_warp = 0;
     long long lay_off = 0;
     for (int64_t u = 0; u < U; ++u) {
         UnitDesc& d = units[u];
@@ -397,22 +398,31 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
             size_t smem = 16 + (size_t)(a_elems + b_elems + nb_elems + t_elems) * 16;
             if (d.n_chunks > 1) smem += (size_t)kWarpsPerCta * 2 * d.m_pairs * 4;
             if (cc.tailp) smem += (size_t)kWarpsPerCta * 32 * (cc.ta + 1) * 4;
-            if (smem > (size_t)kMaxDynSmem)
-                return set_err(ctx, MMRS_ERR_ARG,
-                               "unit too large for the shared-memory staging of the sweep kernel (" +
-                                   std::to_string(smem) + " B > 227 KB)");
+            static const bool force_big = std::getenv("MMRS_FORCE_BIG") && std::getenv("MMRS_FORCE_BIG")[0] == '1';
+            const bool big = smem > (size_t)kMaxDynSmem || (force_big && d.n >= 64);
+            if (big) {
+                // does not fit K1's shared-memory staging: K1b streams the reference set through shared memory in blocks
+                // (k_sweep_big; register tile 16, the whole staging image stays in global memory / L2)
+                lay_off -= a_elems + b_elems + nb_elems + t_elems;
+                d.ta = kBigTA;
+                d.n_chunks = (d.n + 32 * kBigTA - 1) / (32 * kBigTA);
+                d.n_tail = 0;
+                lay_off += (long long)d.n_chunks * (kBigTA / 2) * 32 + d.m_pairs + (d.m_pairs + 1) / 2;
+                smem = 0;
+                ctx->big_scratch_per_warp = std::max<long long>(ctx->big_scratch_per_warp, (long long)d.n_chunks * 32 * kBigTA);
+            }
             int k = 0;
             for (; k < (int)ctx->classes.size(); ++k) {
                 const auto& c = ctx->classes[k];
-                if (c.ta == cc.ta && c.multi == (d.n_chunks > 1) && c.tailp == cc.tailp) break;
+                if (c.big == big && (big || (c.ta == cc.ta && c.multi == (d.n_chunks > 1) && c.tailp == cc.tailp))) break;
             }
             if (k == (int)ctx->classes.size()) {
                 mmrs_ctx::SweepClass c;
-                c.ta = cc.ta, c.multi = d.n_chunks > 1, c.tailp = cc.tailp;
+                c.ta = big ? kBigTA : cc.ta, c.multi = d.n_chunks > 1, c.tailp = !big && cc.tailp, c.big = big;
                 ctx->classes.push_back(c);
             }
             ctx->classes[k].smem = std::max(ctx->classes[k].smem, smem);
-            ctx->classes[k].cost += (long long)d.n_chunks * 32 * cc.ta * d.m;
+            ctx->classes[k].cost += (long long)d.n_chunks * 32 * d.ta * d.m;
             ctx->class_of_unit[u] = k;
         }
     }
@@ -428,6 +438,7 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
             const int ra = (d.n + 127) / 128 * 128;
             smem_tc = std::max(smem_tc, tc_smem_bytes(d.n, d.m, ra <= 1024 ? 2 : 1));
         }
+        for (const auto& cl : ctx->classes) ok = ok && !cl.big;
         ctx->tc_shape_ok = ok && smem_tc > 0 && smem_tc <= 227 * 1024;
         ctx->smem_tc = smem_tc;
     }
@@ -439,6 +450,7 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
             if (d.n < 128 || d.m < 128) ok = false;
             biggest = std::max(biggest, std::max(d.n, d.m));
         }
+        for (const auto& cl : ctx->classes) ok = ok && !cl.big;   // the list re-scoring kernel does not take K1b's units
         ctx->lb_R = biggest >= 1024 ? 128 : 32;  // rows per lower-bound pass: k_lb<1,8> or k_lb<4,2>
         ctx->lb_shape_ok = ok && biggest > 0;
         ctx->h_units_lb.assign(2 * (size_t)U, UnitDesc{});
@@ -655,7 +667,10 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
         if (env && *env && mode == 0) mode = (*env == '0') ? 1 : 3;
         if (mode == 0) mode = kXfDefault ? 3 : 1;
         // worth it when the sweep is long enough to pay for two extra launches (window + re-scoring)
-        ctx->use_xf = mode == 3 && !ctx->use_tc && ctx->part_active != 2 && live >= (ctx->opt_prefilter == 3 ? 1 : (1 << 20));
+        bool any_big = false;
+        for (const auto& cl : ctx->classes) any_big = any_big || cl.big;
+        ctx->use_xf = mode == 3 && !ctx->use_tc && !any_big && ctx->part_active != 2 &&
+                      live >= (ctx->opt_prefilter == 3 ? 1 : (1 << 20));
         if (ctx->use_xf) {
             ctx->l1_cap = (unsigned)std::min<long long>(std::max<long long>({(long long)U * 64, 65536LL, live / 32}),
                                                         std::max<long long>(live, 1));
@@ -805,20 +820,36 @@ extern "C" int mmrs_sweep_regrid(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t 
 }
 
 // ---- run ------------------------------------------------------------------------------
-static int exact_smem(const mmrs_ctx* ctx) { return 64 + 2 * ctx->max_pts * 16; }
+// K3 launch shape: both point sets of an item in shared memory (f64), or — sets too large for it — the rotated points in
+// a per-CTA scratch row in global memory (d_exact_scratch) and the reference set read in place.
+struct ExactPlan {
+    int smem, grid;
+    double2* scratch;
+};
+static int exact_plan(mmrs_ctx* ctx, int max_pts, int want_grid, ExactPlan* p) {
+    const long long smem = 64 + 2LL * max_pts * 16;
+    if (smem <= kMaxDynSmem) {
+        *p = ExactPlan{(int)smem, want_grid, nullptr};
+        return MMRS_OK;
+    }
+    const int grid = std::max(1, std::min(want_grid, ctx->n_sm * 2));
+    ENSURE(ctx->d_exact_scratch, (size_t)grid * max_pts * 16);
+    *p = ExactPlan{64, grid, (double2*)ctx->d_exact_scratch.p};
+    return MMRS_OK;
+}
 
 // f64 recheck of every candidate of `unit` (shortlist overflow): leftmost arg-min on the host
 // over device-computed reference-arithmetic distances.
 static int full_f64_unit(mmrs_ctx* ctx, int64_t u, UnitResultDev& r) {
     const UnitDesc& d = ctx->h_units[u];
     ENSURE(ctx->d_tmp, (size_t)d.n_cand * 8);
-    const int smem = exact_smem(ctx);
+    ExactPlan ep;
+    if (int rc = exact_plan(ctx, ctx->max_pts, std::min(d.n_cand, ctx->n_sm * 8), &ep)) return rc;
     CUDA_TRY(ctx, RAISE_SMEM(k_exact_dense));
-    const int grid = std::min(d.n_cand, ctx->n_sm * 8);
-    k_exact_dense<<<grid, 256, smem, ctx->stream>>>((const UnitDesc*)ctx->d_units.p, (int)u,
-                                                    (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
-                                                    (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
-                                                    d.cand_off, d.n_cand, (double*)ctx->d_tmp.p, ctx->max_pts);
+    k_exact_dense<<<ep.grid, 256, ep.smem, ctx->stream>>>((const UnitDesc*)ctx->d_units.p, (int)u,
+                                                          (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
+                                                          (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
+                                                          d.cand_off, d.n_cand, (double*)ctx->d_tmp.p, ctx->max_pts, ep.scratch);
     CUDA_TRY(ctx, cudaGetLastError());
     std::vector<double> h(d.n_cand);
     CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_tmp.p, (size_t)d.n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1025,6 +1056,17 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     } else if (!ctx->h_work.empty()) {
         for (const auto& cl : ctx->classes) {   // one launch per size class (register tile / chunked / exact tiling)
             if (!cl.work_count) continue;
+            if (cl.big) {
+                const int grid = (int)std::min<size_t>(cl.work_count, (size_t)ctx->n_sm * 2);
+                ENSURE(ctx->d_big_rows, (size_t)grid * kWarpsPerCta * ctx->big_scratch_per_warp * 4);
+                k_sweep_big<<<grid, kThreads, 0, s>>>(units, (const WorkItem*)ctx->d_work.p + cl.work_begin, (int)cl.work_count,
+                                                      (const float4*)ctx->d_lay.p, (const float2*)ctx->d_cs32.p,
+                                                      (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p,
+                                                      (float*)ctx->d_big_rows.p, ctx->big_scratch_per_warp);
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches += 1;
+                continue;
+            }
             if (!launch_sweep(cl.ta, cl.multi, cl.tailp, (int)cl.work_count, cl.smem, s, units,
                               (const WorkItem*)ctx->d_work.p + cl.work_begin, (const float4*)ctx->d_lay.p,
                               (const float2*)ctx->d_cs32.p, (float*)ctx->d_dist32.p, (unsigned long long*)ctx->d_key.p))
@@ -1049,13 +1091,13 @@ extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     {
-        const int smem = exact_smem(ctx);
+        ExactPlan ep;
+        if (int rc = exact_plan(ctx, ctx->max_pts, ctx->n_sm * 8, &ep)) return rc;
         CUDA_TRY(ctx, RAISE_SMEM(k_exact));
-        const int grid = ctx->n_sm * 8;
-        k_exact<<<grid, 256, smem, s>>>(units, (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
-                                        (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
-                                        (const int2*)ctx->d_items.p, (const unsigned*)ctx->d_nitems.p, ctx->pool_cap,
-                                        (double*)ctx->d_sl_dist.p, ctx->max_pts);
+        k_exact<<<ep.grid, 256, ep.smem, s>>>(units, (const double*)ctx->d_test.p, (const double*)ctx->d_ref.p,
+                                              (const double2*)ctx->d_cs64.p, (const unsigned char*)ctx->d_zero.p,
+                                              (const int2*)ctx->d_items.p, (const unsigned*)ctx->d_nitems.p, ctx->pool_cap,
+                                              (double*)ctx->d_sl_dist.p, ctx->max_pts, ep.scratch);
         CUDA_TRY(ctx, cudaGetLastError());
         k_select<<<(unsigned)((U + 7) / 8), 256, 0, s>>>(units, (int)U, (const double2*)ctx->d_cs64.p,
                                                          (const int2*)ctx->d_items.p,
@@ -1236,7 +1278,7 @@ extern "C" int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[5]) {
     for (const auto& cl : ctx->classes)
         if (!top || cl.cost > top->cost) top = &cl;
     plan_out[0] = top ? top->ta : 0;
-    plan_out[1] = top ? (top->multi ? 1 : 0) | (top->tailp ? 2 : 0) : 0;
+    plan_out[1] = top ? (top->multi ? 1 : 0) | (top->tailp ? 2 : 0) | (top->big ? 4 : 0) : 0;
     plan_out[2] = (int64_t)ctx->h_work.size();
     plan_out[3] = top ? (int64_t)top->smem : 0;
     plan_out[4] = (int64_t)ctx->classes.size();
@@ -1298,14 +1340,13 @@ extern "C" int mmrs_eval_exact(mmrs_ctx* ctx, const double* test_xy, int64_t n_t
     CUDA_TRY(ctx, cudaMemcpyAsync(base + o_zero, zero.data(), (size_t)n_angles, cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(base + o_unit, &d, sizeof(UnitDesc), cudaMemcpyHostToDevice, s));
     const int max_n = (int)std::max(n_test, n_ref);
-    const int smem = 64 + 2 * max_n * 16;
-    if (smem > 227 * 1024) return set_err(ctx, MMRS_ERR_ARG, "mmrs_eval_exact: point sets too large for shared memory");
+    ExactPlan ep;
+    if (int rc = exact_plan(ctx, max_n, (int)std::min<int64_t>(n_angles, (int64_t)ctx->n_sm * 8), &ep)) return rc;
     CUDA_TRY(ctx, RAISE_SMEM(k_exact_dense));
-    const int grid = (int)std::min<int64_t>(n_angles, (int64_t)ctx->n_sm * 8);
-    k_exact_dense<<<grid, 256, smem, s>>>((const UnitDesc*)(base + o_unit), 0, (const double*)base,
-                                          (const double*)(base + (size_t)n_test * 16), (const double2*)(base + o_cs),
-                                          (const unsigned char*)(base + o_zero), 0, (int)n_angles,
-                                          (double*)(base + o_out), max_n);
+    k_exact_dense<<<ep.grid, 256, ep.smem, s>>>((const UnitDesc*)(base + o_unit), 0, (const double*)base,
+                                                (const double*)(base + (size_t)n_test * 16), (const double2*)(base + o_cs),
+                                                (const unsigned char*)(base + o_zero), 0, (int)n_angles,
+                                                (double*)(base + o_out), max_n, ep.scratch);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(dist_out, base + o_out, b_out, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));

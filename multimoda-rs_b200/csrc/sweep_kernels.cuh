@@ -504,6 +504,120 @@ __global__ void __launch_bounds__(kThreads, 2)
 }
 
 // =============================================================================
+// K1b: the FP32 sweep for units that do not fit K1's shared-memory staging (more than ~4 000 points per set; the
+// reference has no size limit, process_utils.rs:84-121). Same arithmetic as K1's chunked flavour (one warp = one
+// candidate, TA = 16 test points per lane and chunk, packed f32x2, 3-input minima, one REDUX per reference point), but
+//   * the REFERENCE set is streamed through shared memory in blocks of kBigBlock points (all warps of the CTA walk the
+//     blocks together, each with its own candidate); the per-warp column-minimum array only spans one block;
+//   * the TEST set is read chunk by chunk from the staging image in global memory (L2) and rotated again per block;
+//   * the ROW minima of a candidate persist across the blocks in a per-warp scratch row in global memory
+//     ([CTA][warp][slot][lane] floats, coalesced, L2-resident: 2 x 4 B per test point and block).
+// Persistent grid: CTA b walks the work items b, b + gridDim.x, ... (its scratch rows are reused).
+// =============================================================================
+constexpr int kBigBlock = 1024;   // reference points per shared-memory block
+constexpr int kBigTA = 16;
+
+__global__ void __launch_bounds__(kThreads, 2)
+    k_sweep_big(const UnitDesc* __restrict__ units, const WorkItem* __restrict__ work, int n_work,
+                const float4* __restrict__ lay, const float2* __restrict__ cs32, float* __restrict__ dist32,
+                unsigned long long* __restrict__ key, float* __restrict__ row_scratch, long long scratch_per_warp) {
+    constexpr int TA = kBigTA, H = TA / 2;
+    __shared__ __align__(16) float4 sB[kBigBlock / 2];
+    __shared__ unsigned s_col[kWarpsPerCta][kBigBlock];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float INF = __int_as_float(0x7f800000);
+    float* my_rows = row_scratch + ((long long)blockIdx.x * kWarpsPerCta + wid) * scratch_per_warp;
+    unsigned* my_col = s_col[wid];
+    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const WorkItem w = work[wi];
+        const UnitDesc ud = units[w.unit];
+        const float4* gA = lay + ud.lay_off;
+        const float4* gB = gA + (long long)ud.n_chunks * H * 32;
+        const int n_blocks = (ud.m_pairs + kBigBlock / 2 - 1) / (kBigBlock / 2);
+        for (int c0 = 0; c0 < w.count; c0 += kWarpsPerCta) {   // one candidate per warp and round; every warp walks the blocks
+            const bool live = c0 + wid < w.count;
+            const int c = w.begin + min(c0 + wid, w.count - 1);
+            const float2 cs = __ldg(&cs32[ud.cand_off + c]);
+            const uint64_t C2 = pk(cs.x, cs.x), S2 = pk(cs.y, cs.y), NS2 = pk(-cs.y, -cs.y);
+            unsigned rowmax = 0u, colmax = 0u;
+            for (int bb = 0; bb < n_blocks; ++bb) {
+                const int j0 = bb * (kBigBlock / 2), jn = min(kBigBlock / 2, ud.m_pairs - j0);
+                __syncthreads();   // every warp is done with the previous block
+                for (int j = threadIdx.x; j < jn; j += kThreads) sB[j] = gB[j0 + j];
+                __syncthreads();
+                const bool last_block = bb == n_blocks - 1;
+                for (int ch = 0; ch < ud.n_chunks; ++ch) {
+                    uint64_t AX[H], AY[H];
+                    float row[TA];
+#pragma unroll
+                    for (int k = 0; k < H; ++k) {
+                        const float4 a = __ldg(&gA[(ch * H + k) * 32 + lane]);
+                        const uint64_t X2 = pk(a.x, a.y), Y2 = pk(a.z, a.w);
+                        AX[k] = fma2(Y2, NS2, mul2(X2, C2));
+                        AY[k] = fma2(X2, S2, mul2(Y2, C2));
+                        if (bb == 0) {
+                            row[2 * k] = INF;
+                            row[2 * k + 1] = INF;
+                        } else {   // the row minima over the previous blocks
+                            const float2 r = *reinterpret_cast<const float2*>(&my_rows[((ch * H + k) * 32 + lane) * 2]);
+                            row[2 * k] = r.x;
+                            row[2 * k + 1] = r.y;
+                        }
+                    }
+                    const bool last_chunk = ch == ud.n_chunks - 1;
+#pragma unroll 2
+                    for (int j = 0; j < jn; ++j) {
+                        const float4 B = sB[j];
+                        const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y), bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
+                        float q0 = INF, q1 = INF;
+                        if (ch > 0 && lane == 0) {
+                            const uint2 prev = *reinterpret_cast<const uint2*>(&my_col[2 * j]);
+                            q0 = __uint_as_float(prev.x);
+                            q1 = __uint_as_float(prev.y);
+                        }
+#pragma unroll
+                        for (int k = 0; k < H; ++k) {
+                            const uint64_t dx0 = sub2(AX[k], bx0), dy0 = sub2(AY[k], by0);
+                            const uint64_t dx1 = sub2(AX[k], bx1), dy1 = sub2(AY[k], by1);
+                            const uint64_t d0 = fma2(dx0, dx0, mul2(dy0, dy0));
+                            const uint64_t d1 = fma2(dx1, dx1, mul2(dy1, dy1));
+                            float d00, d10, d01, d11;
+                            upk(d0, d00, d10);
+                            upk(d1, d01, d11);
+                            row[2 * k] = min3(row[2 * k], d00, d01);
+                            row[2 * k + 1] = min3(row[2 * k + 1], d10, d11);
+                            q0 = min3(q0, d00, d10);
+                            q1 = min3(q1, d01, d11);
+                        }
+                        const unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(q0));
+                        const unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(q1));
+                        if (last_chunk) colmax = max(colmax, max(r0, r1));
+                        else if (lane == 0) *reinterpret_cast<uint2*>(&my_col[2 * j]) = make_uint2(r0, r1);
+                    }
+                    if (last_block) {
+                        float rm = row[0];
+#pragma unroll
+                        for (int k = 1; k < TA; ++k) rm = fmaxf(rm, row[k]);
+                        rowmax = max(rowmax, __float_as_uint(rm));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < H; ++k)
+                            *reinterpret_cast<float2*>(&my_rows[((ch * H + k) * 32 + lane) * 2]) = make_float2(row[2 * k], row[2 * k + 1]);
+                    }
+                    __syncwarp();   // the next chunk reads the column minima lane 0 just stored
+                }
+            }
+            const unsigned h2 = __reduce_max_sync(0xffffffffu, max(rowmax, colmax));
+            const float d = sqrtf(__uint_as_float(h2));
+            if (lane == 0 && live) {
+                dist32[ud.dist_off + c] = d;
+                atomicMin(&key[w.unit], ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c);
+            }
+        }
+    }
+}
+
+// =============================================================================
 // K1p: exact lower-bound pruning tier (opt-in, mmrs_sweep_opts.prune). For ANY subsets A' of the test points and B'
 // of the reference points,
 //     H(A, B) = max( max_{a in A} min_{b in B} |a - b| , max_{b in B} min_{a in A} |a - b| )
@@ -778,9 +892,13 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
     return r;
 }
 
+// s_rot / s_ref: the CTA's staging of the rotated test set / the reference set — shared memory, or (units too large for
+// it) a per-CTA scratch row in global memory for the rotated points and the caller's reference array itself (copy_ref = false).
 __device__ __forceinline__ double exact_cost(const UnitDesc& ud, const double* __restrict__ test_xy,
                                              const double* __restrict__ ref_xy, double cosv, double sinv, bool identity,
-                                             double2* s_rot, double2* s_ref, double* s_red) {
+                                             double2* s_rot, const double2* s_ref_in, double* s_red, bool copy_ref = true) {
+    double2* s_ref_w = const_cast<double2*>(s_ref_in);
+    const double2* s_ref = copy_ref ? s_ref_in : reinterpret_cast<const double2*>(ref_xy + 2 * ud.ref_off);
     for (int i = threadIdx.x; i < ud.n; i += blockDim.x) {
         const double px = test_xy[2 * (ud.test_off + i)], py = test_xy[2 * (ud.test_off + i) + 1];
         double rx = px, ry = py;
@@ -791,8 +909,9 @@ __device__ __forceinline__ double exact_cost(const UnitDesc& ud, const double* _
         }
         s_rot[i] = make_double2(rx, ry);
     }
-    for (int j = threadIdx.x; j < ud.m; j += blockDim.x)
-        s_ref[j] = make_double2(ref_xy[2 * (ud.ref_off + j)], ref_xy[2 * (ud.ref_off + j) + 1]);
+    if (copy_ref)
+        for (int j = threadIdx.x; j < ud.m; j += blockDim.x)
+            s_ref_w[j] = make_double2(ref_xy[2 * (ud.ref_off + j)], ref_xy[2 * (ud.ref_off + j) + 1]);
     __syncthreads();
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     // forward: reference -> rotated
@@ -830,11 +949,12 @@ __global__ void __launch_bounds__(256)
     k_exact(const UnitDesc* __restrict__ units, const double* __restrict__ test_xy, const double* __restrict__ ref_xy,
             const double2* __restrict__ cs64, const unsigned char* __restrict__ zero_flag,
             const int2* __restrict__ items, const unsigned* __restrict__ n_items, unsigned pool_cap,
-            double* __restrict__ sl_dist, int max_n) {
+            double* __restrict__ sl_dist, int max_n, double2* __restrict__ g_scratch) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_red = reinterpret_cast<double*>(smem_raw);
-    double2* s_rot = reinterpret_cast<double2*>(smem_raw + 64);
-    double2* s_ref = s_rot + max_n;
+    // g_scratch != NULL: the point sets do not fit shared memory — rotated points in this CTA's global scratch row
+    double2* s_rot = g_scratch ? g_scratch + (size_t)blockIdx.x * max_n : reinterpret_cast<double2*>(smem_raw + 64);
+    double2* s_ref = g_scratch ? nullptr : s_rot + max_n;
     const unsigned total = min(*n_items, pool_cap);
     for (unsigned it = blockIdx.x; it < total; it += gridDim.x) {
         const int2 item = items[it];
@@ -843,7 +963,7 @@ __global__ void __launch_bounds__(256)
         const int c = item.y;
         const double2 cs = cs64[ud.cand_off + c];
         const bool identity = zero_flag[ud.cand_off + c] != 0;
-        const double d = exact_cost(ud, test_xy, ref_xy, cs.x, cs.y, identity, s_rot, s_ref, s_red);
+        const double d = exact_cost(ud, test_xy, ref_xy, cs.x, cs.y, identity, s_rot, s_ref, s_red, g_scratch == nullptr);
         if (threadIdx.x == 0) sl_dist[it] = d;
         __syncthreads();
     }
@@ -855,16 +975,16 @@ __global__ void __launch_bounds__(256)
     k_exact_dense(const UnitDesc* __restrict__ units, int unit, const double* __restrict__ test_xy,
                   const double* __restrict__ ref_xy, const double2* __restrict__ cs64,
                   const unsigned char* __restrict__ zero_flag, long long cs_off, int count, double* __restrict__ out,
-                  int max_n) {
+                  int max_n, double2* __restrict__ g_scratch) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_red = reinterpret_cast<double*>(smem_raw);
-    double2* s_rot = reinterpret_cast<double2*>(smem_raw + 64);
-    double2* s_ref = s_rot + max_n;
+    double2* s_rot = g_scratch ? g_scratch + (size_t)blockIdx.x * max_n : reinterpret_cast<double2*>(smem_raw + 64);
+    double2* s_ref = g_scratch ? nullptr : s_rot + max_n;
     const UnitDesc ud = units[unit];
     for (int c = blockIdx.x; c < count; c += gridDim.x) {
         const double2 cs = cs64[cs_off + c];
         const bool identity = zero_flag[cs_off + c] != 0;
-        const double d = exact_cost(ud, test_xy, ref_xy, cs.x, cs.y, identity, s_rot, s_ref, s_red);
+        const double d = exact_cost(ud, test_xy, ref_xy, cs.x, cs.y, identity, s_rot, s_ref, s_red, g_scratch == nullptr);
         if (threadIdx.x == 0) out[c] = d;
         __syncthreads();
     }

@@ -236,7 +236,7 @@ class Context:
     def plan(self):
         p = (C.c_int64 * 5)()
         self._check(lib().mmrs_sweep_plan(self._p, p))
-        return dict(TA=p[0], multi=bool(p[1] & 1), exact_tiling=bool(p[1] & 2), ctas=p[2], smem_bytes=p[3],
+        return dict(TA=p[0], multi=bool(p[1] & 1), exact_tiling=bool(p[1] & 2), blocked=bool(p[1] & 4), ctas=p[2], smem_bytes=p[3],
                     size_classes=p[4])
 
     def dist32(self, unit, n_cand):

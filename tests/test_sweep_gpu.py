@@ -208,15 +208,30 @@ def test_degenerate_and_empty_units(ctx):
     assert res["best_idx"][0] == ora.sweep(p, p, (4.5, 4.5), 0, 1.0, 10.0)["index"]
 
 
-def test_oversize_unit_is_refused(ctx):
-    """A unit that does not fit the shared-memory staging of K1 (N = M beyond ~4 800 points) is a clean
-    error of the call, not a crash or a silent fallback; the context stays usable."""
-    rng = np.random.default_rng(5)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_units_beyond_the_shared_memory_staging(ctx, mode):
+    """The reference has no size limit (process_utils.rs:84-121). Units that do not fit K1's shared-memory staging
+    (more than ~4 000 points per set) take the blocked kernel K1b (reference set streamed through shared memory in
+    blocks, row minima kept across blocks) and the f64 recheck with its rotated points in global memory: N = M = 8 000,
+    lopsided sets, next to an ordinary 520-point unit in the same batch — same bars as everywhere else."""
+    rng = np.random.default_rng(5 + mode)
+    sizes = [(8000, 8000), (520, 520), (5000, 300), (300, 9000), (4500, 4600)]
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, sizes)
+    g = nat.make_grid(1.0, 12.0)
+    res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=mode, keep_dist32=True)
+    p = ctx.plan()
+    assert p["blocked"] and p["size_classes"] >= 2
+    for u, (t, r, c) in enumerate(zip(tests, refs, cents)):
+        o = ora.sweep(t, r, c, mode, 1.0, 12.0, threads=16)
+        assert res["best_idx"][u] == o["index"] and res["best_angle"][u] == o["angle"], (u, sizes[u])
+        assert res["best_dist"][u] == o["cost"], (u, sizes[u])
+        d32 = ctx.dist32(u, len(o["costs"])).astype(np.float64)
+        assert (np.abs(d32 - o["costs"]) <= REL_TOL_FP32 * o["costs"]).all(), (u, sizes[u])
+    # the literal cost closure on oversize sets (rotated points in global scratch)
+    ang = np.array([0.0, 0.1, -0.2])
+    assert np.array_equal(ctx.eval_exact(tests[0], refs[0], cents[0], mode, ang), ora.costs(tests[0], refs[0], cents[0], mode, ang))
     big = contour(rng, 6000)
-    with pytest.raises(nat.MmrsError, match="unit too large"):
-        ctx.sweep_batched(big, [0, 6000], big, [0, 6000], np.zeros((1, 2)) + 4.5, [nat.make_grid(1.0, 5.0)], mode=0)
-    ok = contour(rng, 4000)
-    res = ctx.sweep_batched(ok, [0, 4000], ok, [0, 4000], np.zeros((1, 2)) + 4.5, [nat.make_grid(1.0, 5.0)], mode=0)
+    res = ctx.sweep_batched(big, [0, 6000], big, [0, 6000], np.zeros((1, 2)) + 4.5, [nat.make_grid(1.0, 5.0)], mode=0)
     assert res["best_idx"][0] == 5 and res["best_dist"][0] == 0.0          # the identity rotation of a set on itself
 
 
