@@ -258,12 +258,14 @@ typedef struct mmrs_align_params {
  * src/intravascular/binding/entry.rs for a batch of `n_cases` independent
  * cases (patients): mode 4 = full_processing_rs (:71-361), 3 =
  * double_pair_processing_rs (:363-570), 2 = pair_processing_rs (:572-689),
- * 1 = single_processing_rs (:691-780); each with write_obj = false (OBJ export is
- * out of scope). Input: n_cases *
+ * 1 = single_processing_rs (:691-780); each with write_obj = false (the OBJ / MTL / PNG
+ * export is a separate call: mmrs_export_pair / mmrs_export_single below). Input: n_cases *
  * n_in(mode) geometry blobs (n_in = 4,4,2,1). Output: n_cases * n_out(mode)
  * blobs (8,4,2,1: pair ab = (a,b), cd, ac, bd) and n_cases * n_in log arrays.
  * All intrapullback sweeps of all cases run as ONE batch per search stage, all
- * inter-pullback sweeps of a dependency level likewise.                       */
+ * inter-pullback sweeps of a dependency level likewise.
+ * Ownership: every output slot is set to NULL / 0 on entry; on success the caller owns the malloc'ed blobs and
+ * log arrays (mmrs_free); on a non-zero return everything written so far has been released and the slots are NULL. */
 int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, const double* const* blobs,
                        const int64_t* blob_lens, const mmrs_align_params* params, double** out_blobs,
                        int64_t* out_lens, double** out_logs, int64_t* out_nlogs, int32_t* out_anomalous);

@@ -77,9 +77,23 @@ struct Trace {
 
 // Host-side parallelism over independent geometries (the reference runs its 4 pullbacks in a
 // crossbeam scope, binding/entry.rs:140-203). The first exception wins and is rethrown.
+// Host threads this process may use: MMRS_HOST_THREADS, else the hardware concurrency divided by the ranks that share
+// the host (LOCAL_WORLD_SIZE / WORLD_SIZE under torchrun: one process per GPU must not oversubscribe the cores N-fold).
+inline size_t host_thread_budget() {
+    static const size_t budget = [] {
+        if (const char* e = std::getenv("MMRS_HOST_THREADS"))
+            if (std::atoi(e) > 0) return (size_t)std::atoi(e);
+        size_t hw = std::max(1u, std::thread::hardware_concurrency());
+        const char* w = std::getenv("LOCAL_WORLD_SIZE");
+        if (!w) w = std::getenv("WORLD_SIZE");
+        const int ranks = w ? std::atoi(w) : 1;
+        return ranks > 1 ? std::max<size_t>(2, hw / (size_t)ranks) : hw;
+    }();
+    return budget;
+}
 template <class F>
 void parallel_for(size_t n, F&& f, size_t max_threads = ~(size_t)0) {
-    const size_t nt = std::min(max_threads, std::min<size_t>(n, std::max(1u, std::thread::hardware_concurrency())));
+    const size_t nt = std::min(max_threads, std::min<size_t>(n, host_thread_budget()));
     if (nt <= 1) {
         for (size_t i = 0; i < n; ++i) f(i);
         return;
@@ -323,8 +337,8 @@ Contour read_contour(Reader& r) {
     c.at = r.get();
     c.has_pt = r.get() != 0.0;
     c.pt = r.get();
-    const size_t n = (size_t)r.get();
-    if ((size_t)(r.e - r.p) < 6 * n) throw InputErr("geometry blob truncated");
+    const size_t n = as_usize(r.get());   // counts inside a blob are not trusted: NaN / negative / huge values are errors
+    if (n > (size_t)(r.e - r.p) / 6) throw InputErr("geometry blob truncated");
     c.resize(n);
     for (size_t i = 0; i < n; ++i) {
         c.fi[i] = (uint32_t)r.p[0], c.pi[i] = (uint32_t)r.p[1];
@@ -342,7 +356,8 @@ Frame read_frame(Reader& r) {
     f.ref.fi = (uint32_t)r.get(), f.ref.pi = (uint32_t)r.get();
     f.ref.x = r.get(), f.ref.y = r.get(), f.ref.z = r.get();
     f.ref.ao = r.get() != 0.0;
-    const size_t nc = (size_t)r.get();
+    const size_t nc = as_usize(r.get());
+    if (nc > (size_t)(r.e - r.p) / 12) throw InputErr("geometry blob truncated");   // every contour has a 12-double header
     for (size_t q = 0; q < nc; ++q) {
         Contour c = read_contour(r);
         if (q == 0)
@@ -360,7 +375,7 @@ Geometry decode(const double* data, int64_t len) {
     if (!data || len < 1) throw InputErr("geometry blob is empty");
     Reader r{data, data + len};
     Geometry g;
-    const size_t nf = (size_t)r.get();
+    const size_t nf = as_usize(r.get());
     if (nf > (size_t)len / 24) throw InputErr("geometry blob truncated");  // a frame is at least two 12-double headers
     if ((size_t)len < kParallelBlobDoubles || nf < 2 * kBlobThreads) {
         g.frames.reserve(nf);
@@ -371,12 +386,13 @@ Geometry decode(const double* data, int64_t len) {
     for (size_t k = 0; k < nf; ++k) {  // skip over frame k using the counts in its headers
         at[k] = r.p;
         if (r.e - r.p < 12) throw InputErr("geometry blob truncated");
-        const size_t nc = (size_t)r.p[11];
+        const size_t nc = as_usize(r.p[11]);
         r.p += 12;
+        if (nc > (size_t)(r.e - r.p) / 12) throw InputErr("geometry blob truncated");
         for (size_t q = 0; q < nc; ++q) {
             if (r.e - r.p < 12) throw InputErr("geometry blob truncated");
-            const size_t n = (size_t)r.p[11];
-            if ((size_t)(r.e - r.p - 12) < 6 * n) throw InputErr("geometry blob truncated");
+            const size_t n = as_usize(r.p[11]);
+            if (n > (size_t)(r.e - r.p - 12) / 6) throw InputErr("geometry blob truncated");
             r.p += 12 + 6 * n;
         }
     }
@@ -1840,7 +1856,11 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
     const int n_in = mode >= 3 ? 4 : mode;
     const int n_out = mode == 4 ? 8 : mode == 3 ? 4 : mode;
     for (int i = 0; i < 5; ++i) ctx->stats[i] = 0;
-    return guarded(ctx, [&] {
+    // Output contract: every slot is NULL / 0 on entry; on failure everything written so far is released and the slots are
+    // NULL again, so the caller never owns anything after a non-zero return.
+    for (int64_t k = 0; k < n_cases * n_out; ++k) out_blobs[k] = nullptr, out_lens[k] = 0;
+    for (int64_t k = 0; k < n_cases * n_in; ++k) out_logs[k] = nullptr, out_nlogs[k] = 0;
+    const int rc = guarded(ctx, [&] {
         Searcher S{ctx, ctx->stats};
         Trace tr;
         std::vector<Geometry> geo((size_t)n_cases * n_in);
@@ -1919,6 +1939,11 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
         flush();
         tr.lap("level 2 + encode");
     });
+    if (rc != MMRS_OK) {
+        for (int64_t k = 0; k < n_cases * n_out; ++k) std::free(out_blobs[k]), out_blobs[k] = nullptr, out_lens[k] = 0;
+        for (int64_t k = 0; k < n_cases * n_in; ++k) std::free(out_logs[k]), out_logs[k] = nullptr, out_nlogs[k] = 0;
+    }
+    return rc;
 }
 
 extern "C" int mmrs_ctx_set_shard(mmrs_ctx* ctx, int32_t rank, int32_t world, mmrs_exchange_fn fn, void* user) {

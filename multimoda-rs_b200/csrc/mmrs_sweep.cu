@@ -30,6 +30,24 @@ static thread_local std::string g_err_noctx = "";
         }                                                                                         \
     } while (0)
 
+// Every entry point runs on the context's device and leaves the caller's current device as it found it (a host that
+// manages several GPUs itself, e.g. a PyTorch process, must not have its later launches redirected).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ENTER_DEVICE(ctx)                  \
+    DeviceGuard _device_guard((ctx)->device); \
+    CUDA_TRY(ctx, _device_guard.err)
+
 int mmrs::set_err(mmrs_ctx* ctx, int code, const std::string& msg) {
     if (ctx)
         ctx->err = msg;
@@ -142,7 +160,7 @@ extern "C" int mmrs_ctx_create(int device, void* stream, mmrs_ctx** out) {
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
     ctx->sm_clock_khz = prop.clockRate;
-    cudaSetDevice(device);
+    DeviceGuard guard(device);
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
         ctx->own_stream = false;
@@ -154,21 +172,29 @@ extern "C" int mmrs_ctx_create(int device, void* stream, mmrs_ctx** out) {
         }
         ctx->own_stream = true;
     }
-    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-    for (auto& ev : ctx->ev_tc) cudaEventCreate(&ev);
+    bool ev_ok = true;
+    for (auto& ev : ctx->ev) ev_ok = ev_ok && cudaEventCreate(&ev) == cudaSuccess;
+    for (auto& ev : ctx->ev_tc) ev_ok = ev_ok && cudaEventCreate(&ev) == cudaSuccess;
+    if (!ev_ok) {
+        const std::string msg = std::string("cudaEventCreate: ") + cudaGetErrorString(cudaGetLastError());
+        mmrs_ctx_destroy(ctx);
+        return set_err(nullptr, MMRS_ERR_CUDA, msg);
+    }
     *out = ctx;
     return MMRS_OK;
 }
 
 extern "C" void mmrs_ctx_destroy(mmrs_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
     ctx->comm = nullptr;
     ctx->free_all();
-    for (auto& ev : ctx->ev) cudaEventDestroy(ev);
-    for (auto& ev : ctx->ev_tc) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_tc)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -761,7 +787,7 @@ extern "C" int mmrs_sweep_upload(mmrs_ctx* ctx, const mmrs_sweep_batch* b, const
         (b->n_grids < 1 && b->n_units > 0))
         return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: bad batch");
     if (b->mode != 0 && b->mode != 1) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_upload: mode must be 0 or 1");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     ctx->ready = false;
     ctx->ran = false;
     ctx->n_units = b->n_units;
@@ -807,7 +833,7 @@ extern "C" int mmrs_sweep_regrid(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t 
     if (!ctx->ready) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_regrid: no batch uploaded");
     if (ctx->n_units == 0) return MMRS_OK;
     if (!grids || n_grids < 1) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_regrid: bad grids");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     ctx->ready = false;
     ctx->ran = false;
     ctx->tie_margin = tie_margin > 0 ? tie_margin : 0.0;
@@ -875,7 +901,7 @@ static int full_f64_unit(mmrs_ctx* ctx, int64_t u, UnitResultDev& r) {
 extern "C" int mmrs_sweep_run(mmrs_ctx* ctx) {
     if (!ctx) return set_err(nullptr, MMRS_ERR_ARG, "mmrs_sweep_run: ctx is NULL");
     if (!ctx->ready) return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_run: no batch uploaded");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     const int64_t U = ctx->n_units;
     ctx->launches = 0;
     ctx->ran = true;
@@ -1149,7 +1175,7 @@ extern "C" int mmrs_sweep_download(mmrs_ctx* ctx, mmrs_unit_result* out) {
     const int64_t U = ctx->n_units;
     if (U == 0) return MMRS_OK;
     if (!out) return set_err(ctx, MMRS_ERR_ARG, "mmrs_sweep_download: out is NULL");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res.p, U * sizeof(UnitResultDev), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1230,7 +1256,7 @@ extern "C" int mmrs_sweep_get_dist32(mmrs_ctx* ctx, int64_t unit, float* out, in
     if (unit < 0 || unit >= ctx->n_units) return set_err(ctx, MMRS_ERR_ARG, "unit out of range");
     const UnitDesc& d = ctx->h_units[unit];
     const int64_t n = std::min<int64_t>(cap, d.n_cand);
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (n > 0)
         CUDA_TRY(ctx, cudaMemcpy(out, (const float*)ctx->d_dist32.p + d.dist_off, n * 4, cudaMemcpyDeviceToHost));
@@ -1242,7 +1268,7 @@ extern "C" int mmrs_sweep_get_shortlist(mmrs_ctx* ctx, int64_t unit, int64_t* id
     if (!ctx || !ctx->ready || !ctx->ran)
         return set_err(ctx, MMRS_ERR_STATE, "mmrs_sweep_get_shortlist: nothing has been run");
     if (unit < 0 || unit >= ctx->n_units) return set_err(ctx, MMRS_ERR_ARG, "unit out of range");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     auto ov = ctx->overflow_dist.find(unit);
     if (ov != ctx->overflow_dist.end()) {  // the whole unit was rechecked
@@ -1287,7 +1313,7 @@ extern "C" int mmrs_sweep_plan(mmrs_ctx* ctx, int64_t plan_out[5]) {
 
 extern "C" int mmrs_last_timings(mmrs_ctx* ctx, float ms_out[4], int32_t* launches_out) {
     if (!ctx || !ctx->ran) return set_err(ctx, MMRS_ERR_STATE, "mmrs_last_timings: nothing has been run");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     for (int i = 0; i < 4; ++i) ms_out[i] = 0.f;
     if (ctx->n_units > 0) {
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
@@ -1312,7 +1338,7 @@ extern "C" int mmrs_eval_exact(mmrs_ctx* ctx, const double* test_xy, int64_t n_t
         for (int64_t i = 0; i < n_angles; ++i) dist_out[i] = 0.0;
         return MMRS_OK;
     }
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     cudaStream_t s = ctx->stream;
     std::vector<double> cs(2 * n_angles);
     std::vector<unsigned char> zero(n_angles);
@@ -1357,7 +1383,7 @@ extern "C" int mmrs_eval_exact(mmrs_ctx* ctx, const double* test_xy, int64_t n_t
 // ---- FP32 peak probe ------------------------------------------------------------------------
 extern "C" int mmrs_fp32_probe(mmrs_ctx* ctx, int32_t iters, double* tflops_out) {
     if (!ctx || !tflops_out) return set_err(ctx, MMRS_ERR_ARG, "mmrs_fp32_probe: bad arguments");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     const int blocks = ctx->n_sm * 8;
     ENSURE(ctx->d_tmp, (size_t)blocks * 256 * 4);
     cudaEvent_t a, b;
@@ -1385,7 +1411,7 @@ extern "C" int mmrs_sweep_prefilter_info(mmrs_ctx* ctx, double out[6]) {
     for (int i = 0; i < 6; ++i) out[i] = 0.0;
     out[5] = ctx->tc_abs;
     if ((!ctx->tc_ran && !ctx->prune_ran) || ctx->n_units == 0) return MMRS_OK;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
     float a = 0.f, b = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&a, ctx->ev_tc[0], ctx->ev_tc[1]));
@@ -1421,7 +1447,7 @@ extern "C" int mmrs_ctx_comm_init(mmrs_ctx* ctx, const uint8_t id[MMRS_COMM_ID_B
     if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, MMRS_ERR_ARG, "mmrs_ctx_comm_init: bad rank / world");
     NcclApi& nc = nccl_api();
     if (!nc.ok()) return set_err(ctx, MMRS_ERR_STATE, nc.error);
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     if (ctx->comm) {
         nc.CommDestroy(ctx->comm);
         ctx->comm = nullptr;
@@ -1456,7 +1482,7 @@ int mmrs::comm_broadcast(mmrs_ctx* ctx, void* host, size_t bytes, int root) {
     if (!ctx->comm) return set_err(ctx, MMRS_ERR_STATE, "no communicator bound");
     if (bytes == 0) return MMRS_OK;
     NcclApi& nc = nccl_api();
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     ENSURE(ctx->d_bcast, bytes);
     if (ctx->shard_rank == root)
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_bcast.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -479,13 +479,18 @@ __global__ void __launch_bounds__(kThreads, 2)
         const unsigned h2 = __reduce_max_sync(0xffffffffu, max(rowmax, colmax));
         const float d = sqrtf(__uint_as_float(h2));
         if (lane == 0) {
-            if (LIST) {
+            // A candidate that gave up holds only a proven LOWER BOUND (above the unit's window): it is stored as such
+            // (mmrs_b200.h: dist32 of pruned / given-up candidates is a bound) but enters neither the error diagnostic
+            // nor the unit's key.
+            if (LIST && !gave_up) {
                 const float old = dist32[ud.dist_off + c];
                 worst = fmaxf(worst, fabsf(d * d - old * old));
             }
             dist32[ud.dist_off + c] = d;
-            const unsigned long long k64 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c;
-            best = min(best, k64);
+            if (!LIST || !gave_up) {
+                const unsigned long long k64 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c;
+                best = min(best, k64);
+            }
         }
     }
     if (LIST && lane == 0 && worst > 0.f) {

@@ -38,7 +38,7 @@ mm.from_array_single(mm.numpy_to_inputdata(a, rp, True, label="w"), sample_size=
 
 # ---- config 4: one case, units sharded across ranks ---------------------------------------------------------
 if F4 > 0:
-    _dist.enable_unit_sharding(ctx)
+    _dist.init_comm(ctx)   # the library's NCCL communicator: every batched sweep of the call is partitioned across the ranks
     ins = []
     for k, dia in enumerate((True, False, True, False)):
         a, rp = rows(20261018 + k, F4, 2000)
@@ -49,9 +49,8 @@ if F4 > 0:
                              bruteforce=True, smooth=True, postprocessing=False)
     torch.cuda.synchronize(); dist.barrier()
     wall = time.perf_counter() - t0
-    st = ctx.process_stats()
+    st = ctx.process_stats()   # counters are global (every rank issues every batched sweep; the library partitions it)
     tot = torch.tensor([st["evals"]], dtype=torch.float64, device="cuda")
-    dist.all_reduce(tot)
     logs = res[4]
     h = hash(tuple(np.concatenate([np.array(l, dtype=np.float64).reshape(-1) for l in logs]).tobytes()))
     hs = [None] * world
@@ -61,7 +60,7 @@ if F4 > 0:
                           plan=ctx.plan())
     if rank == 0:
         print("config4", json.dumps(out["config4"]), flush=True)
-    ctx.set_shard(0, 1, None)
+    ctx.set_partition(0)
 
 # ---- config 5: cohort, whole patients dealt to ranks -----------------------------------------------------------
 if P5 > 0:

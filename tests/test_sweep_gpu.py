@@ -390,3 +390,38 @@ def test_non_finite_points_take_no_part(ctx):
     for u in (0, 1, 2, 3):
         got = ctx.eval_exact(tests[u], refs[u], cents[u], 0, angles)
         assert np.array_equal(got, ora.costs(tests[u], refs[u], cents[u], 0, angles)), u
+
+
+def test_contexts_on_several_host_threads_with_different_unit_sizes():
+    """Several contexts driven from several host threads on one GPU (the cohort pipeline does this): the dynamic
+    shared-memory limit of a kernel is per-function state shared by all of them, so it is raised once to the opt-in
+    maximum and never lowered — launches of the same instantiation with different sizes must not disturb each other."""
+    import threading
+
+    rng = np.random.default_rng(77)
+    jobs = []
+    for sizes in ([(520, 520)] * 3, [(700, 650)] * 3, [(300, 310), (2020, 2020)], [(130, 128)] * 4):
+        tests, refs, cents, txy, toff, rxy, roff = make_units(rng, sizes)
+        want = [ora.sweep(t, r, c, 0, 0.5, 20.0) for t, r, c in zip(tests, refs, cents)]
+        jobs.append((txy, toff, rxy, roff, cents, want))
+    errs = []
+
+    def run(job):
+        txy, toff, rxy, roff, cents, want = job
+        try:
+            c = nat.Context(0)
+            g = nat.make_grid(0.5, 20.0)
+            for _ in range(6):
+                res = c.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=0)
+                for u, o in enumerate(want):
+                    assert res["best_idx"][u] == o["index"] and res["best_dist"][u] == o["cost"]
+            c.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    threads = [threading.Thread(target=run, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
