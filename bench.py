@@ -542,19 +542,35 @@ def full_mode_legs(ctx, nat, world, rank, dist, barrier):
         "chain_resolved_units": st["chain_resolved"], "logs_sha256": logs_sha(r[4]),
         "extrapolated_full_config4_s": dt * (4 * 999) / max(4 * (F4 - 1), 1)}
 
-    # config 5 slice: a cohort of full-mode patients in ONE call (200 frames x 500 pts, brute 0.05 deg over +-90)
-    P5 = int(os.environ.get("MMRS_BENCH_CFG5_PATIENTS", "8"))
+    # config 5 slice: a cohort of full-mode patients (200 frames x 500 pts, brute 0.05 deg over +-90). Patients are
+    # independent cases: with N > 1 whole patients are dealt to the ranks (rank r takes patients r, r + N, ...), each rank
+    # runs ONE mmrs_process_cases call on its share with the partition of the sweeps switched off, and the per-frame logs
+    # are gathered — no host work is replicated ("cfg 5: 32 patients/GPU").
+    P5 = int(os.environ.get("MMRS_BENCH_CFG5_PATIENTS", "16"))
+    mine = list(range(rank, P5, world))
     blobs = []
-    for p in range(P5):
+    for p in mine:
         for k in range(4):
             a, rp = pullback_rows(SEED + 5000 + 10 * p + k, 200, 500)
             blobs.append(nat.geometry_from_arrays(a, rp, diastole=k % 2 == 0, label=f"pt{p}_{k}"))
-    dt, r = timed(lambda: nat.process_cases(ctx, 4, blobs, 0.05, 90.0, 500, False, True, False), reps=2)
-    st = ctx.process_stats()
+    ctx.set_partition(0)
+    dt, r = timed(lambda: nat.process_cases(ctx, 4, blobs, 0.05, 90.0, 500, False, True, False) if blobs else ([], [], []),
+                  reps=2)
+    ctx.set_partition(1)
+    st = ctx.process_stats() if blobs else {"evals": 0, "units": 0}
+    shas = {p: logs_sha(r[1][4 * i:4 * i + 4]) for i, p in enumerate(mine)}
+    evals5, units5 = st["evals"], st["units"]
+    if world > 1:
+        box = [None] * world
+        dist.all_gather_object(box, (shas, evals5, units5))
+        shas = {k: v for b_ in box for k, v in b_[0].items()}
+        evals5, units5 = sum(b_[1] for b_ in box), sum(b_[2] for b_ in box)
     out["config5_slice_process_cases"] = {
-        "call": f"mmrs_process_cases, {P5} of 256 patients x full mode (4 x 200 frames x 500 pts), brute 0.05 deg over +-90",
-        "wall_s": dt, "evals": st["evals"], "value": st["evals"] / dt, "unit": UNIT, "units": st["units"],
-        "logs_sha256": logs_sha(r[1]), "extrapolated_256_patients_s": dt * 256 / P5}
+        "call": f"mmrs_process_cases, {P5} of 256 patients x full mode (4 x 200 frames x 500 pts), brute 0.05 deg over +-90; "
+                f"whole patients dealt to the {world} rank(s), one call per rank",
+        "wall_s": dt, "evals": evals5, "value": evals5 / dt, "unit": UNIT, "units": units5,
+        "logs_sha256": sha(np.frombuffer("".join(shas[p] for p in sorted(shas)).encode(), dtype=np.uint8)),
+        "extrapolated_256_patients_s": dt * 256 / P5}
     if world > 1:   # every rank must have produced the same logs
         mine = [out[k]["logs_sha256"] for k in ("config2_from_array_singlepair", "config4_slice_from_array_full",
                                                   "config5_slice_process_cases")]

@@ -1059,6 +1059,35 @@ struct Searcher {
         check(mmrs_sweep_upload(ctx, &b, &o));
         return finish(U, grids, which);
     }
+    // Explicit per-unit grids (the chain's own re-search rounds): upload + run when `upload`, else regrid + run.
+    // single_frame: a handful of single-frame sweeps — with a communicator bound they are split along the CANDIDATE axis.
+    std::vector<mmrs_unit_result> run_grids(const SweepUnits& u, bool upload, int mode, const std::vector<mmrs_grid>& grids,
+                                            const std::vector<int32_t>& which, double tie_margin, bool single_frame) {
+        const size_t U = u.count();
+        if (U == 0) return {};
+        if (upload) {
+            mmrs_sweep_batch b{};
+            b.n_units = (int64_t)U;
+            b.test_xy = u.test.data();
+            b.test_off = u.toff.data();
+            b.ref_xy = u.ref.data();
+            b.ref_off = u.roff.data();
+            b.centre_xy = u.centre.data();
+            b.grids = grids.data();
+            b.n_grids = (int64_t)grids.size();
+            b.grid_of_unit = which.data();
+            b.mode = mode;
+            mmrs_sweep_opts o{};
+            o.tie_margin = tie_margin;
+            int32_t info[4] = {0, 1, 0, 0};
+            mmrs_ctx_comm_info(ctx, info);
+            o.partition = (single_frame && info[3] && info[1] > 1) ? 2 : (U > 1 ? 0 : -1);
+            check(mmrs_sweep_upload(ctx, &b, &o));
+        } else {
+            check(mmrs_sweep_regrid(ctx, grids.data(), (int64_t)grids.size(), which.data(), tie_margin));
+        }
+        return finish(U, grids, which);
+    }
     // Next window of the same search: the points stay on the device, only the grids change.
     std::vector<mmrs_unit_result> next(size_t U, double step_deg, double window_deg, double limes_deg,
                                        const std::vector<double>& centres, const std::vector<char>* skip,
@@ -1460,40 +1489,21 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
         }
     }
     tr.lap("within: batched sweeps");
-    // 3. replay the chain on the host (one thread per pullback); re-search uncertified frames on the chain's own points
-    parallel_for(G, [&](size_t g) {
+    // 3. replay the chain on the host (one thread per pullback). An uncertified frame is searched again on the chain's own
+    //    points — the reference's computation verbatim. The chains run in ROUNDS: every pullback advances to its next
+    //    uncertified frame (or its end), the pending frames of all pullbacks are searched in ONE batched sweep, and the
+    //    chains continue. The order of the sweeps is therefore a function of the data only: every rank of a multi-GPU run
+    //    issues the same batches, so they can be partitioned like any other (along the CANDIDATE axis when a communicator
+    //    is bound: a round is a handful of single-frame sweeps, mmrs_b200.h "axis 2").
+    struct Chain {
+        size_t i = 1;
+        double cumulative = 0.0, tx = 0.0, ty = 0.0, result = 0.0;
+        bool placed = false, have_result = false, done = false;
+    };
+    std::vector<Chain> chain(G);
+    std::vector<char> pending(G, 0);
+    auto post_steps = [&](size_t g) {
         Geometry& geo = *geoms[g];
-        double cumulative = 0.0;
-        for (size_t i = 1; i < geo.frames.size(); ++i) {
-            const size_t u = meta[g].first_unit + (i - 1);
-            const Frame& prev = geo.frames[i - 1];
-            Frame& cur = geo.frames[i];
-            if (cumulative != 0.0) cur.spin(cumulative, cur.c[0], cur.c[1]);
-            const double tx = prev.c[0] - cur.c[0], ty = prev.c[1] - cur.c[1];
-            cur.shift(tx, ty, 0.0);
-            double best = angle[u];
-            if (good_stages[u] < plan.n) {
-                SweepUnits one;
-                gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.test);
-                gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, one.ref);
-                one.close_unit(cur.c[0], cur.c[1]);
-                std::lock_guard<std::mutex> lk(S.gpu);
-                bool uploaded = false;
-                for (int s = good_stages[u]; s < plan.n; ++s) {
-                    std::vector<double> centres;
-                    if (s > 0) centres.push_back(best);
-                    auto r = uploaded ? S.next(1, plan.step[s], plan.window[s], P.range_deg, centres, nullptr, 0.0)
-                                      : S.first(one, 0, plan.step[s], plan.window[s], P.range_deg, centres, 0.0);
-                    uploaded = true;
-                    best = r[0].best_angle;
-                }
-                S.stats[3] += 1;
-            }
-            cur.spin(best, cur.c[0], cur.c[1]);
-            cumulative += best;
-            const double row[7] = {(double)cur.id, (double)prev.id, rad2deg(best), tx, ty, cur.c[0], cur.c[1]};
-            outs[g].logs.insert(outs[g].logs.end(), row, row + 7);
-        }
         // 4. post steps (align_within.rs:136-158)
         fill_holes(geo);
         if (meta[g].ref_idx >= geo.frames.size()) throw InputErr("index out of bounds: reference frame");
@@ -1513,7 +1523,88 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
         add_walls(geo, anomalous);
         if (P.smooth) smooth(geo);
         outs[g].anomalous = anomalous;
-    });
+        };
+    for (;;) {
+        parallel_for(G, [&](size_t g) {
+            Geometry& geo = *geoms[g];
+            Chain& ch = chain[g];
+            if (ch.done) return;
+            for (;;) {
+                if (ch.i >= geo.frames.size()) {
+                    post_steps(g);
+                    ch.done = true;
+                    return;
+                }
+                const size_t u = meta[g].first_unit + (ch.i - 1);
+                const Frame& prev = geo.frames[ch.i - 1];
+                Frame& cur = geo.frames[ch.i];
+                if (!ch.placed) {
+                    if (ch.cumulative != 0.0) cur.spin(ch.cumulative, cur.c[0], cur.c[1]);
+                    ch.tx = prev.c[0] - cur.c[0], ch.ty = prev.c[1] - cur.c[1];
+                    cur.shift(ch.tx, ch.ty, 0.0);
+                    ch.placed = true;
+                }
+                double best = angle[u];
+                if (good_stages[u] < plan.n) {
+                    if (!ch.have_result) {
+                        pending[g] = 1;   // searched by the batched sweep below, then the chain goes on
+                        return;
+                    }
+                    best = ch.result;
+                    ch.have_result = false;
+                }
+                cur.spin(best, cur.c[0], cur.c[1]);
+                ch.cumulative += best;
+                const double row[7] = {(double)cur.id, (double)prev.id, rad2deg(best), ch.tx, ch.ty, cur.c[0], cur.c[1]};
+                outs[g].logs.insert(outs[g].logs.end(), row, row + 7);
+                ch.i += 1;
+                ch.placed = false;
+            }
+        });
+        std::vector<size_t> todo;
+        for (size_t g = 0; g < G; ++g)
+            if (pending[g]) todo.push_back(g);
+        if (todo.empty()) break;
+        // the pending frames on the chain's own points (centre = the frame centroid), remaining stages of each search
+        SweepUnits batch;
+        std::vector<int> stage0(todo.size());
+        int rounds = 0;
+        for (size_t k = 0; k < todo.size(); ++k) {
+            const size_t g = todo[k];
+            const Geometry& geo = *geoms[g];
+            const Frame &cur = geo.frames[chain[g].i], &prev = geo.frames[chain[g].i - 1];
+            gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, batch.test);
+            gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, 0.0, 0.0, batch.ref);
+            batch.close_unit(cur.c[0], cur.c[1]);
+            stage0[k] = good_stages[meta[g].first_unit + (chain[g].i - 1)];
+            rounds = std::max(rounds, plan.n - stage0[k]);
+        }
+        std::vector<double> best(todo.size(), 0.0);
+        for (size_t k = 0; k < todo.size(); ++k) best[k] = angle[meta[todo[k]].first_unit + (chain[todo[k]].i - 1)];
+        for (int t = 0; t < rounds; ++t) {
+            // unit k runs stage stage0[k] + t of the plan (its own step / window / centre); finished searches sit out
+            std::vector<mmrs_grid> grids(todo.size());
+            std::vector<int32_t> which(todo.size());
+            for (size_t k = 0; k < todo.size(); ++k) {
+                which[k] = (int32_t)k;
+                const int sidx = stage0[k] + t;
+                grids[k] = mmrs_grid{};
+                grids[k].degenerate = 1;
+                if (sidx >= plan.n) continue;
+                S.check(mmrs_grid_from_reference_params(plan.step[sidx], plan.window[sidx], sidx > 0 ? 1 : 0, best[k],
+                                                        P.range_deg, &grids[k]));
+            }
+            auto r = S.run_grids(batch, t == 0, 0, grids, which, 0.0, /*single_frame=*/true);
+            for (size_t k = 0; k < todo.size(); ++k)
+                if (stage0[k] + t < plan.n) best[k] = r[k].best_angle;
+        }
+        for (size_t k = 0; k < todo.size(); ++k) {
+            chain[todo[k]].result = best[k];
+            chain[todo[k]].have_result = true;
+            pending[todo[k]] = 0;
+            S.stats[3] += 1;
+        }
+    }
     tr.lap("within: chain + post steps");
 }
 
