@@ -422,7 +422,7 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
             // shared memory of a CTA of this unit: mbarrier + key, the staging image, then per warp either the chunked
             // column minima (MULTI) or the tail pass's column seeds (exact tiling)
             size_t smem = 16 + (size_t)(a_elems + b_elems + nb_elems + t_elems) * 16;
-            if (d.n_chunks > 1) smem += (size_t)kWarpsPerCta * 2 * d.m_pairs * 4;
+            if (d.n_chunks > 1) smem += (size_t)kWarpsPerCta * ((2 * d.m_pairs + 3) & ~3) * 4;
             if (cc.tailp) smem += (size_t)kWarpsPerCta * 32 * (cc.ta + 1) * 4;
             static const bool force_big = std::getenv("MMRS_FORCE_BIG") && std::getenv("MMRS_FORCE_BIG")[0] == '1';
             const bool big = smem > (size_t)kMaxDynSmem || (force_big && d.n >= 64);

@@ -26,8 +26,8 @@
 
 namespace mmrs {
 
-#ifndef MMRS_J_UNROLL
-#define MMRS_J_UNROLL 0  // 0 = default (2)
+#ifndef MMRS_TRIP_UNROLL
+#define MMRS_TRIP_UNROLL 1   // trips (four reference points each) per loop iteration of the sweep's main loop
 #endif
 #ifndef MMRS_EXP_NOTAIL   // timing experiments only (wrong results): skip the tail pass / the seed loads of exact tiling
 #define MMRS_EXP_NOTAIL 0
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     constexpr int H = TA / 2;          // packed pairs of test points per lane
     constexpr bool TAIL = (TA & 1);    // plus one unpaired point when TA is odd
     constexpr int S = H + (TAIL ? 1 : 0);
-    constexpr int JU = (MMRS_J_UNROLL > 0) ? MMRS_J_UNROLL : 2;  // measured on B200: +2-3 % over 1, 4 is no better
+    constexpr int TU = MMRS_TRIP_UNROLL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw + 8);
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         if (g_pos >= g_hi) return;  // nothing for this CTA (uniform: before any barrier)
     }
     const WorkItem w = LIST ? WorkItem{0, 0, 0, 0} : work[blockIdx.x];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for ptxas: the B-block and seed pointers live in uniform registers
     if (threadIdx.x == 0) mbar_init(bar, 1);
     uint32_t phase = 0;
     const float INF = __int_as_float(0x7f800000);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     float4* sB = sA + a_elems;
     const float2* sNB = reinterpret_cast<const float2*>(sB + b_elems);
     const float4* sT = sB + b_elems + nb_elems;
-    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems + nb_elems + t_elems);  // MULTI: [warp][b_pts]; TAILP: [warp][32 SB]
+    unsigned* s_col = reinterpret_cast<unsigned*>(sB + b_elems + nb_elems + t_elems);  // MULTI: [warp][b_pts rounded up to 4]; TAILP: [warp][32 SB]
 
     if (threadIdx.x == 0) {
         *s_key = ~0ull;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     phase ^= 1u;
 
     unsigned long long best = ~0ull;
-    unsigned* my_col = s_col + wid * (TAILP ? 32 * SB : b_pts);
+    unsigned* my_col = s_col + wid * (TAILP ? 32 * SB : ((b_pts + 3) & ~3));   // 16-byte aligned rows: four seeds per LDS.128
     // LIST: squared give-up threshold from the unit's best exact distance so far (bits; 0xffffffff = none yet)
     unsigned give_up = 0xffffffffu;
     if (LIST) {
@@ -385,24 +385,11 @@ __global__ void __launch_bounds__(kThreads, 2)
                 row[2 * k] = INF;
                 row[2 * k + 1] = INF;
             }
-#pragma unroll JU
-            for (int j = 0; j < ud.m_pairs; ++j) {
-                const float4 B = sB[j];  // (bx0, by0, bx1, by1)
+            // One step = one float4 of the B block = two reference points against this lane's TA test points; c0 / c1 enter
+            // holding the seeds of the two column minima (INF, the tail pass's minima, or the previous chunks' minima).
+            auto step = [&](const float4 B, float c0, float c1, unsigned* col_out) {
                 const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y);
                 const uint64_t bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
-                float c0 = INF, c1 = INF;
-                if (TAILP && !MMRS_EXP_NOSEED) {  // the tail's column minima seed the accumulators (every lane: a minimum is idempotent)
-                    const uint2 seed = *reinterpret_cast<const uint2*>(&my_col[2 * j]);
-                    c0 = __uint_as_float(seed.x);
-                    c1 = __uint_as_float(seed.y);
-                }
-                if (MULTI && ch > 0 && lane == 0) {
-                    // Column minima of the previous chunks enter lane 0's accumulators up front: the load is
-                    // issued a whole iteration before its use and the warp REDUX below does the merge for free.
-                    const uint2 prev = *reinterpret_cast<const uint2*>(&my_col[2 * j]);
-                    c0 = __uint_as_float(prev.x);
-                    c1 = __uint_as_float(prev.y);
-                }
                 if (TAIL) {  // scalar FP32 ops for the unpaired point
                     const float ex0 = tx - B.x, ey0 = ty - B.y, ex1 = tx - B.z, ey1 = ty - B.w;
                     const float t0 = fmaf(ex0, ex0, ey0 * ey0), t1 = fmaf(ex1, ex1, ey1 * ey1);
@@ -411,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                     c1 = (MULTI || TAILP) ? fminf(c1, t1) : t1;
                 }
                 if (XF) {
-                    const float2 nb = sNB[j];
+                    const float2 nb = sNB[(int)(col_out - my_col) >> 1];
                     const uint64_t n0 = pk(nb.x, nb.x), n1 = pk(nb.y, nb.y);
 #pragma unroll
                     for (int k = 0; k < H; ++k) {
@@ -446,19 +433,49 @@ __global__ void __launch_bounds__(kThreads, 2)
                         c1 = min3(c1, d01, d11);
                     }
                 }
-                unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
-                unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
+                const unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
+                const unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
                 if (!MULTI || ch == ud.n_chunks - 1) {
                     colmax = max(colmax, max(r0, r1));  // all test points seen: these are the column minima
-                    // LIST: a column minimum above the unit's best exact distance (+ window) already proves that this
-                    // candidate cannot win: stop, and keep the proven lower bound (uniform across the warp)
-                    if (LIST && colmax > give_up) {
-                        gave_up = true;
-                        break;
-                    }
                 } else if (lane == 0) {
-                    *reinterpret_cast<uint2*>(&my_col[2 * j]) = make_uint2(r0, r1);
+                    *reinterpret_cast<uint2*>(col_out) = make_uint2(r0, r1);
                 }
+            };
+            // The B block is walked two float4 (four reference points) per trip with running pointers: one LDS.128 brings
+            // the four seeds, and the addresses cost two pointer increments instead of an index computation per array.
+            const bool seeded = (TAILP && !MMRS_EXP_NOSEED) || (MULTI && ch > 0);   // MULTI: lane 0 alone carries the seeds
+            const float4* pB = sB;
+            unsigned* pC = my_col;
+            const float4* const pB_end2 = sB + (ud.m_pairs & ~1);
+#pragma unroll TU
+            for (; pB != pB_end2; pB += 2, pC += 4) {
+                const float4 B0 = pB[0], B1 = pB[1];
+                float s0 = INF, s1 = INF, s2 = INF, s3 = INF;
+                if (seeded && (TAILP || lane == 0)) {
+                    const uint4 sd = *reinterpret_cast<const uint4*>(pC);
+                    s0 = __uint_as_float(sd.x), s1 = __uint_as_float(sd.y), s2 = __uint_as_float(sd.z), s3 = __uint_as_float(sd.w);
+                }
+                step(B0, s0, s1, pC);
+                // LIST: a column minimum above the unit's best exact distance (+ window) already proves that this
+                // candidate cannot win: stop, and keep the proven lower bound (uniform across the warp)
+                if (LIST && colmax > give_up) {
+                    gave_up = true;
+                    break;
+                }
+                step(B1, s2, s3, pC + 2);
+                if (LIST && colmax > give_up) {
+                    gave_up = true;
+                    break;
+                }
+            }
+            if ((ud.m_pairs & 1) && !(LIST && gave_up)) {   // the odd last float4
+                float s0 = INF, s1 = INF;
+                if (seeded && (TAILP || lane == 0)) {
+                    const uint2 sd = *reinterpret_cast<const uint2*>(pC);
+                    s0 = __uint_as_float(sd.x), s1 = __uint_as_float(sd.y);
+                }
+                step(*pB, s0, s1, pC);
+                if (LIST && colmax > give_up) gave_up = true;
             }
             if (LIST && gave_up) break;  // the row minima are incomplete: only the column bound counts
             if (XF) {   // row minima of r -> squared distances: + |a|^2 (the odd scalar slot is already a distance)
