@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cuda/std/type_traits>
+
 #include "mmrs_internal.hpp"
 
 namespace mmrs {
@@ -387,7 +389,8 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
             // One step = one float4 of the B block = two reference points against this lane's TA test points; c0 / c1 enter
             // holding the seeds of the two column minima (INF, the tail pass's minima, or the previous chunks' minima).
-            auto step = [&](const float4 B, float c0, float c1, unsigned* col_out) {
+            auto step = [&](auto last_tag, const float4 B, float c0, float c1, unsigned* col_out) {
+                constexpr bool LASTC = decltype(last_tag)::value;   // all test points seen after this chunk
                 const uint64_t bx0 = pk(B.x, B.x), by0 = pk(B.y, B.y);
                 const uint64_t bx1 = pk(B.z, B.z), by1 = pk(B.w, B.w);
                 if (TAIL) {  // scalar FP32 ops for the unpaired point
@@ -435,47 +438,64 @@ __global__ void __launch_bounds__(kThreads, 2)
                 }
                 const unsigned r0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
                 const unsigned r1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
-                if (!MULTI || ch == ud.n_chunks - 1) {
-                    colmax = max(colmax, max(r0, r1));  // all test points seen: these are the column minima
+                if (LASTC) {
+                    colmax = max(colmax, max(r0, r1));  // these are the column minima
                 } else if (lane == 0) {
                     *reinterpret_cast<uint2*>(col_out) = make_uint2(r0, r1);
                 }
             };
             // The B block is walked two float4 (four reference points) per trip with running pointers: one LDS.128 brings
             // the four seeds, and the addresses cost two pointer increments instead of an index computation per array.
-            const bool seeded = (TAILP && !MMRS_EXP_NOSEED) || (MULTI && ch > 0);   // MULTI: lane 0 alone carries the seeds
-            const float4* pB = sB;
-            unsigned* pC = my_col;
-            const float4* const pB_end2 = sB + (ud.m_pairs & ~1);
+            // Specialised on (last chunk, seeded) so that a chunked unit's loop carries no per-step branches.
+            auto walk = [&](auto last_tag, auto seeded_tag) {
+                constexpr bool SEEDED = decltype(seeded_tag)::value;   // MULTI: lane 0 alone carries the seeds
+                const float4* pB = sB;
+                unsigned* pC = my_col;
+                const float4* const pB_end2 = sB + (ud.m_pairs & ~1);
 #pragma unroll TU
-            for (; pB != pB_end2; pB += 2, pC += 4) {
-                const float4 B0 = pB[0], B1 = pB[1];
-                float s0 = INF, s1 = INF, s2 = INF, s3 = INF;
-                if (seeded && (TAILP || lane == 0)) {
-                    const uint4 sd = *reinterpret_cast<const uint4*>(pC);
-                    s0 = __uint_as_float(sd.x), s1 = __uint_as_float(sd.y), s2 = __uint_as_float(sd.z), s3 = __uint_as_float(sd.w);
+                for (; pB != pB_end2; pB += 2, pC += 4) {
+                    const float4 B0 = pB[0], B1 = pB[1];
+                    float s0 = INF, s1 = INF, s2 = INF, s3 = INF;
+                    if (SEEDED && (TAILP || lane == 0)) {
+                        const uint4 sd = *reinterpret_cast<const uint4*>(pC);
+                        s0 = __uint_as_float(sd.x), s1 = __uint_as_float(sd.y), s2 = __uint_as_float(sd.z), s3 = __uint_as_float(sd.w);
+                    }
+                    step(last_tag, B0, s0, s1, pC);
+                    // LIST: a column minimum above the unit's best exact distance (+ window) already proves that this
+                    // candidate cannot win: stop, and keep the proven lower bound (uniform across the warp)
+                    if (LIST && colmax > give_up) {
+                        gave_up = true;
+                        break;
+                    }
+                    step(last_tag, B1, s2, s3, pC + 2);
+                    if (LIST && colmax > give_up) {
+                        gave_up = true;
+                        break;
+                    }
                 }
-                step(B0, s0, s1, pC);
-                // LIST: a column minimum above the unit's best exact distance (+ window) already proves that this
-                // candidate cannot win: stop, and keep the proven lower bound (uniform across the warp)
-                if (LIST && colmax > give_up) {
-                    gave_up = true;
-                    break;
+                if ((ud.m_pairs & 1) && !(LIST && gave_up)) {   // the odd last float4
+                    float s0 = INF, s1 = INF;
+                    if (SEEDED && (TAILP || lane == 0)) {
+                        const uint2 sd = *reinterpret_cast<const uint2*>(pC);
+                        s0 = __uint_as_float(sd.x), s1 = __uint_as_float(sd.y);
+                    }
+                    step(last_tag, *pB, s0, s1, pC);
+                    if (LIST && colmax > give_up) gave_up = true;
                 }
-                step(B1, s2, s3, pC + 2);
-                if (LIST && colmax > give_up) {
-                    gave_up = true;
-                    break;
-                }
-            }
-            if ((ud.m_pairs & 1) && !(LIST && gave_up)) {   // the odd last float4
-                float s0 = INF, s1 = INF;
-                if (seeded && (TAILP || lane == 0)) {
-                    const uint2 sd = *reinterpret_cast<const uint2*>(pC);
-                    s0 = __uint_as_float(sd.x), s1 = __uint_as_float(sd.y);
-                }
-                step(*pB, s0, s1, pC);
-                if (LIST && colmax > give_up) gave_up = true;
+            };
+            using T_ = cuda::std::true_type;
+            using F_ = cuda::std::false_type;
+            if (!MULTI) {
+                if (TAILP && !MMRS_EXP_NOSEED) walk(T_{}, T_{});
+                else walk(T_{}, F_{});
+            } else if (ud.n_chunks == 1) {
+                walk(T_{}, F_{});
+            } else if (ch == 0) {
+                walk(F_{}, F_{});
+            } else if (ch < ud.n_chunks - 1) {
+                walk(F_{}, T_{});
+            } else {
+                walk(T_{}, T_{});
             }
             if (LIST && gave_up) break;  // the row minima are incomplete: only the column bound counts
             if (XF) {   // row minima of r -> squared distances: + |a|^2 (the odd scalar slot is already a distance)
@@ -546,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     constexpr int TA = kBigTA, H = TA / 2;
     __shared__ __align__(16) float4 sB[kBigBlock / 2];
     __shared__ unsigned s_col[kWarpsPerCta][kBigBlock];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for ptxas
     const float INF = __int_as_float(0x7f800000);
     float* my_rows = row_scratch + ((long long)blockIdx.x * kWarpsPerCta + wid) * scratch_per_warp;
     unsigned* my_col = s_col[wid];
@@ -729,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     const UnitDesc ud = lb_units[w.unit];
     const int a_elems = 16 * RS, b_elems = ud.m_pairs;   // 32 RS rows x 8 B
     float4* sB = sA + a_elems;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for ptxas
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         const uint32_t bytes = (uint32_t)(a_elems + b_elems) * 16u;

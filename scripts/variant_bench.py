@@ -12,7 +12,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     qb.run(ctx, 80, 520, 0.01, 180.0)
     qb.run(ctx, 80, 510, 0.01, 180.0)
     if os.environ.get("MMRS_VARIANT_FULL"):
-        qb.run(ctx, 4, 2020, 0.05, 180.0)
+        qb.run(ctx, 16, 2020, 0.05, 180.0)
 else:
     libs = [ROOT / "multimoda-rs_b200" / "libmmrs_b200.so"] + sorted((ROOT / "multimoda-rs_b200" / "variants").glob("libmmrs_*.so"))
     for lib in libs:
