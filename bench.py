@@ -197,6 +197,15 @@ def run_reference(args):
 
 
 # ---- our arm --------------------------------------------------------------------------------------------
+_T0 = time.perf_counter()
+
+
+def progress(rank, msg):
+    """Where the run is, on stderr (rank 0): a stuck N-rank run must say which leg it is in."""
+    if rank == 0:
+        print(f"[bench +{time.perf_counter() - _T0:6.1f} s] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -258,6 +267,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    progress(rank, f"workload built: {U} units x {ncand} candidates")
     # ---- value: batch resident in HBM ------------------------------------------------------------------
     ctx.sweep_upload(txy, toff, rxy, roff, cen, [grid], mode=0, prefilter=1, prune=-1)   # the dense FP32 sweep
     plan = ctx.plan()
@@ -304,6 +314,7 @@ def main():
                                            and np.array_equal(g["best_dist"], res["best_dist"]))
     ok_partition = check["all_ranks_identical"] and check["equals_1gpu_golden"] is not False
 
+    progress(rank, f"value leg done: {value:.4g} evals/s")
     # ---- e2e: C ABI call with host buffers (pinned), H2D + kernels + D2H every step ------------------------
     pin = [torch.from_numpy(a).pin_memory() for a in (txy, rxy)]
     h_t, h_r = pin[0].numpy(), pin[1].numpy()
@@ -323,25 +334,6 @@ def main():
     ok_partition = ok_partition and bool(np.array_equal(res_e["best_idx"], res["best_idx"]))
     h2d = txy.nbytes + rxy.nbytes + toff.nbytes + roff.nbytes + cen.nbytes + ncand * 17 + U * 96
     d2h = U * 32
-
-    # ---- candidate-axis partition (axis 2), checked in the same run: 72 000-candidate units split `world` ways must
-    # equal the unpartitioned (1-GPU) result, ties included ---------------------------------------------------------
-    angle = None
-    if world > 1:
-        angle = angle_axis_check(ctx, nat, world, dist)
-        ok_partition = ok_partition and angle["equal_to_unpartitioned"] and angle["all_ranks_identical"]
-
-    # ---- full-mode wall times through the public entry points (all ranks take part) --------------------------------
-    full_mode = None
-    if not args.no_api:
-        full_mode = optional("full_mode", lambda: full_mode_legs(ctx, nat, world, rank, dist, barrier))
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        if not ok_partition:
-            raise SystemExit(3)
-        return
 
     # ---- roofline of the dominant kernel (k_sweep) ------------------------------------------------------------
     peak, peak_src = peaks()
@@ -375,6 +367,79 @@ def main():
                 "note": "frac counts the reference's arithmetic (10 N M + 6 N per evaluation, SURVEY §8d); the kernel computes "
                         "each pair distance once for both directed passes, so it EXECUTES about half of that: frac_executed"}
 
+    def head_line():
+        return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": base_config(U, ncand, n, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "call": "mmrs_sweep_batched (host buffers in, host results out); every rank uploads the whole batch"},
+                "e2e_api": None,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None, "clocks": clk,
+                "partition_check": check, "angle_axis_check": None, "full_mode": None,
+                "tc_prefilter": None, "pruned": None}
+
+    # ---- the legs reported beside the headline. They run under a watchdog: whatever happens in them (a collective that
+    # never completes included), rank 0 still prints the line with the headline numbers measured above, every rank leaves,
+    # and the exit code only reflects the partition check of the headline.
+    state = {"angle": None, "full_mode": None, "emitted": False, "ok": ok_partition}
+    lock = threading.Lock()
+
+    def emit(extra):
+        with lock:
+            if state["emitted"]:
+                return
+            state["emitted"] = True
+            if rank == 0:
+                line = head_line()
+                line.update({"angle_axis_check": state["angle"], "full_mode": state["full_mode"]})
+                line.update(extra)
+                line["e2e_api"] = (state["full_mode"] or {}).get("config2_from_array_singlepair") if isinstance(state["full_mode"], dict) else None
+                sys.stdout.flush()
+                os.dup2(saved_stdout, 1)
+                print(json.dumps(line), flush=True)
+
+    def bail():
+        import faulthandler
+
+        print(f"bench.py: rank {rank}: the reported-beside legs exceeded {deadline:.0f} s; printing the headline without them",
+              file=sys.stderr, flush=True)
+        faulthandler.dump_traceback(file=sys.stderr)
+        if state["full_mode"] is None:
+            state["full_mode"] = {}
+        state["full_mode"]["error"] = f"exceeded the {deadline:.0f} s budget of the reported-beside legs"
+        emit({"cpu_baseline": None, "tc_prefilter": None, "pruned": None})
+        sys.stderr.flush()
+        os._exit(0 if state["ok"] else 3)
+
+    deadline = float(os.environ.get("MMRS_BENCH_LEG_DEADLINE_S", "200"))
+    watchdog = threading.Timer(deadline, bail)
+    watchdog.daemon = True
+    watchdog.start()
+
+    # ---- candidate-axis partition (axis 2), checked in the same run: 72 000-candidate units split `world` ways must
+    # equal the unpartitioned (1-GPU) result, ties included ---------------------------------------------------------
+    if world > 1:
+        progress(rank, "candidate-axis partition check")
+        state["angle"] = optional("angle_axis_check", lambda: angle_axis_check(ctx, nat, world, dist))
+        state["ok"] = state["ok"] and bool(state["angle"].get("equal_to_unpartitioned")) and bool(state["angle"].get("all_ranks_identical"))
+
+    # ---- full-mode wall times through the public entry points (all ranks take part) --------------------------------
+    if not args.no_api:
+        progress(rank, "full-mode legs")
+        state["full_mode"] = {}   # filled leg by leg: what was measured before a failure or the deadline is kept
+        err = optional("full_mode", lambda: full_mode_legs(ctx, nat, world, rank, dist, barrier, state["full_mode"]))
+        if isinstance(err, dict) and "error" in err:
+            state["full_mode"]["error"] = err["error"]
+    progress(rank, "full-mode legs done")
+
+    if rank != 0:
+        watchdog.cancel()
+        if world > 1:
+            dist.destroy_process_group()
+        if not state["ok"]:
+            raise SystemExit(3)
+        return
+
     cpu = None
 
     def cpu_leg():
@@ -399,22 +464,12 @@ def main():
         pruned = optional("pruned", lambda: pruned_leg(ctx, flush, txy, toff, rxy, roff, cen, grid, n, ncand, res,
                                                        float(np.mean(dev_ms))))
 
-    e2e_api = full_mode.get("config2_from_array_singlepair") if isinstance(full_mode, dict) else None
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": base_config(U, ncand, n, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "call": "mmrs_sweep_batched (host buffers in, host results out); every rank uploads the whole batch"},
-            "e2e_api": e2e_api,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "partition_check": check, "angle_axis_check": angle, "full_mode": full_mode,
-            "tc_prefilter": tcp, "pruned": pruned}
-    sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
-    print(json.dumps(line), flush=True)
+    progress(rank, "opt-in tier legs done")
+    watchdog.cancel()
+    emit({"cpu_baseline": cpu, "tc_prefilter": tcp, "pruned": pruned})
     if world > 1:
         dist.destroy_process_group()
-    if not ok_partition:
+    if not state["ok"]:
         print("bench.py: partitioned results differ between ranks or from the 1-GPU golden", file=sys.stderr)
         raise SystemExit(3)
 
@@ -473,7 +528,7 @@ def pullback_rows(seed, n_frames, n_points):
     return a, np.array([n_frames - 1, last[1] + 0.1, last[2], last[3]])
 
 
-def full_mode_legs(ctx, nat, world, rank, dist, barrier):
+def full_mode_legs(ctx, nat, world, rank, dist, barrier, out):
     """Wall time (host clock, barrier + device synchronise on both sides, best of the repetitions) of the public entry
     points on BASELINE's other configurations. With N > 1 every rank makes the same call; the library partitions the
     batched sweeps of the call across the ranks (frame pairs of one case / patients of a cohort)."""
@@ -482,7 +537,6 @@ def full_mode_legs(ctx, nat, world, rank, dist, barrier):
     from tests import golden_io as gio
 
     P._ctx = ctx   # the public entry points run on the bench's context (and its communicator)
-    out = {}
 
     def timed(fn, reps=3):
         best = None
@@ -517,6 +571,7 @@ def full_mode_legs(ctx, nat, world, rank, dist, barrier):
     c1["note"] = ("from_file_full(examples ivus_rest, ivus_stress), +-90 deg, write_obj=False, postprocessing=False; published: "
                   "Xeon Gold 6234, 16 threads (docs/benchmark.rst:36-40)")
     out["config1_from_file_full"] = c1
+    progress(rank, "full mode: config 1 done")
 
     # config 2 through the public API: one pullback pair (pair 0 of the bench workload) -> e2e_api
     ins2 = [mm.numpy_to_inputdata(*pullback_rows(SEED + k, N_FRAMES, N_POINTS), k == 0, label="dia" if k == 0 else "sys")
@@ -530,6 +585,7 @@ def full_mode_legs(ctx, nat, world, rank, dist, barrier):
         "wall_s": dt, "evals": st["evals"], "value": st["evals"] / dt, "unit": UNIT, "units": st["units"],
         "chain_resolved_units": st["chain_resolved"], "logs_sha256": logs_sha(r[1])}
 
+    progress(rank, "full mode: config 2 done")
     # config 4 slice: full mode, OCT-resolution contours, 0.005 deg brute force (72 000 candidates, N = M = 2 020)
     F4 = int(os.environ.get("MMRS_BENCH_CFG4_FRAMES", "26"))
     ins4 = [mm.numpy_to_inputdata(*pullback_rows(SEED + 40 + k, F4, 2000), k % 2 == 0, label=f"phase{k}") for k in range(4)]
@@ -542,6 +598,7 @@ def full_mode_legs(ctx, nat, world, rank, dist, barrier):
         "chain_resolved_units": st["chain_resolved"], "logs_sha256": logs_sha(r[4]),
         "extrapolated_full_config4_s": dt * (4 * 999) / max(4 * (F4 - 1), 1)}
 
+    progress(rank, "full mode: config 4 slice done")
     # config 5 slice: a cohort of full-mode patients (200 frames x 500 pts, brute 0.05 deg over +-90). Patients are
     # independent cases: with N > 1 whole patients are dealt to the ranks (rank r takes patients r, r + N, ...), each rank
     # runs ONE mmrs_process_cases call on its share with the partition of the sweeps switched off, and the per-frame logs
@@ -577,7 +634,8 @@ def full_mode_legs(ctx, nat, world, rank, dist, barrier):
         box = [None] * world
         dist.all_gather_object(box, mine)
         out["all_ranks_identical"] = all(b == box[0] for b in box)
-    return out
+    progress(rank, "full mode: config 5 slice done")
+    return None
 
 
 # ---- opt-in tiers --------------------------------------------------------------------------------------------------

@@ -1081,7 +1081,9 @@ struct Searcher {
             o.tie_margin = tie_margin;
             int32_t info[4] = {0, 1, 0, 0};
             mmrs_ctx_comm_info(ctx, info);
-            o.partition = (single_frame && info[3] && info[1] > 1) ? 2 : (U > 1 ? 0 : -1);
+            // info[2] = the context's axis: 0 = the caller switched the partition off (ranks working on DIFFERENT cases, e.g.
+            // a cohort dealt patient-wise): then no rank may enter a collective here — the other ranks are not in this call
+            o.partition = info[2] == 0 ? -1 : (single_frame && info[3] && info[1] > 1) ? 2 : (U > 1 ? 0 : -1);
             check(mmrs_sweep_upload(ctx, &b, &o));
         } else {
             check(mmrs_sweep_regrid(ctx, grids.data(), (int64_t)grids.size(), which.data(), tie_margin));
