@@ -345,6 +345,11 @@ int mmrs_align_centerline(mmrs_ctx* ctx, int32_t method, const double* centerlin
  *          rank), the global leftmost f64 arg-min is taken and the tie counts are summed. For single-frame sweeps.
  * With a communicator bound (mmrs_ctx_comm_init) the collectives are NCCL calls on device buffers on the context's
  * stream, between the kernels of a run. mmrs_ctx_set_shard binds a host callback instead (axis 1 only).
+ * The context's default (axis 1 with `partition` left 0 in the opts) is a policy decided from the batch shape alone,
+ * identically on every rank: whole units where they balance; candidate sub-ranges (axis 2, communicator bound, every
+ * unit >= 64 candidates per rank) where a few large units cannot be dealt evenly (block cost > 1.25 x the mean: the
+ * inter-pullback stages); NO partition (no collective, every rank sweeps the batch) below 2e9 pair evaluations.
+ * An explicit `partition` of 1, 2 or -1 in the opts overrides the policy.
  *
  * mmrs_comm_unique_id: rank 0 creates the rendezvous token (ncclGetUniqueId) and hands it to the other ranks by any
  * means (MPI, torch.distributed, a file); mmrs_ctx_comm_init is collective (ncclCommInitRank on the context's device).

@@ -1015,10 +1015,9 @@ struct Searcher {
                 check(mmrs_grid_from_reference_params(step_deg, window_deg, 1, centres[i], limes_deg, &grids[i]));
         }
     }
-    // Multi-GPU: the sweep layer partitions every batch of more than one unit across the ranks of the context and
-    // merges the results (mmrs_ctx_comm_init / mmrs_ctx_set_shard); every rank must therefore issue the same batched
-    // sweeps in the same order. A one-unit batch (the chain's own re-search of a tie set) is never partitioned, so it
-    // may be issued by one rank alone.
+    // Multi-GPU: the sweep layer partitions the batches across the ranks of the context and merges the results
+    // (mmrs_ctx_comm_init / mmrs_ctx_set_shard); every rank must therefore issue the same batched sweeps in the same
+    // order (the chain's re-search rounds included: they are a function of the data only).
     std::vector<mmrs_unit_result> finish(size_t U, const std::vector<mmrs_grid>& grids,
                                          const std::vector<int32_t>& which) {
         std::vector<mmrs_unit_result> out(U);
@@ -1055,7 +1054,7 @@ struct Searcher {
         b.mode = mode;
         mmrs_sweep_opts o{};
         o.tie_margin = tie_margin;
-        o.partition = U > 1 ? 0 : -1;
+        o.partition = 0;   // the context's policy (mmrs_b200.h): units, candidate sub-ranges, or none for a tiny batch
         check(mmrs_sweep_upload(ctx, &b, &o));
         return finish(U, grids, which);
     }
@@ -1083,7 +1082,7 @@ struct Searcher {
             mmrs_ctx_comm_info(ctx, info);
             // info[2] = the context's axis: 0 = the caller switched the partition off (ranks working on DIFFERENT cases, e.g.
             // a cohort dealt patient-wise): then no rank may enter a collective here — the other ranks are not in this call
-            o.partition = info[2] == 0 ? -1 : (single_frame && info[3] && info[1] > 1) ? 2 : (U > 1 ? 0 : -1);
+            o.partition = info[2] == 0 ? -1 : 0;   // else the context's policy
             check(mmrs_sweep_upload(ctx, &b, &o));
         } else {
             check(mmrs_sweep_regrid(ctx, grids.data(), (int64_t)grids.size(), which.data(), tie_margin));

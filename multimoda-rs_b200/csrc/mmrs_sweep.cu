@@ -596,6 +596,30 @@ static int apply_grids(mmrs_ctx* ctx, const mmrs_grid* grids, int64_t n_grids, c
         const int world = ctx->shard_world, rank = ctx->shard_rank;
         int axis = ctx->opt_partition == 0 ? ctx->part_axis : ctx->opt_partition;
         if (world <= 1 || (!ctx->comm && !ctx->exchange) || axis < 1 || axis > 2) axis = 0;
+        if (axis == 1 && ctx->opt_partition == 0) {
+            // The context's default axis is a POLICY, decided from the shape of the batch alone (so every rank decides
+            // alike): whole units where they balance; candidate sub-ranges where a handful of large units cannot be
+            // dealt evenly (the inter-pullback stages: 2 units, 72 000 candidates each, would keep 2 of 8 GPUs busy);
+            // no partition at all where the whole batch is cheaper than the collective that would merge it.
+            double total = 0.0, biggest = 0.0;
+            long long min_cand = (1ll << 62);
+            for (int64_t u = 0; u < U; ++u) {
+                const UnitDesc& d = units[u];
+                if (d.flags) continue;
+                const double c = (double)d.n * d.m * d.n_cand;
+                total += c;
+                biggest = std::max(biggest, c);
+                min_cand = std::min<long long>(min_cand, d.n_cand);
+            }
+            constexpr double kTinyBatch = 2.0e9;   // pair evaluations: ~0.3 ms of one B200, a few NCCL latencies
+            if (total < kTinyBatch) {
+                axis = 0;
+            } else if (ctx->comm && min_cand >= 64ll * world) {
+                // best unit partition possible: no block can be smaller than the largest unit
+                const double block = std::max(total / world, biggest);
+                if (block > 1.25 * total / world) axis = 2;
+            }
+        }
         if (axis == 2 && !ctx->comm)
             return set_err(ctx, MMRS_ERR_STATE, "the candidate-axis partition needs a communicator (mmrs_ctx_comm_init)");
         ctx->part_active = axis;
