@@ -186,9 +186,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": base_config(398 * N_PAIRS, ncand, n, 1) | {"parallelism": f"{cores} host threads (CPU)",
-                                                                  "l2": "n/a (CPU)", "recheck": "n/a (f64 throughout)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            # the SAME config object as our arm prints for this N (the workload both arms are quoted on); how the CPU arm
+            # runs it — host threads, the bounded sample — is in cpu_baseline
+            "config": base_config(398 * N_PAIRS, ncand, n, max(args.gpus, 1)),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "parallelism": f"{cores} host threads (CPU), f64 throughout"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "CPU oracle = C++ f64 restatement of the reference's rayon path (threads over candidate angles, "

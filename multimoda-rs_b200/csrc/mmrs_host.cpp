@@ -29,6 +29,10 @@
 #include <cctype>
 #include <charconv>
 #include <exception>
+#include <condition_variable>
+#include <deque>
+#include <type_traits>
+#include <future>
 #include <mutex>
 #include <thread>
 #include <chrono>
@@ -91,6 +95,90 @@ inline size_t host_thread_budget() {
     }();
     return budget;
 }
+// A persistent pool instead of a thread per call: the small clinical cases (config 1: 14 ms per call) issue dozens of
+// parallel_for over a few hundred microseconds of work each, and spawning + joining up to 16 threads per call cost more
+// than the work. The SUBMITTER always works on its own job and only then waits for the helpers that joined it, so nested
+// calls (pullbacks -> frames) and concurrent submitters (process_cases_pipelined) cannot dead-lock; the pool is leaked on
+// purpose (no static-destruction order to get wrong inside a Python process), and after a fork() a job simply finds no
+// helpers and runs on its submitter.
+class HostPool {
+  public:
+    struct Job {
+        void (*call)(void*, size_t) = nullptr;
+        void* fn = nullptr;
+        size_t n = 0;
+        std::atomic<size_t> next{0};
+        int wanted = 0;   // helpers that may still join (guarded by the pool mutex)
+        int active = 0;   // helpers inside the job (guarded by the pool mutex)
+        std::exception_ptr err;
+        std::mutex err_mu;
+    };
+    static HostPool& get() {
+        static HostPool* pool = new HostPool(host_thread_budget() > 1 ? host_thread_budget() - 1 : 0);
+        return *pool;
+    }
+    static void work(Job& j) {
+        for (;;) {
+            const size_t i = j.next.fetch_add(1);
+            if (i >= j.n) return;
+            try {
+                j.call(j.fn, i);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(j.err_mu);
+                if (!j.err) j.err = std::current_exception();
+                j.next.store(j.n);
+                return;
+            }
+        }
+    }
+    void run(Job& j, int helpers) {
+        if (helpers > 0 && !workers_.empty()) {
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                j.wanted = std::min<int>(helpers, (int)workers_.size());
+                open_.push_back(&j);
+            }
+            if (j.wanted == 1) cv_.notify_one();
+            else cv_.notify_all();
+        }
+        work(j);
+        if (helpers > 0 && !workers_.empty()) {
+            std::unique_lock<std::mutex> lk(mu_);
+            for (auto it = open_.begin(); it != open_.end(); ++it)
+                if (*it == &j) {
+                    open_.erase(it);
+                    break;
+                }
+            j.wanted = 0;
+            done_.wait(lk, [&] { return j.active == 0; });
+        }
+        if (j.err) std::rethrow_exception(j.err);
+    }
+
+  private:
+    explicit HostPool(size_t n) {
+        for (size_t t = 0; t < n; ++t) workers_.emplace_back([this] { loop(); });
+        for (auto& w : workers_) w.detach();
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [&] { return !open_.empty(); });
+            Job* j = open_.front();
+            if (--j->wanted <= 0) open_.pop_front();
+            ++j->active;
+            lk.unlock();
+            work(*j);
+            lk.lock();
+            if (--j->active == 0) done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<Job*> open_;
+    std::vector<std::thread> workers_;
+};
+
 template <class F>
 void parallel_for(size_t n, F&& f, size_t max_threads = ~(size_t)0) {
     const size_t nt = std::min(max_threads, std::min<size_t>(n, host_thread_budget()));
@@ -98,27 +186,12 @@ void parallel_for(size_t n, F&& f, size_t max_threads = ~(size_t)0) {
         for (size_t i = 0; i < n; ++i) f(i);
         return;
     }
-    std::atomic<size_t> next{0};
-    std::exception_ptr err;
-    std::mutex mu;
-    std::vector<std::thread> pool;
-    for (size_t t = 0; t < nt; ++t)
-        pool.emplace_back([&] {
-            for (;;) {
-                const size_t i = next.fetch_add(1);
-                if (i >= n) return;
-                try {
-                    f(i);
-                } catch (...) {
-                    std::lock_guard<std::mutex> lk(mu);
-                    if (!err) err = std::current_exception();
-                    next.store(n);
-                    return;
-                }
-            }
-        });
-    for (auto& th : pool) th.join();
-    if (err) std::rethrow_exception(err);
+    using Fn = std::remove_reference_t<F>;
+    HostPool::Job job;
+    job.call = [](void* p, size_t i) { (*static_cast<Fn*>(p))(i); };
+    job.fn = const_cast<void*>(static_cast<const void*>(&f));
+    job.n = n;
+    HostPool::get().run(job, (int)nt - 1);
 }
 
 inline double rad2deg(double r) { return r * (180.0 / kPi); }
@@ -1984,15 +2057,16 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
             for (int k = 0; k < n_in; ++k) anomalous = anomalous || w[c * n_in + k].anomalous;
             pending.push_back(Out{c * n_out + slot, a, b, true, anomalous});
         };
-        auto flush = [&] {
-            parallel_for(pending.size(), [&](size_t i) {
-                Out& o = pending[i];
+        auto finish_outputs = [&](std::vector<Out>& batch) {
+            parallel_for(batch.size(), [&](size_t i) {
+                Out& o = batch[i];
                 if (o.pair && params->postprocessing) postprocess_pair(o.a, o.b, 0.03, o.anomalous);
                 out_blobs[o.slot] = encode_malloc(o.a, &out_lens[o.slot]);
                 if (o.pair) out_blobs[o.slot + 1] = encode_malloc(o.b, &out_lens[o.slot + 1]);
             });
-            pending.clear();
+            batch.clear();
         };
+        auto flush = [&] { finish_outputs(pending); };
         if (mode == 1) {
             for (int64_t c = 0; c < n_cases; ++c) emit(c, 0, geo[c]);
             flush();
@@ -2012,9 +2086,16 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
             emit_pair(c, 0, g[0], g[1]);
             if (mode >= 3) emit_pair(c, 2, g[2], g[3]);  // pair CD holds C and D as they were BEFORE level 2 moves them
         }
-        flush();
-        tr.lap("postprocess + encode level 1");
-        if (mode != 4) return;
+        if (mode != 4) {
+            flush();
+            tr.lap("postprocess + encode level 1");
+            return;
+        }
+        // The level-1 outputs are clones: they are post-processed and encoded on a side thread while level 2 searches
+        // (std::async's future joins in its destructor, so an exception in level 2 still waits for the side thread).
+        std::vector<Out> level1;
+        level1.swap(pending);
+        auto side = std::async(std::launch::async, [&] { finish_outputs(level1); });
         // level 2: A<-C and B<-D on the already moved B and D (entry.rs:243-277)
         level.clear();
         for (int64_t c = 0; c < n_cases; ++c) {
@@ -2023,13 +2104,15 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
             level.push_back({g + 1, g + 3});
         }
         align_between_many(S, level, *params);
+        tr.lap("align_between_many level 2 (level-1 outputs encoded beside it)");
         for (int64_t c = 0; c < n_cases; ++c) {
             Geometry* g = &geo[c * n_in];
             emit_pair(c, 4, g[0], g[2]);
             emit_pair(c, 6, g[1], g[3]);
         }
         flush();
-        tr.lap("level 2 + encode");
+        side.get();
+        tr.lap("level 2 encode");
     });
     if (rc != MMRS_OK) {
         for (int64_t k = 0; k < n_cases * n_out; ++k) std::free(out_blobs[k]), out_blobs[k] = nullptr, out_lens[k] = 0;

@@ -102,6 +102,22 @@ class PyContour:
         self.kind = kind
         self._has_centroid = centroid is not None
 
+    @classmethod
+    def _from_blob_rows(cls, h, rows):
+        """Decoder fast path (PyGeometry.from_blob): `h` is the 12-value contour header as Python floats, `rows` a
+        C-contiguous float64 (n, 6) view of the blob. Same state as __init__ leaves, without re-validating."""
+        c = cls.__new__(cls)
+        c.id = int(h[1])
+        c.original_frame = int(h[2])
+        c._rows = rows
+        c._pts = None
+        c._has_centroid = bool(h[3])
+        c.centroid = (h[4], h[5], h[6]) if h[3] else (0.0, 0.0, 0.0)
+        c.aortic_thickness = h[8] if h[7] else None
+        c.pulmonary_thickness = h[10] if h[9] else None
+        c.kind = KIND_NAMES[int(h[0])]
+        return c
+
     # the reference's `points: Vec<PyContourPoint>` attribute
     @property
     def points(self):
@@ -607,28 +623,27 @@ class PyGeometry:
     @staticmethod
     def from_blob(blob, label="") -> "PyGeometry":
         b = np.asarray(blob, dtype=np.float64)
-        pos = 0
         nf = int(b[0])
         pos = 1
         frames = []
+        new_contour = PyContour._from_blob_rows
         for _ in range(nf):
-            fid, cx, cy, cz, has_ref = b[pos:pos + 5]
-            rp = b[pos + 5:pos + 11]
-            nc = int(b[pos + 11])
+            # one .tolist() per header: Python floats instead of a dozen numpy scalar reads
+            fid, cx, cy, cz, has_ref, r0, r1, r2, r3, r4, r5, nc = b[pos:pos + 12].tolist()
             pos += 12
             lumen, extras = None, {}
-            for k in range(nc):
-                h = b[pos:pos + 12]
+            for k in range(int(nc)):
+                h = b[pos:pos + 12].tolist()
                 n = int(h[11])
                 rows = b[pos + 12:pos + 12 + 6 * n].reshape(n, 6)   # a view: the blob stays alive through it
                 pos += 12 + 6 * n
-                c = PyContour(int(h[1]), int(h[2]), rows, tuple(h[4:7]) if h[3] else None,
-                              float(h[8]) if h[7] else None, float(h[10]) if h[9] else None, KIND_NAMES[int(h[0])])
+                c = new_contour(h, rows)
                 if k == 0:
                     lumen = c
                 else:
                     extras[c.kind] = c
-            frames.append(PyFrame(int(fid), (cx, cy, cz), lumen, extras, PyContourPoint(*rp) if has_ref else None))
+            frames.append(PyFrame(int(fid), (cx, cy, cz), lumen, extras,
+                                  PyContourPoint(r0, r1, r2, r3, r4, r5) if has_ref else None))
         if pos != len(b):
             raise ValueError("geometry blob not fully consumed")
         return PyGeometry(frames, label)

@@ -37,3 +37,6 @@ def test_reference_arm_prints_one_json_line():
     # the reference arm's config is the GPU arm's (the driver compares them): the bounded sample lives in cpu_baseline
     assert d["config"]["units"] == 398 * bench.N_PAIRS and d["config"]["candidates_per_unit"] == 36000
     assert "sample" not in d["config"] and "1 of the 3184" in d["cpu_baseline"]["sample"]
+    # ... key for key: both arms build it with the same function for the same N
+    assert d["config"] == bench.base_config(398 * bench.N_PAIRS, 36000, bench.N_POINTS + bench.N_CATH, 1)
+    assert "host threads" in d["cpu_baseline"]["parallelism"]

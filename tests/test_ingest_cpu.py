@@ -216,3 +216,52 @@ def test_array_ingest_row_orders_and_parallel_paths_match_oracle():
             want = ora.build_geometry_from_arrays(*args)
             assert np.array_equal(got, want), (nf, npnt, variant)
             assert np.array_equal(mm.PyGeometry.from_blob(got, "x").to_blob(), got)      # Python codec round trip
+
+
+def test_host_pool_concurrent_submitters_nested_jobs_and_errors(tmp_path):
+    """The library's persistent host pool (csrc/mmrs_host.cpp HostPool): several Python threads ingest big pullbacks at
+    once (each call runs frame-parallel jobs, nested under the caller), the blobs equal the single-threaded ones byte
+    for byte, an ingest error raised on a pool thread reaches its caller only, and the pool keeps working afterwards."""
+    import threading
+
+    rng = np.random.default_rng(5)
+
+    def pullback(nf, npnt, seed):
+        r = np.random.default_rng(seed)
+        rows = []
+        for f in range(nf):
+            ang = np.sort(r.uniform(0, 2 * np.pi, npnt))
+            rad = 2 + 0.3 * np.cos(2 * ang)
+            rows.append(np.column_stack([np.full(npnt, f), 4.5 + rad * np.cos(ang), 4.5 + rad * np.sin(ang),
+                                         np.full(npnt, 0.5 * (nf - 1 - f))]))
+        a = np.concatenate(rows)
+        return a[r.permutation(len(a))], np.array([nf - 1, 6.5, 4.5, 0.0])
+
+    cases = [pullback(120, 400, 100 + k) for k in range(6)] + [pullback(5, 20, 200 + k) for k in range(6)]
+    want = [np.array(nat.geometry_from_arrays(a, rp, diastole=True, label="p")) for a, rp in cases]
+    got, errors = [None] * len(cases), []
+
+    def worker(k):
+        try:
+            for _ in range(3):
+                got[k] = np.array(nat.geometry_from_arrays(*cases[k], diastole=True, label="p"))
+            if k % 4 == 0:   # an error inside a call: no lumen rows at all
+                try:
+                    nat.geometry_from_arrays(np.zeros((0, 4)), cases[k][1], diastole=True, label="bad")
+                    errors.append((k, "no error raised"))
+                except Exception:   # noqa: BLE001  (the message is pinned in test_ingest_errors_*)
+                    pass
+        except Exception as e:   # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not any(t.is_alive() for t in threads), "a pool job never completed"
+    assert not errors, errors
+    for w, g in zip(want, got):
+        assert g is not None and np.array_equal(w, g, equal_nan=True)
+    again = np.array(nat.geometry_from_arrays(*cases[0], diastole=True, label="p"))
+    assert np.array_equal(want[0], again, equal_nan=True)
