@@ -172,14 +172,20 @@ def from_file_single(input_path, labels=None, diastole=True, step_rotation_deg=0
                 export=export)
 
 
+_EXECUTOR = None
+
+
 def _parallel(fn, args):
     """The pullbacks of a case are ingested concurrently (the C side releases the GIL), like the reference's
-    crossbeam scope over its 4 geometries (binding/entry.rs:140-203)."""
+    crossbeam scope over its 4 geometries (binding/entry.rs:140-203). One executor for the life of the process: creating
+    and joining four threads per call costs as much as ingesting a small pullback."""
     if len(args) <= 1:
         return [fn(a) for a in args]
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=len(args)) as ex:
-        return list(ex.map(fn, args))
+    global _EXECUTOR
+    if _EXECUTOR is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _EXECUTOR = ThreadPoolExecutor(max_workers=8, thread_name_prefix="mmrs-ingest")
+    return list(_EXECUTOR.map(fn, args))
 
 
 def _from_inputs(mode, inputs, step, rng, sample_size, image_center, radius, n_points, smooth, bruteforce,
