@@ -87,3 +87,24 @@ def test_stage_plan_matches_reference_arms(step, rng):
     else:
         want = [(1.0, rng), (0.1, r5), (0.01, 0.1 if rng > 0.1 else rng), (step, r10)]
     assert plan == want
+
+
+def test_integration_md_binds_every_declared_symbol():
+    """INTEGRATION.md's Rust `extern "C"` block (what a maintainer pastes into the -sys crate) names every function
+    include/mmrs_b200.h declares, and its mmrs_sweep_opts carries every field of the C struct in order."""
+    import re
+
+    root = Path(__file__).resolve().parent.parent
+    header = (root / "include" / "mmrs_b200.h").read_text()
+    doc = (root / "INTEGRATION.md").read_text()
+    declared = set(re.findall(r"^(?:int|void|double|const char\*)\s+(mmrs_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 30
+    bound = set(re.findall(r"pub fn (mmrs_[a-z0-9_]+)\s*\(", doc))
+    assert declared <= bound, sorted(declared - bound)
+    end = header.index("} mmrs_sweep_opts;")
+    opts_c = header[header.rindex("typedef struct", 0, end):end]
+    opts_c = re.sub(r"/\*.*?\*/", "", opts_c, flags=re.S)
+    fields_c = re.findall(r"(?:double|int32_t|int64_t|float)\s+([a-z0-9_]+);", opts_c)
+    opts_rs = re.search(r"pub struct mmrs_sweep_opts \{(.*?)\}", doc, flags=re.S).group(1)
+    fields_rs = re.findall(r"pub ([a-z0-9_]+):", opts_rs)
+    assert fields_c == fields_rs, (fields_c, fields_rs)
