@@ -1320,22 +1320,32 @@ Contour aortic_wall(const Contour& c) {  // wall.rs:112-210
     }
     return o;
 }
+// Frames are independent in the post steps below; a pullback of a few hundred frames is walked frame-parallel on the host
+// pool (nested under the per-pullback job), a short one serially.
+constexpr size_t kFrameParallelMin = 32;
+template <class F>
+void for_frames(size_t n, F&& f) {
+    if (n >= kFrameParallelMin) parallel_for(n, f, 8);
+    else for (size_t i = 0; i < n; ++i) f(i);
+}
 void add_walls(Geometry& g, bool anomalous) {  // wall.rs:7-43
-    for (auto& f : g.frames) {
+    for_frames(g.frames.size(), [&](size_t i) {
+        Frame& f = g.frames[i];
         const Contour* eem = f.extra(kEem);
         const Contour& base = (anomalous || !eem) ? f.lumen : *eem;
-        if (base.has_at)
-            f.extras[kWall] = aortic_wall(base);
-        else {
+        if (base.has_at) {
+            Contour w = aortic_wall(base);   // built before the map is touched: `base` may live in f.extras
+            f.extras[kWall] = std::move(w);
+        } else {
             Contour w = pushed_out(base, 1.0, false, 0, 0);
             f.extras[kWall] = std::move(w);
         }
-    }
+    });
 }
 void smooth(Geometry& g) {  // Geometry::smooth_frames, geometry.rs:165-239
     const std::vector<Frame> old = g.frames;
     const size_t nf = old.size();
-    for (size_t i = 0; i < nf; ++i) {
+    for_frames(nf, [&](size_t i) {
         const Frame& prev = old[i == 0 ? i : i - 1];
         const Frame& next = old[i == nf - 1 ? i : i + 1];
         const size_t count = old[i].lumen.size();
@@ -1356,7 +1366,7 @@ void smooth(Geometry& g) {  // Geometry::smooth_frames, geometry.rs:165-239
             const Contour *c = old[i].extra(k), *p = prev.extra(k), *n = next.extra(k);
             if (c && p && n) g.frames[i].extras[k] = avg3(*c, *p, *n);
         }
-    }
+    });
 }
 
 // =============================================================================
@@ -1474,10 +1484,11 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
         const bool anomalous = elliptic_ratio(rf.lumen) > 2.0 || rf.lumen.has_at || rf.lumen.has_pt;
         const double extra = ref_point_to_right(rf, anomalous);
         if (extra != 0.0)  // Geometry::rotate_geometry, geometry.rs:241-250
-            for (auto& f : geo.frames) {
+            for_frames(geo.frames.size(), [&](size_t i) {
+                Frame& f = geo.frames[i];
                 f.spin(extra, f.c[0], f.c[1]);
                 f.sort_points();
-            }
+            });
         if (anomalous)  // assign_aortic, :319-331
             for (auto& f : geo.frames) {
                 const size_t len = f.lumen.size();

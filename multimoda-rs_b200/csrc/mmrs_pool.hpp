@@ -46,7 +46,8 @@ class HostPool {
         std::atomic<size_t> next{0};
         int wanted = 0;   // helpers that may still join (guarded by the pool mutex)
         int active = 0;   // helpers inside the job (guarded by the pool mutex)
-        std::exception_ptr err;
+        std::exception_ptr err;   // of the LOWEST failing index: what a serial loop would have thrown first
+        size_t err_index = ~(size_t)0;
         std::mutex err_mu;
     };
     static HostPool& get() {
@@ -60,8 +61,11 @@ class HostPool {
             try {
                 j.call(j.fn, i);
             } catch (...) {
+                // Indices are handed out in increasing order, so every index below a failing one has been claimed and
+                // runs to its end: keeping the exception of the lowest failing index reproduces the serial loop's error
+                // (the reference reports the first bad frame). No new indices are handed out after a failure.
                 std::lock_guard<std::mutex> lk(j.err_mu);
-                if (!j.err) j.err = std::current_exception();
+                if (i < j.err_index) j.err_index = i, j.err = std::current_exception();
                 j.next.store(j.n);
                 return;
             }
