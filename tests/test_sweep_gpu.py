@@ -359,6 +359,19 @@ def test_mixed_size_classes_in_one_batch(ctx):
         assert (pr[k] == res[k]).all(), k
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_chunked_units_with_odd_reference_counts(ctx, mode):
+    """The main loop walks four reference points per trip and closes with an odd float4; chunked units keep their
+    column minima in a per-warp shared-memory row whose stride is rounded up to 16 bytes. Reference counts of every
+    residue mod 4 (and odd), against chunked (N > 576), padded and exact-tiling test sets."""
+    rng = np.random.default_rng(31 + mode)
+    sizes = [(700, 601), (1301, 1203), (1154, 1150), (640, 77), (900, 3), (2021, 2017), (577, 578), (96, 5), (520, 2)]
+    tests, refs, cents, txy, toff, rxy, roff = make_units(rng, sizes)
+    g = nat.make_grid(0.5, 20.0)
+    res = ctx.sweep_batched(txy, toff, rxy, roff, cents, [g], mode=mode, keep_dist32=True)
+    check_against_oracle(ctx, tests, refs, cents, res, 0.5, 20.0, mode)
+
+
 # ---- non-finite coordinates (process_utils.rs:108, :112) -------------------------------------------------
 def test_non_finite_points_take_no_part(ctx):
     """A NaN distance never passes `d2 < min_sq` and a non-finite row minimum is skipped (process_utils.rs:104-114), so
