@@ -365,6 +365,9 @@ def main():
                 "kernel_share_of_step": k1 / float(np.mean(dev_ms)),
                 "peak_source": f"148 SM x 128 FP32 lanes x 2 x {peak_src} (no FP32 figure in MEASURED_PEAKS.json)",
                 "ffma_probe_tflops": probe, "frac_of_ffma_probe": achieved / probe,
+                # north star: "plus HBM GB/s for the point streams" — DRAM traffic of the launch over its duration (the
+                # staging images are read once per CTA and mostly hit L2; dist32 stays in L2): HBM is idle on this path
+                "hbm_gbps": (traffic / (k1 * 1e-3) / 1e9) if traffic else None,
                 "algorithmic_flops_per_eval": F, "executed_flops_per_eval": exec_flops,
                 "note": "frac counts the reference's arithmetic (10 N M + 6 N per evaluation, SURVEY §8d); the kernel computes "
                         "each pair distance once for both directed passes, so it EXECUTES about half of that: frac_executed"}

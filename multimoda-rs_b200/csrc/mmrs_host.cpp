@@ -50,6 +50,7 @@
 #include <string>
 #include <vector>
 
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 
@@ -395,6 +396,20 @@ double* write_frame(double* w, const Frame& f) {
     for (auto& kv : f.extras) w = write_contour(w, kv.second);
     return w;
 }
+// Result blobs are fresh memory, so writing them is first-touch bound (a 40 MB geometry = 10 000 page faults). Large
+// blobs are therefore 2 MB-aligned and marked for transparent huge pages where the kernel offers them (madvise is a hint:
+// without THP this is a plain allocation); the caller still releases them with free() / mmrs_free.
+void* blob_alloc(size_t bytes) {
+    constexpr size_t kHuge = 2u << 20;
+    if (bytes >= 4 * kHuge) {
+        void* p = nullptr;
+        if (posix_memalign(&p, kHuge, (bytes + kHuge - 1) / kHuge * kHuge) == 0 && p) {
+            madvise(p, (bytes + kHuge - 1) / kHuge * kHuge, MADV_HUGEPAGE);
+            return p;
+        }
+    }
+    return std::malloc(bytes);
+}
 double* encode_malloc(const Geometry& g, int64_t* len_out) {
     const size_t nf = g.frames.size();
     std::vector<size_t> at(nf + 1);
@@ -405,7 +420,7 @@ double* encode_malloc(const Geometry& g, int64_t* len_out) {
         at[k + 1] = at[k] + n;
     }
     const size_t n = at[nf];
-    double* base = (double*)std::malloc(n * sizeof(double));
+    double* base = (double*)blob_alloc(n * sizeof(double));
     if (!base) throw std::bad_alloc();
     base[0] = (double)nf;
     if (n < kParallelBlobDoubles || nf < 2 * kBlobThreads) {
@@ -1505,7 +1520,6 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
             if (ch.done) return;
             for (;;) {
                 if (ch.i >= geo.frames.size()) {
-                    post_steps(g);
                     ch.done = true;
                     return;
                 }
@@ -1579,7 +1593,9 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
             S.stats[3] += 1;
         }
     }
-    tr.lap("within: chain + post steps");
+    tr.lap("within: chain replay");
+    parallel_for(G, [&](size_t g) { post_steps(g); });
+    tr.lap("within: post steps");
 }
 
 // =============================================================================
@@ -1942,27 +1958,35 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
             out_nlogs[k] = (int64_t)w[k].logs.size() / 7;
             if (out_anomalous) out_anomalous[k] = w[k].anomalous ? 1 : 0;
         }
-        // Outputs are clones taken at the moment the reference takes them (align_between.rs:91); they are
-        // post-processed (maybe_postprocess, entry.rs:56-69, with the case-wide anomalous flag, :279-289) and
-        // encoded in parallel at the end of each dependency level.
+        // Outputs are clones taken at the moment the reference takes them (align_between.rs:91) — except at the LAST
+        // dependency level of a mode, where nothing moves the geometries any more: those are post-processed and encoded in
+        // place (a 400-frame x 1 000-point geometry is 40 MB; cloning four of them cost as much as encoding them). They are
+        // post-processed (maybe_postprocess, entry.rs:56-69, with the case-wide anomalous flag, :279-289) and encoded in
+        // parallel at the end of each dependency level.
         struct Out {
             int64_t slot;
-            Geometry a, b;
+            Geometry a, b;                          // the clones (levels that are followed by another)
+            Geometry *pa = nullptr, *pb = nullptr;  // or the geometries themselves (last level)
             bool pair, anomalous;
         };
         std::vector<Out> pending;
-        auto emit = [&](int64_t c, int slot, const Geometry& g) { pending.push_back(Out{c * n_out + slot, g, Geometry{}, false, false}); };
-        auto emit_pair = [&](int64_t c, int slot, const Geometry& a, const Geometry& b) {
+        auto emit = [&](int64_t c, int slot, Geometry& g) {   // mode 1: its only level
+            pending.push_back(Out{c * n_out + slot, Geometry{}, Geometry{}, &g, nullptr, false, false});
+        };
+        auto emit_pair = [&](int64_t c, int slot, Geometry& a, Geometry& b, bool last_level) {
             bool anomalous = false;
             for (int k = 0; k < n_in; ++k) anomalous = anomalous || w[c * n_in + k].anomalous;
-            pending.push_back(Out{c * n_out + slot, a, b, true, anomalous});
+            if (last_level) pending.push_back(Out{c * n_out + slot, Geometry{}, Geometry{}, &a, &b, true, anomalous});
+            else pending.push_back(Out{c * n_out + slot, a, b, nullptr, nullptr, true, anomalous});
         };
         auto finish_outputs = [&](std::vector<Out>& batch) {
             parallel_for(batch.size(), [&](size_t i) {
                 Out& o = batch[i];
-                if (o.pair && params->postprocessing) postprocess_pair(o.a, o.b, 0.03, o.anomalous);
-                out_blobs[o.slot] = encode_malloc(o.a, &out_lens[o.slot]);
-                if (o.pair) out_blobs[o.slot + 1] = encode_malloc(o.b, &out_lens[o.slot + 1]);
+                Geometry& A = o.pa ? *o.pa : o.a;
+                Geometry& B = o.pb ? *o.pb : o.b;
+                if (o.pair && params->postprocessing) postprocess_pair(A, B, 0.03, o.anomalous);
+                out_blobs[o.slot] = encode_malloc(A, &out_lens[o.slot]);
+                if (o.pair) out_blobs[o.slot + 1] = encode_malloc(B, &out_lens[o.slot + 1]);
             });
             batch.clear();
         };
@@ -1983,8 +2007,8 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
         tr.lap("align_between_many level 1");
         for (int64_t c = 0; c < n_cases; ++c) {
             Geometry* g = &geo[c * n_in];
-            emit_pair(c, 0, g[0], g[1]);
-            if (mode >= 3) emit_pair(c, 2, g[2], g[3]);  // pair CD holds C and D as they were BEFORE level 2 moves them
+            emit_pair(c, 0, g[0], g[1], mode != 4);
+            if (mode >= 3) emit_pair(c, 2, g[2], g[3], mode != 4);  // pair CD holds C and D as they were BEFORE level 2 moves them
         }
         if (mode != 4) {
             flush();
@@ -2007,8 +2031,8 @@ extern "C" int mmrs_process_cases(mmrs_ctx* ctx, int32_t mode, int64_t n_cases, 
         tr.lap("align_between_many level 2 (level-1 outputs encoded beside it)");
         for (int64_t c = 0; c < n_cases; ++c) {
             Geometry* g = &geo[c * n_in];
-            emit_pair(c, 4, g[0], g[2]);
-            emit_pair(c, 6, g[1], g[3]);
+            emit_pair(c, 4, g[0], g[2], true);
+            emit_pair(c, 6, g[1], g[3], true);
         }
         flush();
         side.get();

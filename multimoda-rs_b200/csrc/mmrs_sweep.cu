@@ -479,7 +479,10 @@ static int upload_points(mmrs_ctx* ctx, const mmrs_sweep_batch* b_in) {
         }
         for (const auto& cl : ctx->classes) ok = ok && !cl.big;   // the list re-scoring kernel does not take K1b's units
         ctx->lb_R = biggest >= 1024 ? 128 : 32;  // rows per lower-bound pass: k_lb<1,8> or k_lb<4,2>
-        ctx->lb_shape_ok = ok && biggest > 0;
+        // the bound tier's staging images are only built for a batch that may use it (opts / context default / MMRS_PRUNE)
+        const char* prune_env = std::getenv("MMRS_PRUNE");
+        const bool may_prune = (prune_env && *prune_env) ? (*prune_env != '0') : ctx->opt_prune == 1;
+        ctx->lb_shape_ok = ok && biggest > 0 && may_prune;
         ctx->h_units_lb.assign(2 * (size_t)U, UnitDesc{});
         long long off = 0;
         size_t smem_lb = 0;
