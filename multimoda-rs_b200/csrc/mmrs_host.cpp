@@ -1358,28 +1358,36 @@ void add_walls(Geometry& g, bool anomalous) {  // wall.rs:7-43
     });
 }
 void smooth(Geometry& g) {  // Geometry::smooth_frames, geometry.rs:165-239
-    const std::vector<Frame> old = g.frames;
-    const size_t nf = old.size();
+    // Every smoothed contour is the OLD contour truncated to the frame's lumen count with x, y replaced by the 3-frame mean
+    // of the OLD values, so only the old x / y of the three kinds involved are saved (not a deep copy of the geometry) and
+    // the contours are rewritten in place, frame-parallel.
+    constexpr int kKinds[3] = {-1, (int)kEem, (int)kWall};   // -1 = the lumen
+    struct Saved {
+        std::vector<double> x, y;
+        bool present = false;
+    };
+    const size_t nf = g.frames.size();
+    std::vector<std::array<Saved, 3>> old(nf);
+    auto contour_of = [](Frame& f, int kind) -> Contour* { return kind < 0 ? &f.lumen : f.extra(kind); };
     for_frames(nf, [&](size_t i) {
-        const Frame& prev = old[i == 0 ? i : i - 1];
-        const Frame& next = old[i == nf - 1 ? i : i + 1];
-        const size_t count = old[i].lumen.size();
-        auto avg3 = [&](const Contour& cur, const Contour& p, const Contour& n) {
-            if (cur.size() < count || p.size() < count || n.size() < count)
+        for (int q = 0; q < 3; ++q)
+            if (Contour* c = contour_of(g.frames[i], kKinds[q])) old[i][q].x = c->x, old[i][q].y = c->y, old[i][q].present = true;
+    });
+    for_frames(nf, [&](size_t i) {
+        const size_t ip = i == 0 ? i : i - 1, in = i == nf - 1 ? i : i + 1;
+        const size_t count = old[i][0].x.size();
+        for (int q = 0; q < 3; ++q) {
+            const Saved &cur = old[i][q], &p = old[ip][q], &n = old[in][q];
+            if (!(cur.present && p.present && n.present)) continue;   // the lumen is always present
+            if (cur.x.size() < count || p.x.size() < count || n.x.size() < count)
                 throw InputErr("index out of bounds (smooth_frames)");
-            Contour o = cur;
+            Contour& o = *contour_of(g.frames[i], kKinds[q]);
             o.resize(count);
             for (size_t j = 0; j < count; ++j) {
                 o.x[j] = (p.x[j] + cur.x[j] + n.x[j]) / 3.0;
                 o.y[j] = (p.y[j] + cur.y[j] + n.y[j]) / 3.0;
             }
             o.centroid();
-            return o;
-        };
-        g.frames[i].lumen = avg3(old[i].lumen, prev.lumen, next.lumen);
-        for (int k : {(int)kEem, (int)kWall}) {
-            const Contour *c = old[i].extra(k), *p = prev.extra(k), *n = next.extra(k);
-            if (c && p && n) g.frames[i].extras[k] = avg3(*c, *p, *n);
         }
     });
 }
@@ -1417,39 +1425,66 @@ void align_within_many(Searcher& S, std::vector<Geometry*>& geoms, const mmrs_al
             meta[g].n_cath = as_usize(std::ceil((double)c->size() * ratio));
         }
     }
-    // 1. decoupled units from the ORIGINAL frames, each centred on its own frame centroid (built per pullback
-    //    in parallel, then concatenated in pullback order)
-    std::vector<SweepUnits> part(G);
-    parallel_for(G, [&](size_t g) {
-        const Geometry& geo = *geoms[g];
-        SweepUnits& u = part[g];
-        for (size_t i = 1; i < geo.frames.size(); ++i) {
-            const Frame &cur = geo.frames[i], &prev = geo.frames[i - 1];
-            gather_frame_sample(cur, sample, meta[g].use_cath, meta[g].n_cath, cur.c[0], cur.c[1], u.test);
-            gather_frame_sample(prev, sample, meta[g].use_cath, meta[g].n_cath, prev.c[0], prev.c[1], u.ref);
-            u.close_unit(0.0, 0.0);
-        }
-    });
-    SweepUnits units;
+    tr.lap("within: guards");
+    // 1. decoupled units from the ORIGINAL frames, each centred on its own frame centroid. Frame i of a pullback is the
+    //    test set of unit i and the reference set of unit i + 1 with the SAME centring, so every frame is sampled once
+    //    (frame-parallel over all pullbacks) and the two point arrays are assembled from those samples by block copies.
+    std::vector<size_t> frame0(G + 1, 0);   // index of a pullback's first frame in the flat list of frames
+    for (size_t g = 0; g < G; ++g) frame0[g + 1] = frame0[g] + geoms[g]->frames.size();
+    std::vector<std::vector<double>> fs(frame0[G]);
     {
-        size_t nt = 0, nr = 0, nu = 0;
-        for (auto& p : part) nt += p.test.size(), nr += p.ref.size(), nu += p.count();
-        units.test.reserve(nt);
-        units.ref.reserve(nr);
-        units.centre.reserve(2 * nu);
-        for (size_t g = 0; g < G; ++g) {
-            meta[g].first_unit = units.count();
-            const int64_t t0 = (int64_t)units.test.size() / 2, r0 = (int64_t)units.ref.size() / 2;
-            units.test.insert(units.test.end(), part[g].test.begin(), part[g].test.end());
-            units.ref.insert(units.ref.end(), part[g].ref.begin(), part[g].ref.end());
-            units.centre.insert(units.centre.end(), part[g].centre.begin(), part[g].centre.end());
-            for (size_t k = 1; k < part[g].toff.size(); ++k) {
-                units.toff.push_back(t0 + part[g].toff[k]);
-                units.roff.push_back(r0 + part[g].roff[k]);
-            }
-            part[g] = SweepUnits{};
+        std::vector<uint32_t> owner(frame0[G]);
+        for (size_t g = 0; g < G; ++g)
+            for (size_t k = frame0[g]; k < frame0[g + 1]; ++k) owner[k] = (uint32_t)g;
+        auto sample_frame = [&](size_t k) {
+            const size_t g = owner[k];
+            const Frame& f = geoms[g]->frames[k - frame0[g]];
+            fs[k].reserve(2 * (std::min(sample, f.lumen.size()) + meta[g].n_cath));
+            gather_frame_sample(f, sample, meta[g].use_cath, meta[g].n_cath, f.c[0], f.c[1], fs[k]);
+        };
+        if (fs.size() >= 64) parallel_for(fs.size(), sample_frame);
+        else for (size_t k = 0; k < fs.size(); ++k) sample_frame(k);
+    }
+    tr.lap("within: sample frames");
+    SweepUnits units;
+    // the two big point arrays live in the context between calls (warm pages); handed back when this function leaves
+    struct Lend {
+        SweepUnits& u;
+        mmrs_ctx* ctx;
+        Lend(SweepUnits& u_, mmrs_ctx* c) : u(u_), ctx(c) {
+            u.test.swap(ctx->host_units_test);
+            u.ref.swap(ctx->host_units_ref);
+            u.test.clear();
+            u.ref.clear();
+        }
+        ~Lend() {
+            u.test.swap(ctx->host_units_test);
+            u.ref.swap(ctx->host_units_ref);
+        }
+    } lend(units, S.ctx);
+    std::vector<size_t> unit_frame;   // flat frame index of each unit's test frame (its reference frame is the one before)
+    for (size_t g = 0; g < G; ++g) {
+        meta[g].first_unit = units.count();
+        for (size_t k = frame0[g] + 1; k < frame0[g + 1]; ++k) {
+            unit_frame.push_back(k);
+            units.toff.push_back(units.toff.back() + (int64_t)fs[k].size() / 2);
+            units.roff.push_back(units.roff.back() + (int64_t)fs[k - 1].size() / 2);
         }
     }
+    units.centre.assign(2 * unit_frame.size(), 0.0);
+    units.test.resize(2 * (size_t)units.toff.back());
+    units.ref.resize(2 * (size_t)units.roff.back());
+    {
+        auto place = [&](size_t u) {
+            const size_t k = unit_frame[u];
+            if (!fs[k].empty()) std::memcpy(units.test.data() + 2 * units.toff[u], fs[k].data(), fs[k].size() * sizeof(double));
+            if (!fs[k - 1].empty())
+                std::memcpy(units.ref.data() + 2 * units.roff[u], fs[k - 1].data(), fs[k - 1].size() * sizeof(double));
+        };
+        if (unit_frame.size() >= 64) parallel_for(unit_frame.size(), place, 8);
+        else for (size_t u = 0; u < unit_frame.size(); ++u) place(u);
+    }
+    fs.clear();
     const size_t U = units.count();
     tr.lap("within: build units");
     const Plan plan = make_plan(P.step_deg, P.range_deg, P.bruteforce != 0);

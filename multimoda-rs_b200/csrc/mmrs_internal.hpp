@@ -141,6 +141,9 @@ struct mmrs_ctx {
 
     // counters of the last mmrs_process_cases call
     int64_t stats[5] = {0, 0, 0, 0, 0};
+    // host staging of the intrapullback units, kept across calls: 26 MB of FRESH memory per call (config 3) is 6 500
+    // page faults, more than sampling the frames costs
+    std::vector<double> host_units_test, host_units_ref;
 
     void free_all();
 };
