@@ -1654,25 +1654,41 @@ void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>
     if (!N) return;
     const size_t sample = std::max<size_t>((size_t)std::max<int64_t>(P.sample_size, 0), 500);
     std::vector<std::array<double, 2>> pivot(N);
-    SweepUnits units;
-    for (size_t k = 0; k < N; ++k) {
+    // The pairs of one level move disjoint geometries (AB | CD, then AC | BD: only the second of a pair is written), so
+    // they are prepared side by side, each walking its frames on the host pool; the units are appended in pair order.
+    auto shift_frames = [](Geometry& g, double dx, double dy, double dz) {
+        for_frames(g.frames.size(), [&](size_t i) { g.frames[i].shift(dx, dy, dz); });
+    };
+    struct Prep {
+        std::vector<double> ref, test;
+        double cx = 0.0, cy = 0.0;
+    };
+    std::vector<Prep> prep(N);
+    parallel_for(N, [&](size_t k) {
         Geometry &a = *pairs[k].first, &b = *pairs[k].second;
         if (a.frames.empty() || b.frames.empty()) throw InputErr("index out of bounds: empty geometry");
         const size_t ia = a.ref_or_proximal(), ib = b.ref_or_proximal();
         if (ia >= a.frames.size() || ib >= b.frames.size()) throw InputErr("index out of bounds: reference frame");
         const Frame &fa = a.frames[ia], &fb = b.frames[ib];
         pivot[k] = {fa.c[0], fa.c[1]};
-        b.shift_all(fa.c[0] - fb.c[0], fa.c[1] - fb.c[1], fa.c[2] - fb.c[2]);
-        const size_t r0 = units.ref.size();
-        sample_cloud(a, sample, units.ref);
-        sample_cloud(b, sample, units.test);
+        shift_frames(b, fa.c[0] - fb.c[0], fa.c[1] - fb.c[1], fa.c[2] - fb.c[2]);
+        sample_cloud(a, sample, prep[k].ref);
+        sample_cloud(b, sample, prep[k].test);
         // calculate_global_centroid of the reference cloud, :260-271 (x then y, sequential sums)
         double sx = 0.0, sy = 0.0;
-        const size_t cnt = (units.ref.size() - r0) / 2;
-        for (size_t i = 0; i < cnt; ++i) sx += units.ref[r0 + 2 * i];
-        for (size_t i = 0; i < cnt; ++i) sy += units.ref[r0 + 2 * i + 1];
-        units.close_unit(cnt ? sx / (double)cnt : 0.0, cnt ? sy / (double)cnt : 0.0);
+        const size_t cnt = prep[k].ref.size() / 2;
+        for (size_t i = 0; i < cnt; ++i) sx += prep[k].ref[2 * i];
+        for (size_t i = 0; i < cnt; ++i) sy += prep[k].ref[2 * i + 1];
+        prep[k].cx = cnt ? sx / (double)cnt : 0.0;
+        prep[k].cy = cnt ? sy / (double)cnt : 0.0;
+    });
+    SweepUnits units;
+    for (size_t k = 0; k < N; ++k) {
+        units.ref.insert(units.ref.end(), prep[k].ref.begin(), prep[k].ref.end());
+        units.test.insert(units.test.end(), prep[k].test.begin(), prep[k].test.end());
+        units.close_unit(prep[k].cx, prep[k].cy);
     }
+    prep.clear();
     // there is no brute-force switch on this path (align_between.rs:219-257)
     const Plan plan = make_plan(P.step_deg, P.range_deg, false);
     std::vector<double> angle(N, 0.0);
@@ -1691,7 +1707,8 @@ void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>
             x = rx + cx;
             y = ry + cy;
         };
-        for (auto& f : b.frames) {
+        for_frames(b.frames.size(), [&](size_t fi) {
+            Frame& f = b.frames[fi];
             for (size_t i = 0; i < f.lumen.size(); ++i) rot(f.lumen.x[i], f.lumen.y[i]);
             rot(f.c[0], f.c[1]);
             for (auto& kv : f.extras) {
@@ -1699,9 +1716,10 @@ void align_between_many(Searcher& S, std::vector<std::pair<Geometry*, Geometry*>
                 if (kv.second.has_c) rot(kv.second.c[0], kv.second.c[1]);
             }
             if (f.has_ref) rot(f.ref.x, f.ref.y);
-        }
+        });
         const Frame &fa = a.frames.at(a.ref_or_proximal()), &fb = b.frames.at(b.ref_or_proximal());
-        b.shift_all(fa.c[0] - fb.c[0], fa.c[1] - fb.c[1], fa.c[2] - fb.c[2]);
+        const double dx = fa.c[0] - fb.c[0], dy = fa.c[1] - fb.c[1], dz = fa.c[2] - fb.c[2];   // by value: fb is shifted too
+        shift_frames(b, dx, dy, dz);
     });
 }
 
