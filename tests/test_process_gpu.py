@@ -192,6 +192,103 @@ def test_unit_sharding_across_two_gpus():
     assert '"config1_matches_golden": true' in r.stdout and '"config2_all_ranks_identical": true' in r.stdout
 
 
+class _ThreadAllReduce:
+    """An in-place all-reduce(SUM) over int64 arrays between THREADS of this process: the transport of
+    mmrs_ctx_set_shard (any all-reduce will do: NCCL, MPI, gloo — here a barrier and a sum), so that the unit partition
+    and its merge run on a 1-GPU box with one context per emulated rank."""
+
+    def __init__(self, world):
+        import threading
+
+        self.world, self.slots = world, [None] * world
+        self.barrier = threading.Barrier(world, timeout=120)
+        self.calls = [0] * world
+
+    def for_rank(self, rank):
+        def allreduce(arr):
+            self.calls[rank] += 1
+            self.slots[rank] = arr
+            self.barrier.wait()
+            total = np.sum([self.slots[r] for r in range(self.world)], axis=0)
+            self.barrier.wait()          # every rank has read every buffer
+            arr[:] = total
+            self.barrier.wait()          # every rank has written its own before the slots are reused
+        return allreduce
+
+
+def _run_ranks(world, body):
+    """body(rank, ctx) on `world` threads, each with its own context on cuda:0 sharded through _ThreadAllReduce."""
+    import threading
+
+    ar, out, errs = _ThreadAllReduce(world), [None] * world, []
+
+    def run(rank):
+        ctx = nat.Context(0)
+        try:
+            ctx.set_shard(rank, world, ar.for_rank(rank))
+            out[rank] = body(rank, ctx)
+        except Exception as e:  # noqa: BLE001
+            errs.append((rank, repr(e)))
+            ar.barrier.abort()
+        finally:
+            ctx.close()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(300)
+    assert not errs, errs
+    assert not any(t.is_alive() for t in ts)
+    return out, ar
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_unit_partition_with_a_host_transport_on_one_gpu(world):
+    """mmrs_ctx_set_shard: every emulated rank makes the same mmrs_process_cases call (config 1, brute force at 0.05 deg:
+    the 80-unit intrapullback batch is dealt to the ranks in cost-balanced blocks, the 32-byte results are merged by the
+    exchange; the inter-pullback batches are below the partition threshold and are swept by every rank). All ranks must
+    return the unpartitioned result bit for bit."""
+    pack = gio.inputs()
+    blobs = oracle_blobs(pack, FULL)
+    args = (4, blobs, 0.05, 90.0, 500, False, True)
+    want_out, want_logs, _ = nat.process_cases(mm.get_context(), *args)
+    got, ar = _run_ranks(world, lambda rank, ctx: nat.process_cases(ctx, *args))
+    for rank in range(world):
+        out, logs, _ = got[rank]
+        assert all(np.array_equal(a, b) for a, b in zip(logs, want_logs)), rank
+        assert all(np.array_equal(a, b) for a, b in zip(out, want_out)), rank
+    assert ar.calls[0] >= 1 and len(set(ar.calls)) == 1    # the ranks entered the exchange equally often
+
+
+def test_unit_partition_leaves_a_rank_without_units():
+    """Two units on three ranks (explicit unit axis): one rank owns nothing, launches nothing, and still ends up with both
+    results after the merge; a degenerate grid and an empty set keep their flags through the sum."""
+    rng = np.random.default_rng(41)
+    phi = np.linspace(0, 2 * np.pi, 520, endpoint=False)
+
+    def contour(rot):
+        r = 2.4 * (1 + 0.2 * np.cos(2 * phi) + 0.03 * np.cos(3 * phi + 0.4))
+        return np.stack([r * np.cos(phi + rot), r * np.sin(phi + rot)], 1) + rng.normal(0, 0.004, (520, 2))
+
+    tests = [contour(0.3), contour(-0.2), np.zeros((0, 2)), contour(0.1)]
+    refs = [contour(0.0), contour(0.05), contour(0.0), contour(0.0)]
+    toff = np.concatenate([[0], np.cumsum([len(t) for t in tests])])
+    roff = np.concatenate([[0], np.cumsum([len(r) for r in refs])])
+    grids = [nat.make_grid(0.05, 90.0), nat.make_grid(0.0, 10.0, center=0.25)]        # the second one is degenerate
+    gou = np.array([0, 0, 0, 1], dtype=np.int32)
+    args = (np.concatenate(tests), toff, np.concatenate(refs), roff, np.zeros((4, 2)), grids)
+    kw = dict(grid_of_unit=gou, mode=0, tie_margin=1e-9)
+    ctx0 = nat.Context(0)
+    want = ctx0.sweep_batched(*args, partition=-1, **kw)
+    ctx0.close()
+    got, ar = _run_ranks(3, lambda rank, ctx: ctx.sweep_batched(*args, partition=1, **kw))
+    for rank in range(3):
+        for f in ("best_idx", "best_angle", "best_dist", "best_dist_f32", "n_shortlist", "n_ties", "flags"):
+            assert np.array_equal(got[rank][f], want[f]), (rank, f)
+    assert ar.calls == [1, 1, 1]
+
+
 # ---- edge cases the reference handles on this path ---------------------------------------------------------
 def _cmp_single(blob, step, rng, sample, smooth, brute):
     ctx = mm.get_context()
