@@ -399,9 +399,15 @@ def main():
                 line.update({"angle_axis_check": state["angle"], "full_mode": state["full_mode"]})
                 line.update(extra)
                 line["e2e_api"] = (state["full_mode"] or {}).get("config2_from_array_singlepair") if isinstance(state["full_mode"], dict) else None
+                try:
+                    text = json.dumps(line)
+                except Exception as e:  # noqa: BLE001  (the watchdog may fire while a leg is still filling its dict)
+                    line["full_mode"] = {"error": f"not serialisable when the line was printed: {type(e).__name__}"}
+                    line["e2e_api"] = None
+                    text = json.dumps(line)
                 sys.stdout.flush()
                 os.dup2(saved_stdout, 1)
-                print(json.dumps(line), flush=True)
+                print(text, flush=True)
 
     def bail():
         import faulthandler

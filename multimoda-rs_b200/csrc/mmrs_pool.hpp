@@ -73,12 +73,13 @@ class HostPool {
     }
     void run(Job& j, int helpers) {
         if (helpers > 0 && !workers_.empty()) {
+            int wanted;
             {
                 std::lock_guard<std::mutex> lk(mu_);
-                j.wanted = std::min<int>(helpers, (int)workers_.size());
+                wanted = j.wanted = std::min<int>(helpers, (int)workers_.size());
                 open_.push_back(&j);
             }
-            if (j.wanted == 1) cv_.notify_one();
+            if (wanted == 1) cv_.notify_one();
             else cv_.notify_all();
         }
         work(j);
