@@ -3,7 +3,7 @@
 // The sweep path shards on independent work: whole units, or contiguous candidate sub-ranges of
 // every unit, are dealt to ranks and only the tiny per-unit results cross NVLink — an all-reduce(MIN, uint64) of the
 // packed (distance, index) keys when the candidate axis is split (the reduction of process_utils.rs:69-74: lowest
-// distance, ties -> lowest index), an all-gather / all-reduce(SUM) of the 40-byte per-unit results otherwise. The
+// distance, ties -> lowest index), an all-gather / all-reduce(SUM) of the 32-byte per-unit results otherwise. The
 // collectives run on the context's stream on DEVICE buffers, between the kernels of a run: no host staging, no extra
 // synchronisation.
 //

@@ -198,7 +198,7 @@ def init_comm(ctx, group=None, axis: int = 1):
 
 def enable_unit_sharding(ctx, group=None):
     """Shard the units of every batched sweep of `ctx` (one frame pair = one unit) across the ranks of `group`:
-    each rank sweeps its block on its own GPU; only 40 B per unit cross NVLink (one all-reduce per search stage)."""
+    each rank sweeps its block on its own GPU; only 32 B per unit cross NVLink (one all-reduce per search stage)."""
     import torch.distributed as dist
 
     ctx.set_shard(dist.get_rank(group), dist.get_world_size(group), make_exchange(group))
